@@ -1,0 +1,338 @@
+// capi.cu -- the device-pointer half of the C ABI (include/hexl_b200.h, part 1)
+// and the keyswitch plan.  Host-pointer API: ../host/src/runtime.cpp.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hexl_b200.h"
+#include "../host/inc/number_theory.h"
+#include "internal.h"
+#include "launch.h"
+
+namespace nt = hexl_b200::nt;
+
+namespace hexl_b200 {
+
+static thread_local std::string g_err = "";
+std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
+static std::atomic<int> g_ntt_variant{0};
+static std::atomic<int64_t> g_ks_workspace_mb{1024};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+
+static int ilog2_exact(uint64_t n) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1ull << l) < n) ++l;
+    return l;
+}
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const uint64_t* roots,
+                       const uint64_t* precon, const uint64_t* inv_roots,
+                       const uint64_t* precon_inv) {
+    hb::ModTab t;
+    t.q = q;
+    t.twoq = q << 1;
+    t.mu = nt::barrett_mu(q);
+    t.sc.inv_n = inv_n;
+    t.sc.inv_n_p = inv_n < q ? nt::shoup(inv_n, q) : 0;
+    t.sc.inv_n_w = inv_n_w;
+    t.sc.inv_n_w_p = inv_n_w < q ? nt::shoup(inv_n_w, q) : 0;
+    t.roots = roots;
+    t.precon = precon;
+    t.inv_roots = inv_roots;
+    t.precon_inv = precon_inv;
+    return t;
+}
+
+}  // namespace hexl_b200
+
+using namespace hexl_b200;
+
+// keyswitch plan ------------------------------------------------------------
+struct hexl_b200_ks_plan {
+    int device = 0;
+    uint64_t n = 0, D = 0, K = 0, R = 0;
+    hb::KsDev dev{};
+    uint64_t* d_tables = nullptr;   // K * 4 * n
+    uint64_t* d_keys = nullptr;     // D * 2 * K * n
+    uint64_t* d_small = nullptr;    // msf, msf_p
+    hb::ModTab* d_tabs = nullptr;
+    hb::Divisor* d_divs = nullptr;
+    // workspace (grown lazily, reused across calls; guarded by mu)
+    std::mutex mu;
+    uint64_t* ws = nullptr;
+    size_t ws_words = 0;
+};
+
+extern "C" {
+
+int hexl_b200_version(void) { return 100; }
+const char* hexl_b200_last_error(void) { return g_err.c_str(); }
+
+int hexl_b200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(HEXL_B200_ENODEV, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+int hexl_b200_set_option(const char* name, int64_t value) {
+    if (!name) return fail(HEXL_B200_EINVAL, "option name is NULL");
+    if (!strcmp(name, "ntt_variant")) {
+        if (value < 0 || value > 1) return fail(HEXL_B200_EINVAL, "ntt_variant must be 0 or 1");
+        g_ntt_variant = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_workspace_mb")) {
+        if (value < 16) return fail(HEXL_B200_EINVAL, "ks_workspace_mb must be >= 16");
+        g_ks_workspace_mb = value;
+        return 0;
+    }
+    return fail(HEXL_B200_EINVAL, "unknown option '%s'", name);
+}
+
+int hexl_b200_compute_twiddles(uint64_t n, uint64_t q, uint64_t* out4n, uint64_t* inv_n, uint64_t* inv_n_w) {
+    if (!out4n) return fail(HEXL_B200_EINVAL, "compute_twiddles: NULL output");
+    if (ilog2_exact(n) < 1 || n > (1u << 20)) return fail(HEXL_B200_EINVAL, "compute_twiddles: bad n");
+    if (q < 2 || q >> 62 || (q - 1) % (2 * n))
+        return fail(HEXL_B200_EINVAL, "compute_twiddles: modulus must be a prime = 1 mod 2n below 2^62");
+    nt::Tables t = nt::make_tables(n, q);
+    if (t.roots.size() != n || t.inv_n == 0)
+        return fail(HEXL_B200_EINVAL, "compute_twiddles: no primitive 2n-th root of unity mod %llu",
+                    (unsigned long long)q);
+    memcpy(out4n, t.roots.data(), n * 8);
+    memcpy(out4n + n, t.precon.data(), n * 8);
+    memcpy(out4n + 2 * n, t.inv_roots.data(), n * 8);
+    memcpy(out4n + 3 * n, t.precon_inv.data(), n * 8);
+    if (inv_n) *inv_n = t.inv_n;
+    if (inv_n_w) *inv_n_w = t.inv_n_w;
+    return 0;
+}
+
+int hexl_b200_get_stats(hexl_b200_stats* out) {
+    if (!out) return fail(HEXL_B200_EINVAL, "stats pointer is NULL");
+    out->kernel_launches = g_launches.load();
+    out->h2d_bytes = g_h2d.load();
+    out->d2h_bytes = g_d2h.load();
+    return 0;
+}
+int hexl_b200_reset_stats(void) {
+    g_launches = 0;
+    g_h2d = 0;
+    g_d2h = 0;
+    return 0;
+}
+
+int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64_t* d_precon,
+                      uint64_t q, uint64_t n, uint64_t batch, void* stream) {
+    const int logn = ilog2_exact(n);
+    if (logn < 0 || !hb::ntt_shape_supported((uint32_t)logn))
+        return fail(HEXL_B200_EINVAL, "ntt_fwd: n=%llu unsupported (power of two in [1024,16384])",
+                    (unsigned long long)n);
+    if (!d_operand || !d_roots || !d_precon) return fail(HEXL_B200_EINVAL, "ntt_fwd: NULL pointer");
+    if (!aligned16(d_operand)) return fail(HEXL_B200_EINVAL, "ntt_fwd: operand not 16-byte aligned");
+    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "ntt_fwd: modulus must be in [2, 2^62)");
+    hb::ModTab t = make_modtab(q, 0, 0, d_roots, d_precon, nullptr, nullptr);
+    cudaError_t e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, g_ntt_variant.load(),
+                                       (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd launch");
+    g_launches += batch ? 1 : 0;
+    return 0;
+}
+
+int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const uint64_t* d_precon_inv,
+                      uint64_t q, uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch,
+                      void* stream) {
+    const int logn = ilog2_exact(n);
+    if (logn < 0 || !hb::ntt_shape_supported((uint32_t)logn))
+        return fail(HEXL_B200_EINVAL, "ntt_inv: n=%llu unsupported (power of two in [1024,16384])",
+                    (unsigned long long)n);
+    if (!d_operand || !d_inv_roots || !d_precon_inv)
+        return fail(HEXL_B200_EINVAL, "ntt_inv: NULL pointer");
+    if (!aligned16(d_operand)) return fail(HEXL_B200_EINVAL, "ntt_inv: operand not 16-byte aligned");
+    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "ntt_inv: modulus must be in [2, 2^62)");
+    if (inv_n >= q || inv_n_w >= q)
+        return fail(HEXL_B200_EINVAL, "ntt_inv: inv_n / inv_n_w must be reduced mod q");
+    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, nullptr, d_inv_roots, d_precon_inv);
+    cudaError_t e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, g_ntt_variant.load(),
+                                       (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv launch");
+    g_launches += batch ? 1 : 0;
+    return 0;
+}
+
+int hexl_b200_dyadic_multiply(uint64_t* d_results, const uint64_t* d_op1, const uint64_t* d_op2,
+                              uint64_t n, const uint64_t* d_moduli, uint64_t n_moduli,
+                              uint64_t batch, int moduli_per_item, void* stream) {
+    if (!d_results || !d_op1 || !d_op2 || !d_moduli)
+        return fail(HEXL_B200_EINVAL, "dyadic_multiply: NULL pointer");
+    if (n == 0 || (n & 1) || n > (1u << 20))
+        return fail(HEXL_B200_EINVAL, "dyadic_multiply: n=%llu must be even and <= 2^20",
+                    (unsigned long long)n);
+    if (n_moduli == 0 || n_moduli > 4096)
+        return fail(HEXL_B200_EINVAL, "dyadic_multiply: n_moduli=%llu out of range",
+                    (unsigned long long)n_moduli);
+    if (!aligned16(d_results) || !aligned16(d_op1) || !aligned16(d_op2))
+        return fail(HEXL_B200_EINVAL, "dyadic_multiply: buffers must be 16-byte aligned");
+    cudaError_t e = hb::launch_dyadic(d_results, d_op1, d_op2, n, d_moduli, n_moduli, batch,
+                                      moduli_per_item, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dyadic_multiply launch");
+    g_launches += batch ? 1 : 0;
+    return 0;
+}
+
+int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, uint64_t K, uint64_t R,
+                             uint64_t C, const uint64_t* moduli, const uint64_t* const* keys,
+                             const uint64_t* msf, const uint64_t* twiddles) {
+    if (!out) return fail(HEXL_B200_EINVAL, "ks_plan_create: NULL plan pointer");
+    *out = nullptr;
+    const int logn = ilog2_exact(n);
+    // reference checks: host/src/keyswitch.cpp:23-34 (n in {1024..16384},
+    // key_component_count == 2, moduli in [2^16, 2^52]); the FPGA's
+    // key_modulus_size <= 7 limit is lifted (BASELINE config uses 8).
+    if (logn < 0 || !hb::ntt_shape_supported((uint32_t)logn))
+        return fail(HEXL_B200_EINVAL, "keyswitch: n=%llu unsupported", (unsigned long long)n);
+    if (C != 2) return fail(HEXL_B200_EINVAL, "keyswitch: key_component_count must be 2");
+    if (D == 0 || K < 2 || D + 1 > K || K > 64)
+        return fail(HEXL_B200_EINVAL, "keyswitch: need 1 <= decomp < key_modulus_size <= 64");
+    if (R != D + 1) return fail(HEXL_B200_EINVAL, "keyswitch: rns_modulus_size must be decomp+1");
+    if (!moduli || !keys || !msf) return fail(HEXL_B200_EINVAL, "keyswitch: NULL pointer");
+    for (uint64_t i = 0; i < K; ++i) {
+        if (moduli[i] < 2 || moduli[i] >> 61)
+            return fail(HEXL_B200_EINVAL, "keyswitch: modulus %llu out of range [2, 2^61)",
+                        (unsigned long long)moduli[i]);
+        if ((moduli[i] - 1) % (2 * n))
+            return fail(HEXL_B200_EINVAL, "keyswitch: modulus %llu is not 1 mod 2n",
+                        (unsigned long long)moduli[i]);
+    }
+    for (uint64_t j = 0; j < D; ++j)
+        if (!keys[j]) return fail(HEXL_B200_EINVAL, "keyswitch: k_switch_keys[%d] is NULL", (int)j);
+
+    auto* p = new hexl_b200_ks_plan;
+    cudaError_t e = cudaGetDevice(&p->device);
+    if (e != cudaSuccess) {
+        delete p;
+        return cuda_fail(e, "cudaGetDevice");
+    }
+    p->n = n; p->D = D; p->K = K; p->R = R;
+
+    std::vector<uint64_t> h_tables(K * 4 * n), h_small(2 * K);
+    std::vector<hb::ModTab> h_tabs(K);
+    std::vector<hb::Divisor> h_divs(K);
+    auto cleanup = [&](int rc) {
+        hexl_b200_ks_plan_destroy(p);
+        return rc;
+    };
+    if ((e = cudaMalloc(&p->d_tables, K * 4 * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc tables"));
+    if ((e = cudaMalloc(&p->d_keys, D * 2 * K * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc keys"));
+    if ((e = cudaMalloc(&p->d_small, 2 * K * 8))) return cleanup(cuda_fail(e, "cudaMalloc small"));
+    if ((e = cudaMalloc(&p->d_tabs, K * sizeof(hb::ModTab)))) return cleanup(cuda_fail(e, "cudaMalloc tabs"));
+    if ((e = cudaMalloc(&p->d_divs, K * sizeof(hb::Divisor)))) return cleanup(cuda_fail(e, "cudaMalloc divs"));
+
+    for (uint64_t i = 0; i < K; ++i) {
+        const uint64_t q = moduli[i];
+        nt::Tables t = twiddles ? nt::tables_from_keyswitch_block(n, q, twiddles + i * 4 * n)
+                                : nt::make_tables(n, q);
+        if (t.roots.size() != n || t.inv_n == 0)
+            return cleanup(fail(HEXL_B200_EINVAL, "keyswitch: no primitive 2n-th root mod %llu",
+                                (unsigned long long)q));
+        uint64_t* h = h_tables.data() + i * 4 * n;
+        memcpy(h, t.roots.data(), n * 8);
+        memcpy(h + n, t.precon.data(), n * 8);
+        memcpy(h + 2 * n, t.inv_roots.data(), n * 8);
+        memcpy(h + 3 * n, t.precon_inv.data(), n * 8);
+        uint64_t* d = p->d_tables + i * 4 * n;
+        h_tabs[i] = make_modtab(q, t.inv_n, t.inv_n_w, d, d + n, d + 2 * n, d + 3 * n);
+        h_divs[i] = hb::make_divisor(q);
+        h_small[i] = msf[i] % q;                       // host/src/fpga.cpp:1057-1061
+        h_small[K + i] = nt::shoup(h_small[i], q);
+    }
+    if ((e = cudaMemcpy(p->d_tables, h_tables.data(), K * 4 * n * 8, cudaMemcpyHostToDevice)))
+        return cleanup(cuda_fail(e, "upload tables"));
+    for (uint64_t j = 0; j < D; ++j)
+        if ((e = cudaMemcpy(p->d_keys + j * 2 * K * n, keys[j], 2 * K * n * 8, cudaMemcpyHostToDevice)))
+            return cleanup(cuda_fail(e, "upload keys"));
+    if ((e = cudaMemcpy(p->d_small, h_small.data(), 2 * K * 8, cudaMemcpyHostToDevice)))
+        return cleanup(cuda_fail(e, "upload msf"));
+    if ((e = cudaMemcpy(p->d_tabs, h_tabs.data(), K * sizeof(hb::ModTab), cudaMemcpyHostToDevice)))
+        return cleanup(cuda_fail(e, "upload tabs"));
+    if ((e = cudaMemcpy(p->d_divs, h_divs.data(), K * sizeof(hb::Divisor), cudaMemcpyHostToDevice)))
+        return cleanup(cuda_fail(e, "upload divisors"));
+    g_h2d += (K * 4 * n + D * 2 * K * n + 2 * K) * 8;
+
+    p->dev.logn = (uint32_t)logn;
+    p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
+    p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;
+    p->dev.msf = p->d_small; p->dev.msf_p = p->d_small + K;
+    *out = p;
+    return 0;
+}
+
+int hexl_b200_ks_plan_destroy(hexl_b200_ks_plan* p) {
+    if (!p) return 0;
+    cudaFree(p->d_tables); cudaFree(p->d_keys); cudaFree(p->d_small);
+    cudaFree(p->d_tabs); cudaFree(p->d_divs); cudaFree(p->ws);
+    delete p;
+    return 0;
+}
+
+int hexl_b200_keyswitch(hexl_b200_ks_plan* p, uint64_t* d_result, const uint64_t* d_t, uint64_t batch,
+                        void* stream) {
+    if (!p) return fail(HEXL_B200_EINVAL, "keyswitch: NULL plan");
+    if (batch == 0) return 0;
+    if (!d_result || !d_t) return fail(HEXL_B200_EINVAL, "keyswitch: NULL pointer");
+    if (!aligned16(d_result) || !aligned16(d_t))
+        return fail(HEXL_B200_EINVAL, "keyswitch: buffers must be 16-byte aligned");
+    const uint64_t n = p->n, D = p->D, R = p->R;
+    // scratch words per item: U (D*n) + V (R*D*n) + ACC (2*R*n)
+    const uint64_t per_item = (D + R * D + 2 * R) * n;
+    uint64_t chunk = ((uint64_t)g_ks_workspace_mb.load() << 20) / 8 / per_item;
+    if (chunk < 1) chunk = 1;
+    if (chunk > batch) chunk = batch;
+    if (chunk > 16384) chunk = 16384;
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->ws_words < chunk * per_item) {
+        // stream-ordered work may still use the old buffer
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "keyswitch: sync before workspace growth");
+        cudaFree(p->ws);
+        p->ws = nullptr; p->ws_words = 0;
+        if ((e = cudaMalloc(&p->ws, chunk * per_item * 8))) return cuda_fail(e, "keyswitch: workspace");
+        p->ws_words = chunk * per_item;
+    }
+    for (uint64_t off = 0; off < batch; off += chunk) {
+        const uint64_t items = batch - off < chunk ? batch - off : chunk;
+        uint64_t* U = p->ws;
+        uint64_t* V = U + items * D * n;
+        uint64_t* ACC = V + items * R * D * n;
+        cudaError_t e = hb::launch_ks_chunk(p->dev, d_result + off * 2 * D * n, d_t + off * D * n,
+                                            items, U, V, ACC, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "keyswitch launch");
+        g_launches += 5;
+    }
+    return 0;
+}
+
+}  // extern "C"

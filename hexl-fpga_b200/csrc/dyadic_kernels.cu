@@ -1,0 +1,104 @@
+// dyadic_kernels.cu -- ciphertext x ciphertext dyadic multiply (sm_100a).
+// Replaces device/dyadic_multiply.cpp:195-228 (+ MultMod, device/mod_ops.hpp:
+// 31-84).  Pure streaming kernel: 4 input words and 3 output words per
+// coefficient, 16-byte accesses, one CTA per slab of one (item, modulus).
+//
+//   res[m]      = x0*y0 mod q_m
+//   res[M+m]    = (x0*y1 mod q_m + x1*y0 mod q_m) mod q_m
+//   res[2M+m]   = x1*y1 mod q_m
+//
+// Any modulus >= 1 and unreduced operands are accepted, as the reference's
+// tests require (tests/test_dyadic_multiply.cpp:35-84).
+#include "launch.h"
+
+namespace hb {
+
+constexpr int kDyThreads = 256;
+constexpr int kDyCoeffPerThread = 2;   // one 16-byte access per array
+constexpr int kDySlab = 2048;          // coefficients per CTA
+
+__global__ void __launch_bounds__(kDyThreads)
+k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
+         const uint64_t* __restrict__ op2, uint32_t n, const uint64_t* __restrict__ moduli,
+         uint32_t M, int moduli_per_item, uint32_t slabs_per_poly) {
+    __shared__ Divisor s_dv;
+    // blockIdx.x = ((item * M) + m) * slabs_per_poly + slab
+    const uint64_t bid = blockIdx.x;
+    const uint32_t slab = (uint32_t)(bid % slabs_per_poly);
+    const uint64_t im = bid / slabs_per_poly;
+    const uint32_t m = (uint32_t)(im % M);
+    const uint64_t item = im / M;
+    if (threadIdx.x == 0)
+        s_dv = make_divisor(moduli[(moduli_per_item ? item * M : 0) + m]);
+    __syncthreads();
+    const Divisor dv = s_dv;
+
+    const uint64_t in_item = item * 2ull * M * n;
+    const uint64_t out_item = item * 3ull * M * n;
+    const uint64_t* x0p = op1 + in_item + (uint64_t)m * n;
+    const uint64_t* x1p = op1 + in_item + (uint64_t)(M + m) * n;
+    const uint64_t* y0p = op2 + in_item + (uint64_t)m * n;
+    const uint64_t* y1p = op2 + in_item + (uint64_t)(M + m) * n;
+    uint64_t* r0p = res + out_item + (uint64_t)m * n;
+    uint64_t* r1p = res + out_item + (uint64_t)(M + m) * n;
+    uint64_t* r2p = res + out_item + (uint64_t)(2 * M + m) * n;
+
+    const uint32_t begin = slab * kDySlab;
+    const uint32_t end = min(begin + kDySlab, n);
+#pragma unroll 2
+    for (uint32_t i = begin + threadIdx.x * kDyCoeffPerThread; i < end;
+         i += kDyThreads * kDyCoeffPerThread) {
+        uint64_t x0[2], x1[2], y0[2], y1[2], r0[2], r1[2], r2[2];
+        if (i + 1 < end) {
+            ld2(x0p + i, x0[0], x0[1]);
+            ld2(x1p + i, x1[0], x1[1]);
+            ld2(y0p + i, y0[0], y0[1]);
+            ld2(y1p + i, y1[0], y1[1]);
+        } else {  // odd tail
+            x0[0] = x0p[i]; x1[0] = x1p[i]; y0[0] = y0p[i]; y1[0] = y1p[i];
+            x0[1] = x1[1] = y0[1] = y1[1] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t a0 = mod64(x0[k], dv), a1 = mod64(x1[k], dv);
+            const uint64_t b0 = mod64(y0[k], dv), b1 = mod64(y1[k], dv);
+            r0[k] = mulmod_reduced(a0, b0, dv);
+            const uint64_t c = mulmod_reduced(a0, b1, dv);
+            const uint64_t d = mulmod_reduced(a1, b0, dv);
+            uint64_t s = c + d;                      // c,d < q <= 2^64-1: detect wrap
+            if (s < c || s >= dv.q) s -= dv.q;
+            r1[k] = s;
+            r2[k] = mulmod_reduced(a1, b1, dv);
+        }
+        if (i + 1 < end) {
+            st2(r0p + i, r0[0], r0[1]);
+            st2(r1p + i, r1[0], r1[1]);
+            st2(r2p + i, r2[0], r2[1]);
+        } else {
+            r0p[i] = r0[0]; r1p[i] = r1[0]; r2p[i] = r2[0];
+        }
+    }
+}
+
+cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op2, uint64_t n,
+                          const uint64_t* moduli, uint64_t n_moduli, uint64_t batch,
+                          int moduli_per_item, cudaStream_t st) {
+    if (batch == 0 || n == 0 || n_moduli == 0) return cudaSuccess;
+    // 16-byte accesses need even n for every slab base to stay aligned.
+    if (n & 1) return cudaErrorInvalidValue;
+    const uint32_t slabs = (uint32_t)((n + kDySlab - 1) / kDySlab);
+    const uint64_t per_item = n_moduli * slabs;
+    const uint64_t kMaxGrid = 1u << 30;
+    const uint64_t items_per_launch = kMaxGrid / per_item ? kMaxGrid / per_item : 1;
+    for (uint64_t off = 0; off < batch; off += items_per_launch) {
+        const uint64_t cnt = batch - off < items_per_launch ? batch - off : items_per_launch;
+        k_dyadic<<<(unsigned)(cnt * per_item), kDyThreads, 0, st>>>(
+            res + off * 3 * n_moduli * n, op1 + off * 2 * n_moduli * n,
+            op2 + off * 2 * n_moduli * n, (uint32_t)n,
+            moduli + (moduli_per_item ? off * n_moduli : 0), (uint32_t)n_moduli,
+            moduli_per_item, slabs);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace hb

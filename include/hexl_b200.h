@@ -1,0 +1,167 @@
+/*
+ * hexl_b200.h -- C ABI of libhexl_b200.so, the B200 (sm_100a) device path that
+ * replaces intel/hexl-fpga's FPGA bitstream libraries and device runtime.
+ *
+ * Two layers, both plain C (pointers + sizes, no C++/torch/CUDA types):
+ *
+ *  (1) DEVICE-POINTER entry points: the kernel launchers.  They stand where the
+ *      reference's dlsym'd bitstream symbols stood
+ *      (host/inc/dl_kernel_interfaces.hpp:45-136: ntt_input/fwd_ntt/ntt_output,
+ *      intt_input/inv_ntt/intt_output, input_fifo_usm/output_nb_fifo_usm,
+ *      load/store/launchStoreSwitchKeys/launchConfigurableKernels) -- those take
+ *      sycl::queue& / sycl::buffer& and cannot be a C ABI, so each group is
+ *      replaced by one batched launcher taking device pointers and a
+ *      cudaStream_t (passed as void*).
+ *
+ *  (2) HOST-POINTER entry points hexl_b200_host_*: the 14 functions of the
+ *      reference's public API (host/inc/hexl-fpga.h:15-161), same argument
+ *      meaning, same asynchronous worksize/Completed protocol, same
+ *      accumulate-into-result behaviour for KeySwitch.  This is what a cgo /
+ *      JNI / ctypes / C++ binding of the reference's API binds to; the C++
+ *      drop-in libhexl-fpga.so (hexl-fpga_b200/host) forwards to them 1:1.
+ *
+ * All functions return 0 on success and a non-zero code on failure (negative:
+ * argument/shape error detected by this library; positive: a cudaError_t);
+ * hexl_b200_last_error() gives the message for the calling thread.  The
+ * library never falls back to a CPU computation: without a CUDA device every
+ * compute entry point fails.
+ */
+#ifndef HEXL_B200_H_
+#define HEXL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEXL_B200_OK 0
+#define HEXL_B200_EINVAL (-1)   /* bad argument / unsupported shape */
+#define HEXL_B200_ENODEV (-2)   /* no CUDA device / library not acquired */
+#define HEXL_B200_ESTATE (-3)   /* protocol misuse (e.g. Completed without work) */
+
+int hexl_b200_version(void);                 /* 10000*major + 100*minor + patch */
+const char* hexl_b200_last_error(void);      /* thread-local, never NULL */
+int hexl_b200_device_count(void);            /* visible CUDA devices, <0 on error */
+
+/* ------------------------------------------------------------------------- */
+/* (1) device-pointer launchers.  All pointers are device pointers on the    */
+/*     current CUDA device, 16-byte aligned; `stream` is a cudaStream_t.      */
+/* ------------------------------------------------------------------------- */
+
+/* Batched in-place forward negacyclic NTT, natural -> bit-reversed order,
+ * output in [0,q).  Replaces ntt_input + fwd_ntt + ntt_output
+ * (device/fwd_ntt.cpp:499-646; host call host/src/fpga.cpp:1014-1021).
+ * d_operand: batch*n words; d_roots/d_precon: n words each, index m+i
+ * (host/inc/hexl-fpga.h:110-120).  n = 2^10 .. 2^14 (the reference accepts
+ * only 16384, host/src/ntt.cpp:24). */
+int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_root_of_unity_powers,
+                      const uint64_t* d_precon_root_of_unity_powers, uint64_t coeff_modulus,
+                      uint64_t n, uint64_t batch, void* stream);
+
+/* Batched in-place inverse NTT, bit-reversed -> natural, output in [0,q).
+ * Replaces intt_input + inv_ntt + intt_output (device/inv_ntt.cpp:444-607;
+ * host/inc/hexl-fpga.h:139-156 for the argument meaning). */
+int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_root_of_unity_powers,
+                      const uint64_t* d_precon_inv_root_of_unity_powers, uint64_t coeff_modulus,
+                      uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch, void* stream);
+
+/* Batched dyadic ciphertext multiply.  Replaces input_fifo_usm + dyadic_multiply
+ * + output_nb_fifo_usm (device/dyadic_multiply.cpp:61-376).  Per item:
+ * op1/op2 [2][n_moduli][n], results [3][n_moduli][n] (host/inc/hexl-fpga.h:
+ * 28-44).  d_moduli holds n_moduli words (moduli_per_item == 0) or
+ * batch*n_moduli words (moduli_per_item != 0, one set per item as in
+ * tests/test_dyadic_multiply.cpp:36-38).  Any modulus >= 1, operands need not
+ * be reduced. */
+int hexl_b200_dyadic_multiply(uint64_t* d_results, const uint64_t* d_operand1,
+                              const uint64_t* d_operand2, uint64_t n, const uint64_t* d_moduli,
+                              uint64_t n_moduli, uint64_t batch, int moduli_per_item,
+                              void* stream);
+
+/* KeySwitch plan: the device-resident constants of one (shape, moduli, key set)
+ * -- twiddle tables, Barrett/Shoup metadata and the switch keys.  Replaces the
+ * host-side metadata/key upload of host/src/fpga.cpp:1039-1123,1158-1248 and
+ * the launchStoreSwitchKeys / launchConfigurableKernels bitstream calls.
+ * Arguments are HOST pointers with the meaning of host/inc/hexl-fpga.h:54-64;
+ * k_switch_keys[j] points to key_component_count*key_modulus_size*n words.
+ * twiddle_factors may be NULL (tables are then derived from `moduli` with the
+ * minimal primitive 2n-th root, as host/src/fpga.cpp:1097-1109 does). */
+typedef struct hexl_b200_ks_plan hexl_b200_ks_plan;
+int hexl_b200_ks_plan_create(hexl_b200_ks_plan** plan, uint64_t n, uint64_t decomp_modulus_size,
+                             uint64_t key_modulus_size, uint64_t rns_modulus_size,
+                             uint64_t key_component_count, const uint64_t* moduli,
+                             const uint64_t* const* k_switch_keys,
+                             const uint64_t* modswitch_factors, const uint64_t* twiddle_factors);
+int hexl_b200_ks_plan_destroy(hexl_b200_ks_plan* plan);
+
+/* Batched keyswitch on device-resident items.  Replaces load + the autorun
+ * pipeline + store (device/keyswitch.cpp:15-65) AND the host accumulate of
+ * host/src/fpga.cpp:441-475: d_result[b] (2*decomp*n words, [c][i][coeff]) is
+ * read-modify-written, d_t_target[b] is decomp*n words. */
+int hexl_b200_keyswitch(hexl_b200_ks_plan* plan, uint64_t* d_result, const uint64_t* d_t_target,
+                        uint64_t batch, void* stream);
+
+/* Host-side twiddle generation (no GPU needed): the tables a caller of _NTT /
+ * _INTT must supply, from the minimal primitive 2n-th root of unity mod q.
+ * Replaces host/src/twiddle-factors.cpp:16-62 + number_theory_util.cpp
+ * (ComputeRootOfUnityPowers / MinimalPrimitiveRoot / InverseUIntMod).
+ * out4n receives [roots | precon_roots | inv_roots | precon_inv_roots], n words
+ * each, in the layouts of host/inc/hexl-fpga.h:110-156; *inv_n = n^-1 mod q,
+ * *inv_n_w = inv_n * inv_roots[n-1] mod q. */
+int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, uint64_t* inv_n,
+                               uint64_t* inv_n_w);
+
+/* Kernel selection knobs for benchmarking (0 = default).  Not part of the
+ * reference surface. */
+int hexl_b200_set_option(const char* name, int64_t value);
+
+/* ------------------------------------------------------------------------- */
+/* (2) host-pointer API: the reference's public functions, C linkage.        */
+/*     (host/inc/hexl-fpga.h line numbers in brackets)                        */
+/* ------------------------------------------------------------------------- */
+int hexl_b200_host_acquire(void);                       /* acquire_FPGA_resources [19] */
+int hexl_b200_host_release(void);                       /* release_FPGA_resources [23] */
+
+int hexl_b200_host_set_worksize_dyadic_multiply(uint64_t ws);                 /* [34] */
+int hexl_b200_host_dyadic_multiply(uint64_t* results, const uint64_t* operand1,
+                                   const uint64_t* operand2, uint64_t n,
+                                   const uint64_t* moduli, uint64_t n_moduli);  /* [46] */
+int hexl_b200_host_dyadic_multiply_completed(void);                           /* [55] */
+
+int hexl_b200_host_set_worksize_keyswitch(uint64_t ws);                       /* [63] */
+int hexl_b200_host_keyswitch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n,
+                             uint64_t decomp_modulus_size, uint64_t key_modulus_size,
+                             uint64_t rns_modulus_size, uint64_t key_component_count,
+                             const uint64_t* moduli, const uint64_t** k_switch_keys,
+                             const uint64_t* modswitch_factors,
+                             const uint64_t* twiddle_factors);                /* [83] */
+int hexl_b200_host_keyswitch_completed(void);                                 /* [95] */
+
+int hexl_b200_host_set_worksize_ntt(uint64_t ws);                             /* [108] */
+int hexl_b200_host_ntt(uint64_t* operand, const uint64_t* root_of_unity_powers,
+                       const uint64_t* precon_root_of_unity_powers, uint64_t coeff_modulus,
+                       uint64_t n);                                           /* [120] */
+int hexl_b200_host_ntt_completed(void);                                       /* [130] */
+
+int hexl_b200_host_set_worksize_intt(uint64_t ws);                            /* [138] */
+int hexl_b200_host_intt(uint64_t* operand, const uint64_t* inv_root_of_unity_powers,
+                        const uint64_t* precon_inv_root_of_unity_powers, uint64_t coeff_modulus,
+                        uint64_t inv_n, uint64_t inv_n_w, uint64_t n);        /* [152] */
+int hexl_b200_host_intt_completed(void);                                      /* [161] */
+
+/* Counters since acquire: kernel launches issued by this library and bytes
+ * moved host<->device by the host-pointer API (for bench.py's gpu_launches /
+ * h2d / d2h fields). */
+typedef struct {
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} hexl_b200_stats;
+int hexl_b200_get_stats(hexl_b200_stats* out);
+int hexl_b200_reset_stats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEXL_B200_H_ */

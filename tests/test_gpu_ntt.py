@@ -1,0 +1,158 @@
+"""GPU parity of forward / inverse NTT against the CPU oracle, through the C ABI.
+
+Mirrors the reference's tests/test_fwd_ntt.cpp:97-170 and
+tests/test_inv_ntt.cpp:97-178: same stimuli (RANDOM, RAMP, ALL_ZEROS, ALL_ONES,
+IMPULSE, ALL_MAX_VALUES = 2^64-1) and prime sizes, bit-exact comparison.
+"""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+N = 16384
+STIMULI = ["random", "ramp", "zeros", "ones", "impulse", "all_max", "garbage"]
+
+
+def stimulus(kind, n, q, seed):
+    if kind == "random":
+        return ob.splitmix(n, seed, q)
+    if kind == "ramp":
+        return np.arange(n, dtype=np.uint64)
+    if kind == "zeros":
+        return np.zeros(n, dtype=np.uint64)
+    if kind == "ones":
+        return np.ones(n, dtype=np.uint64)
+    if kind == "impulse":
+        a = np.zeros(n, dtype=np.uint64)
+        a[0] = 1
+        return a
+    if kind == "all_max":
+        return np.full(n, 2**64 - 1, dtype=np.uint64)
+    if kind == "garbage":
+        return ob.splitmix(n, seed, 0)
+    raise ValueError(kind)
+
+
+def to_gpu(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def to_np(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def run_fwd(hb, polys, t):
+    d = to_gpu(np.stack(polys))
+    hb.ntt_fwd(d, to_gpu(t.roots), to_gpu(t.precon), t.q, t.n)
+    return to_np(d)
+
+
+def run_inv(hb, polys, t):
+    d = to_gpu(np.stack(polys))
+    hb.ntt_inv(d, to_gpu(t.inv_roots), to_gpu(t.precon_inv), t.q, t.inv_n, t.inv_n_w, t.n)
+    return to_np(d)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("bits", [20, 32, 51, 55, 61])
+def test_fwd_inv_all_stimuli_n16384(hb, bits, variant):
+    hb.set_option("ntt_variant", variant)
+    try:
+        q = ob.primes(1, bits, N)[0]
+        t = ob.Tables(N, q)
+        polys = [stimulus(k, N, q, 100 + i) for i, k in enumerate(STIMULI)]
+        got = run_fwd(hb, polys, t)
+        for i, k in enumerate(STIMULI):
+            assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t)), f"fwd {k} bits={bits}"
+        got = run_inv(hb, polys, t)
+        for i, k in enumerate(STIMULI):
+            assert np.array_equal(got[i], ob.inv_ntt(polys[i], t)), f"inv {k} bits={bits}"
+    finally:
+        hb.set_option("ntt_variant", 0)
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+def test_fwd_inv_other_sizes(hb, n):
+    q = ob.primes(1, 51, n)[0]
+    t = ob.Tables(n, q)
+    polys = [stimulus(k, n, q, 7 + i) for i, k in enumerate(["random", "ramp", "all_max", "garbage"])]
+    got = run_fwd(hb, polys, t)
+    goti = run_inv(hb, polys, t)
+    for i in range(len(polys)):
+        assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t))
+        assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t))
+
+
+def test_known_answers(hb):
+    """SURVEY.md Appendix B KAT-1 / KAT-2 / KAT-3 through the GPU path."""
+    q = 2251799814045697
+    t = ob.Tables(N, q)
+    a = ob.splitmix(N, 1, q)
+    out = run_fwd(hb, [a], t)[0]
+    assert [int(x) for x in out[:3]] == [1955457978075445, 1092550199427436, 1923103082448610]
+    assert ob.fnv(out) == 0x428B5C898DD187A3
+    assert np.array_equal(run_inv(hb, [out], t)[0], a)
+    ramp = {20: 0xBB10994907704BC4, 32: 0xBD3ECAEEF0141E84, 52: 0x64381823DFF21901,
+            55: 0xFAE12F2917FA203E}
+    for bits, h in ramp.items():
+        qq = ob.primes(1, bits, N)[0]
+        tt = ob.Tables(N, qq)
+        assert ob.fnv(run_fwd(hb, [np.arange(N, dtype=np.uint64)], tt)[0]) == h, bits
+    qq = 4503599627763713
+    out = run_fwd(hb, [np.full(N, 2**64 - 1, dtype=np.uint64)], ob.Tables(N, qq))[0]
+    assert int(out[0]) == 18373839436896342053 and ob.fnv(out) == 0x47244FE2BFC8E399
+
+
+def test_full_size_roundtrip_and_linearity(hb):
+    """BASELINE config 2 size (batch 4096): inverse(forward(x)) == x and
+    NTT(a) + NTT(b) == NTT(a + b) mod q, checked on the GPU with torch."""
+    import torch
+
+    q = 2251799814045697
+    t = ob.Tables(N, q)
+    B = 4096
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = torch.randint(0, q, (B, N), dtype=torch.int64, device="cuda", generator=g)
+    y = x.clone()
+    r, p = to_gpu(t.roots), to_gpu(t.precon)
+    hb.ntt_fwd(y, r, p, q, N)
+    assert int(y.max()) < q and int(y.min()) >= 0
+    # spot-check three polynomials against the oracle
+    for i in (0, 1777, B - 1):
+        assert np.array_equal(to_np(y[i]), ob.fwd_ntt(to_np(x[i]), t))
+    # linearity on the first half vs second half
+    s = (x[: B // 2] + x[B // 2:]) % q
+    hb.ntt_fwd(s, r, p, q, N)
+    assert torch.equal(s, (y[: B // 2] + y[B // 2:]) % q)
+    hb.ntt_inv(y, to_gpu(t.inv_roots), to_gpu(t.precon_inv), q, t.inv_n, t.inv_n_w, N)
+    assert torch.equal(x, y)
+
+
+def test_host_api_ntt_intt(acquired):
+    """_set_worksize_NTT / _NTT / _NTTCompleted on host pointers, batch laid out
+    contiguously as the reference tests do (tests/test_fwd_ntt.cpp:109-115)."""
+    hb = acquired
+    q = ob.primes(1, 51, N)[0]
+    t = ob.Tables(N, q)
+    B = 9
+    data = np.stack([ob.splitmix(N, 50 + i, q) for i in range(B)])
+    work = data.copy()
+    hb.set_worksize_NTT(B)
+    for i in range(B):
+        hb.NTT(work[i], t.roots, t.precon, q, N)
+    assert hb.NTTCompleted()
+    for i in range(B):
+        assert np.array_equal(work[i], ob.fwd_ntt(data[i], t))
+    hb.set_worksize_INTT(B)
+    for i in range(B):
+        hb.INTT(work[i], t.inv_roots, t.precon_inv, q, t.inv_n, t.inv_n_w, N)
+    assert hb.INTTCompleted()
+    assert np.array_equal(work, data)
+    # synchronous mode (worksize 1, the default)
+    one = data[0].copy()
+    hb.NTT(one, t.roots, t.precon, q, N)
+    assert np.array_equal(one, ob.fwd_ntt(data[0], t))
