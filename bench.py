@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hexl-fpga B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): NTT/s at N=16384.  Workload = BASELINE configs[1]:
+forward + inverse negacyclic NTT, N=16384, one 52-bit prime, batch 4096
+polynomials per GPU (512 MiB, four times the 126 MB L2, so every step streams
+from HBM).  One step = one forward NTT launch + one inverse NTT launch over the
+whole batch = 8192 transforms.  With N GPUs every rank runs its own batch
+(independent polynomials, no data-path collective -> weak scaling); NCCL is
+used only to replicate the twiddle tables from rank 0 and to agree on the
+time (max over ranks).
+
+Also reported on the same line (N=1: measured after the headline region):
+keyswitch (configs[3]: N=16384, decomp 7, key 8, batch 1024) and dyadic
+multiply (configs[2]) device-resident throughput with their own roofline
+fractions, the end-to-end numbers through the reference's host-pointer API,
+and a CPU baseline timed on the host cores.
+
+--impl reference times the reference's own CPU code for this path (its scalar
+NTT, tests/test_utils/ntt.cpp compiled unmodified into oracle/_ref; intel-hexl
+itself is an unvendored dependency) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "hexl-fpga_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N = 16384
+Q52 = 2251799814045697            # GeneratePrimes(1, 51, 16384)[0], a true 52-bit prime
+BATCH = 4096
+NTT_BYTES = 2 * N * 8             # algorithmic HBM bytes per transform (read + write)
+KS_D, KS_K, KS_BATCH = 7, 8, 1024
+KS_BYTES = (KS_D + 2 * 2 * KS_D) * N * 8          # t_target + result read + result write
+DY_N, DY_M, DY_BATCH = 8192, 4, 8192
+DY_BYTES = (2 * 2 + 3) * DY_M * DY_N * 8
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """per-launch DRAM bytes of `kernel` from the committed ncu summary, or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# reference arm / CPU baseline
+# --------------------------------------------------------------------------
+def cpu_ntt_rate(polys, threads, reps=1):
+    """fwd + inv NTT over `polys` polynomials on `threads` host threads.
+    Uses oracle/_ref (the reference's own scalar NTT) when it was built, else
+    the oracle port.  Returns (transforms/s, kind)."""
+    import oracle_binding as ob
+
+    t = ob.Tables(N, Q52)
+    a = np.stack([ob.splitmix(N, 1234 + i, Q52) for i in range(min(polys, 64))])
+    a = np.ascontiguousarray(np.resize(a, (polys, N)))
+    r = ob.ref()
+    best = None
+    for _ in range(reps + 1):          # first pass warms caches / thread pool
+        t0 = time.perf_counter()
+        if r is not None:
+            r.ref_fwd_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.roots), ob.P(t.precon), threads)
+            r.ref_inv_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.inv_roots), ob.P(t.precon_inv), threads)
+        else:
+            o = ob.oracle()
+            o.ho_fwd_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.roots), ob.P(t.precon), threads)
+            o.ho_inv_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.inv_roots), ob.P(t.precon_inv), t.inv_n,
+                               t.inv_n_w, threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 2 * polys / best, ("reference" if r is not None else "port")
+
+
+def host_threads():
+    import oracle_binding as ob
+
+    return max(1, min(ob.oracle().ho_max_threads(), os.cpu_count() or 1))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = host_threads()
+    polys = 64 * threads                                   # bounded sample per step
+    import oracle_binding as ob
+
+    t = ob.Tables(N, Q52)
+    a = np.ascontiguousarray(np.resize(np.stack([ob.splitmix(N, 1234 + i, Q52) for i in range(16)]), (polys, N)))
+    r = ob.ref()
+    kind = "reference" if r is not None else "port"
+
+    def step():
+        if r is not None:
+            r.ref_fwd_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.roots), ob.P(t.precon), threads)
+            r.ref_inv_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.inv_roots), ob.P(t.precon_inv), threads)
+        else:
+            o = ob.oracle()
+            o.ho_fwd_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.roots), ob.P(t.precon), threads)
+            o.ho_inv_ntt_batch(ob.P(a), polys, N, Q52, ob.P(t.inv_roots), ob.P(t.precon_inv), t.inv_n,
+                               t.inv_n_w, threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = 2 * polys * args.steps / dt
+    sample = f"{polys} polynomials fwd+inv per step ({threads} threads), scalar Harvey NTT"
+    print(json.dumps({
+        "impl": "reference", "metric": "NTT/s (N=16384)", "value": value, "unit": "NTT/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "fwd+inv NTT N=16384, 52-bit prime (BASELINE configs[1]); bounded CPU sample",
+                   "n": N, "modulus": Q52, "batch_per_step": polys},
+        "cpu_baseline": {"value": value, "unit": "NTT/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "NTT/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference CPU path: tests/test_utils/ntt.cpp (intel-hexl's scalar NTT as vendored by the "
+                "reference) compiled unmodified into oracle/_ref; intel-hexl AVX-512 itself is unvendored"}))
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def gpu_tensor(a, dev):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).to(dev)
+
+
+def event_pair():
+    import torch
+
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import hexl_b200 as hb
+    import oracle_binding as ob
+
+    hb.lib()                                   # fails loudly if the CUDA library is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, peak_src = peaks()
+
+    # twiddle tables: rank 0 computes, NCCL broadcast replicates (the only collective)
+    tab_np = None
+    if rank == 0:
+        t = ob.Tables(N, Q52)
+        tab_np = np.stack([t.roots, t.precon, t.inv_roots, t.precon_inv])
+    tabs = gpu_tensor(tab_np, dev) if rank == 0 else torch.empty((4, N), dtype=torch.int64, device=dev)
+    scal = torch.tensor([t.inv_n, t.inv_n_w] if rank == 0 else [0, 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(tabs, 0)
+        dist.broadcast(scal, 0)
+    roots, precon, inv_roots, precon_inv = tabs[0], tabs[1], tabs[2], tabs[3]
+    inv_n, inv_n_w = int(scal[0]), int(scal[1])
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randint(0, Q52, (BATCH, N), dtype=torch.int64, device=dev, generator=g)
+    x0 = x[:2].clone()
+
+    def step(timing=None):
+        if timing is not None:
+            e0, e1 = event_pair()
+            e0.record()
+        hb.ntt_fwd(x, roots, precon, Q52, N)
+        if timing is not None:
+            e1.record()
+            timing.append((e0, e1))
+        hb.ntt_inv(x, inv_roots, precon_inv, Q52, inv_n, inv_n_w, N)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    hb.reset_stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    fwd_events = []
+    s0, s1 = event_pair()
+    barrier()
+    w0 = time.time()
+    s0.record()
+    for _ in range(args.steps):
+        step(fwd_events)
+    s1.record()
+    barrier()
+    w1 = time.time()
+    elapsed = s0.elapsed_time(s1) * 1e-3
+    launches = hb.get_stats()["kernel_launches"]
+    clocks = sampler.stop(w0, w1) if sampler else None
+    if world > 1:
+        tt = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt[0])
+        ll = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ll)
+        launches = int(ll[0])
+    # the data went through steps x (fwd, inv): must be back where it started
+    assert torch.equal(x[:2], x0), "fwd/inv round trip changed the data"
+    value = world * 2 * BATCH * args.steps / elapsed
+    fwd_s = float(np.mean([a.elapsed_time(b) for a, b in fwd_events])) * 1e-3
+    achieved = BATCH * NTT_BYTES / fwd_s / 1e9
+
+    line = {
+        "metric": "NTT/s (N=16384)", "value": value, "unit": "NTT/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "fwd+inv negacyclic NTT, N=16384, one 52-bit prime, batch 4096 per GPU "
+                               "(BASELINE configs[1]); step = 1 fwd + 1 inv launch = 8192 transforms per GPU",
+                   "n": N, "modulus": Q52, "batch_per_gpu": BATCH, "sharding": f"batch x{world}, no collective",
+                   "l2": "working set 512 MiB per GPU > 126 MB L2 (no flush needed)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_ntt_fwd (forward NTT, one CTA per polynomial)",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "peak_source": peak_src, "traffic": ncu_traffic("ntt_fwd"),
+                     "algorithmic_bytes_per_launch": BATCH * NTT_BYTES, "launch_s": fwd_s},
+        "clocks": clocks,
+    }
+    if rank == 0:
+        line.update(extras(args, hb, ob, dev, hbm_peak, world))
+    # ---- end-to-end through the reference's host-pointer API (every rank) ----
+    e2e = e2e_ntt(args, hb, ob, dev, world)
+    if world > 1:
+        tt = torch.tensor([e2e["s"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["s"] = float(tt[0])
+    line["e2e"] = {"value": world * 2 * e2e["batch"] * e2e["steps"] / e2e["s"], "unit": "NTT/s",
+                   "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                   "api": "hexl_b200_host_{set_worksize_,}ntt/intt(+completed) on pinned host buffers",
+                   "batch_per_gpu": e2e["batch"], "steps": e2e["steps"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_ntt(args, hb, ob, dev, world):
+    """Same workload through the host API: host buffers in, host buffers out."""
+    import torch
+
+    t = ob.Tables(N, Q52)
+    hb.acquire_FPGA_resources()
+    try:
+        host = torch.randint(0, Q52, (BATCH, N), dtype=torch.int64).pin_memory()
+        ref0 = host[:1].clone()
+        ptr = host.data_ptr()
+        steps = max(2, min(args.steps, 5))
+
+        def step():
+            hb.set_worksize_NTT(BATCH)
+            hb.NTT_many(ptr, N, BATCH, t.roots, t.precon, Q52, N)
+            hb.NTTCompleted()
+            hb.set_worksize_INTT(BATCH)
+            hb.INTT_many(ptr, N, BATCH, t.inv_roots, t.precon_inv, Q52, t.inv_n, t.inv_n_w, N)
+            hb.INTTCompleted()
+
+        step()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        hb.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        st = hb.get_stats()
+        assert torch.equal(host[:1], ref0)
+        return {"s": dt, "steps": steps, "batch": BATCH, "h2d": st["h2d_bytes"] // steps,
+                "d2h": st["d2h_bytes"] // steps}
+    finally:
+        hb.release_FPGA_resources()
+
+
+def extras(args, hb, ob, dev, hbm_peak, world):
+    """keyswitch + dyadic device-resident numbers and the CPU baseline (rank 0)."""
+    import torch
+
+    from ks_util import KsProblem
+
+    out = {}
+    # -- keyswitch, BASELINE configs[3] --
+    p = KsProblem(N, KS_D, KS_K, 1, 51)
+    plan = hb.KsPlan(N, KS_D, KS_K, KS_D + 1, 2, p.moduli, p.keys, p.msf)
+    g = torch.Generator(device=dev).manual_seed(99)
+    res = torch.empty((KS_BATCH, 2 * KS_D * N), dtype=torch.int64, device=dev)
+    tt = torch.empty((KS_BATCH, KS_D * N), dtype=torch.int64, device=dev)
+    for j in range(KS_D):
+        q = int(p.moduli[j])
+        tt[:, j * N:(j + 1) * N] = torch.randint(0, q, (KS_BATCH, N), dtype=torch.int64, device=dev, generator=g)
+        for c in range(2):
+            o = (c * KS_D + j) * N
+            res[:, o:o + N] = torch.randint(0, q, (KS_BATCH, N), dtype=torch.int64, device=dev, generator=g)
+    plan.keyswitch(res, tt, KS_BATCH)
+    torch.cuda.synchronize()
+    hb.reset_stats()
+    ksteps = 3
+    e0, e1 = event_pair()
+    e0.record()
+    for _ in range(ksteps):
+        plan.keyswitch(res, tt, KS_BATCH)
+    e1.record()
+    e1.synchronize()
+    ks_s = e0.elapsed_time(e1) * 1e-3 / ksteps
+    out["keyswitch"] = {
+        "metric": "KeySwitch/s (N=16384, decomp=7, key=8)", "value": KS_BATCH / ks_s, "unit": "KeySwitch/s",
+        "batch": KS_BATCH, "ms_per_step": ks_s * 1e3, "gpu_launches": hb.get_stats()["kernel_launches"],
+        "roofline": {"bound": "hbm", "achieved": KS_BATCH * KS_BYTES / ks_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": KS_BATCH * KS_BYTES / ks_s / 1e9 / hbm_peak,
+                     "note": "compute-bound by construction: 72 NTT-equivalents per 4.4 MiB"}}
+    del res, tt
+    plan.close()
+    # -- dyadic multiply, BASELINE configs[2] --
+    moduli = np.array(ob.primes(DY_M, 51, DY_N), dtype=np.uint64)
+    op1 = torch.randint(0, int(moduli[0]), (DY_BATCH, 2 * DY_M * DY_N), dtype=torch.int64, device=dev)
+    op2 = torch.randint(0, int(moduli[0]), (DY_BATCH, 2 * DY_M * DY_N), dtype=torch.int64, device=dev)
+    rs = torch.empty((DY_BATCH, 3 * DY_M * DY_N), dtype=torch.int64, device=dev)
+    dm = gpu_tensor(moduli, dev)
+    hb.dyadic_multiply(rs, op1, op2, DY_N, dm, DY_M, DY_BATCH)
+    e0, e1 = event_pair()
+    e0.record()
+    for _ in range(3):
+        hb.dyadic_multiply(rs, op1, op2, DY_N, dm, DY_M, DY_BATCH)
+    e1.record()
+    e1.synchronize()
+    dy_s = e0.elapsed_time(e1) * 1e-3 / 3
+    out["dyadic_multiply"] = {
+        "metric": "DyadicMultiply/s (n=8192, 4 moduli)", "value": DY_BATCH / dy_s, "unit": "multiplies/s",
+        "batch": DY_BATCH, "roofline": {"bound": "hbm", "achieved": DY_BATCH * DY_BYTES / dy_s / 1e9,
+                                        "peak": hbm_peak, "unit": "GB/s",
+                                        "frac": DY_BATCH * DY_BYTES / dy_s / 1e9 / hbm_peak}}
+    del op1, op2, rs
+    # -- CPU baseline (bounded sample of the headline workload) --
+    threads = host_threads()
+    polys = 128 * threads
+    rate, kind = cpu_ntt_rate(polys, threads)
+    out["cpu_baseline"] = {"value": rate, "unit": "NTT/s", "cores": threads, "kind": kind,
+                           "sample": f"{polys} polynomials fwd+inv, N=16384, 52-bit prime, {threads} threads; "
+                                     "reference tests/test_utils/ntt.cpp scalar Harvey NTT "
+                                     "(intel-hexl AVX-512 is unvendored)"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+               os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup",
+               str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,10 @@ _SIGNATURES = {
     "hexl_b200_host_set_worksize_intt": ([u64], C.c_int),
     "hexl_b200_host_intt": ([vp, vp, vp, u64, u64, u64, u64], C.c_int),
     "hexl_b200_host_intt_completed": ([], C.c_int),
+    "hexl_b200_host_ntt_many": ([vp, u64, u64, vp, vp, u64, u64], C.c_int),
+    "hexl_b200_host_intt_many": ([vp, u64, u64, vp, vp, u64, u64, u64, u64], C.c_int),
+    "hexl_b200_host_dyadic_multiply_many": ([vp, vp, vp, u64, u64, vp, u64], C.c_int),
+    "hexl_b200_host_keyswitch_many": ([vp, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, vp], C.c_int),
     "hexl_b200_get_stats": ([vp], C.c_int),
     "hexl_b200_reset_stats": ([], C.c_int),
 }
@@ -283,6 +287,29 @@ def INTT(operand, inv_root_of_unity_powers, precon_inv_root_of_unity_powers, coe
 def INTTCompleted():
     _check(lib().hexl_b200_host_intt_completed(), "_INTTCompleted")
     return True
+
+
+# bulk submission: `count` calls in one FFI crossing; `ptr` arguments are raw
+# host addresses (numpy .ctypes.data or a pinned torch tensor's data_ptr()).
+def NTT_many(base_ptr, stride_words, count, roots, precon, q, n):
+    _check(lib().hexl_b200_host_ntt_many(base_ptr, stride_words, count, _hptr(roots), _hptr(precon), q, n),
+           "_NTT x count")
+
+
+def INTT_many(base_ptr, stride_words, count, inv_roots, precon_inv, q, inv_n, inv_n_w, n):
+    _check(lib().hexl_b200_host_intt_many(base_ptr, stride_words, count, _hptr(inv_roots), _hptr(precon_inv), q,
+                                          inv_n, inv_n_w, n), "_INTT x count")
+
+
+def DyadicMultiply_many(res_ptr, op1_ptr, op2_ptr, count, n, moduli, n_moduli):
+    _check(lib().hexl_b200_host_dyadic_multiply_many(res_ptr, op1_ptr, op2_ptr, count, n, _hptr(moduli),
+                                                     n_moduli), "DyadicMultiply x count")
+
+
+def KeySwitch_many(res_ptr, t_ptr, count, n, D, K, R, Cc, moduli, keys, msf, twiddles=None):
+    _check(lib().hexl_b200_host_keyswitch_many(res_ptr, t_ptr, count, n, D, K, R, Cc, _hptr(moduli), keys.ptr,
+                                               _hptr(msf), _hptr(twiddles) if twiddles is not None else None),
+           "KeySwitch x count")
 
 
 # the reference spells the deprecated entry points with a leading underscore

@@ -617,4 +617,38 @@ int hexl_b200_host_intt(uint64_t* operand, const uint64_t* inv_roots, const uint
     return submit(r);
 }
 
+
+int hexl_b200_host_ntt_many(uint64_t* base, uint64_t stride, uint64_t count, const uint64_t* roots,
+                            const uint64_t* precon, uint64_t q, uint64_t n) {
+    for (uint64_t i = 0; i < count; ++i)
+        if (int rc = hexl_b200_host_ntt(base + i * stride, roots, precon, q, n)) return rc;
+    return 0;
+}
+int hexl_b200_host_intt_many(uint64_t* base, uint64_t stride, uint64_t count, const uint64_t* inv_roots,
+                             const uint64_t* precon_inv, uint64_t q, uint64_t inv_n, uint64_t inv_n_w,
+                             uint64_t n) {
+    for (uint64_t i = 0; i < count; ++i)
+        if (int rc = hexl_b200_host_intt(base + i * stride, inv_roots, precon_inv, q, inv_n, inv_n_w, n))
+            return rc;
+    return 0;
+}
+int hexl_b200_host_dyadic_multiply_many(uint64_t* results, const uint64_t* op1, const uint64_t* op2,
+                                        uint64_t count, uint64_t n, const uint64_t* moduli,
+                                        uint64_t n_moduli) {
+    for (uint64_t i = 0; i < count; ++i)
+        if (int rc = hexl_b200_host_dyadic_multiply(results + i * 3 * n_moduli * n, op1 + i * 2 * n_moduli * n,
+                                                    op2 + i * 2 * n_moduli * n, n, moduli, n_moduli))
+            return rc;
+    return 0;
+}
+int hexl_b200_host_keyswitch_many(uint64_t* result, const uint64_t* t_target, uint64_t count, uint64_t n,
+                                  uint64_t D, uint64_t K, uint64_t R, uint64_t C, const uint64_t* moduli,
+                                  const uint64_t** keys, const uint64_t* msf, const uint64_t* twiddles) {
+    for (uint64_t i = 0; i < count; ++i)
+        if (int rc = hexl_b200_host_keyswitch(result + i * 2 * D * n, t_target + i * D * n, n, D, K, R, C,
+                                              moduli, keys, msf, twiddles))
+            return rc;
+    return 0;
+}
+
 }  // extern "C"

@@ -150,6 +150,28 @@ int hexl_b200_host_intt(uint64_t* operand, const uint64_t* inv_root_of_unity_pow
                         uint64_t inv_n, uint64_t inv_n_w, uint64_t n);        /* [152] */
 int hexl_b200_host_intt_completed(void);                                      /* [161] */
 
+/* Bulk submission helpers (not in the reference): exactly `count` calls of the
+ * function above on items `base + i*stride_words`, made in one FFI crossing so
+ * that bindings with an expensive call path (ctypes, JNI, cgo) do not pay it
+ * per polynomial.  They do not call set_worksize / Completed. */
+int hexl_b200_host_ntt_many(uint64_t* operand_base, uint64_t stride_words, uint64_t count,
+                            const uint64_t* root_of_unity_powers,
+                            const uint64_t* precon_root_of_unity_powers, uint64_t coeff_modulus,
+                            uint64_t n);
+int hexl_b200_host_intt_many(uint64_t* operand_base, uint64_t stride_words, uint64_t count,
+                             const uint64_t* inv_root_of_unity_powers,
+                             const uint64_t* precon_inv_root_of_unity_powers,
+                             uint64_t coeff_modulus, uint64_t inv_n, uint64_t inv_n_w, uint64_t n);
+int hexl_b200_host_dyadic_multiply_many(uint64_t* results_base, const uint64_t* operand1_base,
+                                        const uint64_t* operand2_base, uint64_t count, uint64_t n,
+                                        const uint64_t* moduli, uint64_t n_moduli);
+int hexl_b200_host_keyswitch_many(uint64_t* result_base, const uint64_t* t_target_base,
+                                  uint64_t count, uint64_t n, uint64_t decomp_modulus_size,
+                                  uint64_t key_modulus_size, uint64_t rns_modulus_size,
+                                  uint64_t key_component_count, const uint64_t* moduli,
+                                  const uint64_t** k_switch_keys, const uint64_t* modswitch_factors,
+                                  const uint64_t* twiddle_factors);
+
 /* Counters since acquire: kernel launches issued by this library and bytes
  * moved host<->device by the host-pointer API (for bench.py's gpu_launches /
  * h2d / d2h fields). */
