@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -21,7 +22,7 @@ namespace hexl_b200 {
 
 static thread_local std::string g_err = "";
 std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
-static std::atomic<int> g_ntt_variant{0};
+static std::atomic<int> g_ntt_variant{1};   // 1: 32 words/thread at N=16384 (default), 0: 16
 static std::atomic<int64_t> g_ks_workspace_mb{1024};
 
 int fail(int code, const char* fmt, ...) {
@@ -45,9 +46,8 @@ static int ilog2_exact(uint64_t n) {
 }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const uint64_t* roots,
-                       const uint64_t* precon, const uint64_t* inv_roots,
-                       const uint64_t* precon_inv) {
+hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
+                       const hb::TwPair* itw, int logn) {
     hb::ModTab t;
     t.q = q;
     t.twoq = q << 1;
@@ -56,12 +56,40 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const uint6
     t.sc.inv_n_p = inv_n < q ? nt::shoup(inv_n, q) : 0;
     t.sc.inv_n_w = inv_n_w;
     t.sc.inv_n_w_p = inv_n_w < q ? nt::shoup(inv_n_w, q) : 0;
-    t.roots = roots;
-    t.precon = precon;
-    t.inv_roots = inv_roots;
-    t.precon_inv = precon_inv;
+    t.fm = hb::make_fastmod(q);
+    t.ftw = ftw;
+    t.itw = itw;
+    t.fwd_fast_ok = hb::fwd_fast_modulus_ok(q, logn) ? 1u : 0u;
+    t.inv_fast_ok = hb::inv_fast_modulus_ok(q) ? 1u : 0u;
     return t;
 }
+
+// Scratch for the packed twiddles of a plain NTT call: one small buffer per
+// (device, stream), allocated once and reused -- work on one stream is ordered,
+// so the pack kernel of call k+1 cannot overtake the transform of call k.
+struct StreamScratch {
+    std::mutex mu;
+    std::map<std::pair<int, cudaStream_t>, std::pair<void*, size_t>> bufs;
+    cudaError_t get(cudaStream_t st, size_t bytes, void** out) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        std::lock_guard<std::mutex> lk(mu);
+        auto& b = bufs[{dev, st}];
+        if (b.second < bytes) {
+            if (b.first) {
+                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+                cudaFree(b.first);
+                b = {nullptr, 0};
+            }
+            if ((e = cudaMalloc(&b.first, bytes)) != cudaSuccess) return e;
+            b.second = bytes;
+        }
+        *out = b.first;
+        return cudaSuccess;
+    }
+};
+static StreamScratch g_scratch;
 
 }  // namespace hexl_b200
 
@@ -72,7 +100,7 @@ struct hexl_b200_ks_plan {
     int device = 0;
     uint64_t n = 0, D = 0, K = 0, R = 0;
     hb::KsDev dev{};
-    uint64_t* d_tables = nullptr;   // K * 4 * n
+    hb::TwPair* d_packed = nullptr; // K * (FWD_ENTRIES + INV_ENTRIES) packed twiddles
     uint64_t* d_keys = nullptr;     // D * 2 * K * n
     uint64_t* d_small = nullptr;    // msf, msf_p
     hb::ModTab* d_tabs = nullptr;
@@ -101,7 +129,9 @@ int hexl_b200_device_count(void) {
 int hexl_b200_set_option(const char* name, int64_t value) {
     if (!name) return fail(HEXL_B200_EINVAL, "option name is NULL");
     if (!strcmp(name, "ntt_variant")) {
-        if (value < 0 || value > 1) return fail(HEXL_B200_EINVAL, "ntt_variant must be 0 or 1");
+        // bit 0: 32 words/thread at N=16384; bit 1 (perf exploration only): skip the
+        // input-range vote, i.e. the caller guarantees in-contract inputs
+        if (value < 0 || value > 3) return fail(HEXL_B200_EINVAL, "ntt_variant must be 0..3");
         g_ntt_variant = (int)value;
         return 0;
     }
@@ -154,11 +184,18 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
     if (!d_operand || !d_roots || !d_precon) return fail(HEXL_B200_EINVAL, "ntt_fwd: NULL pointer");
     if (!aligned16(d_operand)) return fail(HEXL_B200_EINVAL, "ntt_fwd: operand not 16-byte aligned");
     if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "ntt_fwd: modulus must be in [2, 2^62)");
-    hb::ModTab t = make_modtab(q, 0, 0, d_roots, d_precon, nullptr, nullptr);
-    cudaError_t e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, g_ntt_variant.load(),
-                                       (cudaStream_t)stream);
+    if (batch == 0) return 0;
+    const int variant = g_ntt_variant.load();
+    hb::TwPair* packed = nullptr;
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20), (void**)&packed);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: twiddle scratch");
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr,
+                                 (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack twiddles");
+    hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn);
+    e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, variant, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd launch");
-    g_launches += batch ? 1 : 0;
+    g_launches += 2;
     return 0;
 }
 
@@ -175,11 +212,20 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
     if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "ntt_inv: modulus must be in [2, 2^62)");
     if (inv_n >= q || inv_n_w >= q)
         return fail(HEXL_B200_EINVAL, "ntt_inv: inv_n / inv_n_w must be reduced mod q");
-    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, nullptr, d_inv_roots, d_precon_inv);
-    cudaError_t e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, g_ntt_variant.load(),
-                                       (cudaStream_t)stream);
+    if (batch == 0) return 0;
+    const int variant = g_ntt_variant.load();
+    hb::TwPair* packed = nullptr;
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20), (void**)&packed);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: twiddle scratch");
+    // second half of the scratch, so a forward and an inverse call may be queued back to back
+    packed += (1u << 19) / sizeof(hb::TwPair);
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed,
+                                 (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack twiddles");
+    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn);
+    e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, variant, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv launch");
-    g_launches += batch ? 1 : 0;
+    g_launches += 2;
     return 0;
 }
 
@@ -245,7 +291,11 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         hexl_b200_ks_plan_destroy(p);
         return rc;
     };
-    if ((e = cudaMalloc(&p->d_tables, K * 4 * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc tables"));
+    const int ks_variant = 1;   // keyswitch_kernels.cu uses NttCfg<14,5> at N = 16384
+    const size_t fe = hb::packed_fwd_entries((uint32_t)logn, ks_variant), ie = hb::packed_inv_entries((uint32_t)logn, ks_variant);
+    uint64_t* d_raw = nullptr;      // raw tables, only needed while packing
+    if ((e = cudaMalloc(&p->d_packed, K * (fe + ie) * sizeof(hb::TwPair)))) return cleanup(cuda_fail(e, "cudaMalloc tables"));
+    if ((e = cudaMalloc(&d_raw, K * 4 * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc raw tables"));
     if ((e = cudaMalloc(&p->d_keys, D * 2 * K * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc keys"));
     if ((e = cudaMalloc(&p->d_small, 2 * K * 8))) return cleanup(cuda_fail(e, "cudaMalloc small"));
     if ((e = cudaMalloc(&p->d_tabs, K * sizeof(hb::ModTab)))) return cleanup(cuda_fail(e, "cudaMalloc tabs"));
@@ -263,14 +313,22 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         memcpy(h + n, t.precon.data(), n * 8);
         memcpy(h + 2 * n, t.inv_roots.data(), n * 8);
         memcpy(h + 3 * n, t.precon_inv.data(), n * 8);
-        uint64_t* d = p->d_tables + i * 4 * n;
-        h_tabs[i] = make_modtab(q, t.inv_n, t.inv_n_w, d, d + n, d + 2 * n, d + 3 * n);
+        hb::TwPair* pk = p->d_packed + i * (fe + ie);
+        h_tabs[i] = make_modtab(q, t.inv_n, t.inv_n_w, pk, pk + fe, logn);
         h_divs[i] = hb::make_divisor(q);
         h_small[i] = msf[i] % q;                       // host/src/fpga.cpp:1057-1061
         h_small[K + i] = nt::shoup(h_small[i], q);
     }
-    if ((e = cudaMemcpy(p->d_tables, h_tables.data(), K * 4 * n * 8, cudaMemcpyHostToDevice)))
-        return cleanup(cuda_fail(e, "upload tables"));
+    e = cudaMemcpy(d_raw, h_tables.data(), K * 4 * n * 8, cudaMemcpyHostToDevice);
+    for (uint64_t i = 0; i < K && e == cudaSuccess; ++i) {
+        const uint64_t* d = d_raw + i * 4 * n;
+        hb::TwPair* pk = p->d_packed + i * (fe + ie);
+        e = hb::launch_pack_twiddles((uint32_t)logn, ks_variant, d, d + n, pk, d + 2 * n, d + 3 * n, pk + fe, 0);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_raw);
+    if (e != cudaSuccess) return cleanup(cuda_fail(e, "upload / pack tables"));
+    g_launches += K;
     for (uint64_t j = 0; j < D; ++j)
         if ((e = cudaMemcpy(p->d_keys + j * 2 * K * n, keys[j], 2 * K * n * 8, cudaMemcpyHostToDevice)))
             return cleanup(cuda_fail(e, "upload keys"));
@@ -292,7 +350,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
 
 int hexl_b200_ks_plan_destroy(hexl_b200_ks_plan* p) {
     if (!p) return 0;
-    cudaFree(p->d_tables); cudaFree(p->d_keys); cudaFree(p->d_small);
+    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_small);
     cudaFree(p->d_tabs); cudaFree(p->d_divs); cudaFree(p->ws);
     delete p;
     return 0;
@@ -305,9 +363,8 @@ int hexl_b200_keyswitch(hexl_b200_ks_plan* p, uint64_t* d_result, const uint64_t
     if (!d_result || !d_t) return fail(HEXL_B200_EINVAL, "keyswitch: NULL pointer");
     if (!aligned16(d_result) || !aligned16(d_t))
         return fail(HEXL_B200_EINVAL, "keyswitch: buffers must be 16-byte aligned");
-    const uint64_t n = p->n, D = p->D, R = p->R;
-    // scratch words per item: U (D*n) + V (R*D*n) + ACC (2*R*n)
-    const uint64_t per_item = (D + R * D + 2 * R) * n;
+    const uint64_t n = p->n, D = p->D;
+    const uint64_t per_item = hb::ks_scratch_words_per_item(p->dev);
     uint64_t chunk = ((uint64_t)g_ks_workspace_mb.load() << 20) / 8 / per_item;
     if (chunk < 1) chunk = 1;
     if (chunk > batch) chunk = batch;
@@ -324,13 +381,11 @@ int hexl_b200_keyswitch(hexl_b200_ks_plan* p, uint64_t* d_result, const uint64_t
     }
     for (uint64_t off = 0; off < batch; off += chunk) {
         const uint64_t items = batch - off < chunk ? batch - off : chunk;
-        uint64_t* U = p->ws;
-        uint64_t* V = U + items * D * n;
-        uint64_t* ACC = V + items * R * D * n;
-        cudaError_t e = hb::launch_ks_chunk(p->dev, d_result + off * 2 * D * n, d_t + off * D * n,
-                                            items, U, V, ACC, (cudaStream_t)stream);
+        int launches = 0;
+        cudaError_t e = hb::launch_ks_chunk(p->dev, d_result + off * 2 * D * n, d_t + off * D * n, items, p->ws,
+                                            (cudaStream_t)stream, &launches);
         if (e != cudaSuccess) return cuda_fail(e, "keyswitch launch");
-        g_launches += 5;
+        g_launches += launches;
     }
     return 0;
 }

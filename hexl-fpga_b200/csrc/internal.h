@@ -11,7 +11,6 @@ namespace hexl_b200 {
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 extern std::atomic<uint64_t> g_launches, g_h2d, g_d2h;
-hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const uint64_t* roots,
-                       const uint64_t* precon, const uint64_t* inv_roots,
-                       const uint64_t* precon_inv);
+hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
+                       const hb::TwPair* itw, int logn);
 }  // namespace hexl_b200

@@ -5,45 +5,83 @@
 // -> dyadmult.hpp -> intt2_redu.hpp -> ntt2.hpp -> ms.hpp) plus the host-side
 // accumulate into `result` (host/src/fpga.cpp:441-475), for a chunk of items:
 //
-//   S1  U[b][j]      = INTT_{q_j}(t[b][j])                          grid items*D
-//   S2  V[b][r][j]   = NTT_{q_idx(r)}(U[b][j] mod q_idx(r)), j != r grid items*R*D
-//   S3  ACC[b][c][r] = sum_j V[b][r][j] (.) key[j][c][idx(r)]       elementwise
-//                      (digit j == r is taken from t[b][j] directly:
+//   S1  U[b][j]      = INTT_{q_j}(t[b][j])                          items*D polys
+//   S2  V[b][y]      = NTT_{q_idx(r)}(U[b][j] mod q_idx(r)), j != r items*D*D polys
+//   S3  ACC[b][c][r] = sum_j op(b,r,j) (.) key[j][c][idx(r)]        elementwise
+//                      (op = V entry, or t[b][j] itself when j == r:
 //                       NTT(INTT(t_j)) == t_j)
-//   S4  ACC[b][c][D] = INTT_{q_k}(ACC[b][c][D])                     grid items*2
+//   S4  ACC[b][c][D] = INTT_{q_k}(ACC[b][c][D])                     items*2 polys
 //   S5  w = NTT_{q_i}(round/convert(ACC[b][c][D]));
-//       result[b][c][i] += (ACC[b][c][i] - w) * msf_i  (mod q_i)    grid items*2*D
+//       result[b][c][i] += (ACC[b][c][i] - w) * msf_i  (mod q_i)    items*2*D polys
 //
-// idx(r) = r for r < D and K-1 (the special prime) for r == D.  Every stage
-// output is canonical in [0,q), so the result is the unique value the
-// reference pipeline produces.
+// idx(r) = r for r < D and K-1 (the special prime) for r == D.  y enumerates
+// the D*D (r, j) pairs with j != r: y = r*(D-1) + (j < r ? j : j-1) for r < D,
+// y = D*(D-1) + j for r == D.  Every stage output is canonical in [0,q), so the
+// result is the unique value the reference pipeline produces.  The four
+// transform stages are the persistent TMA-fed kernels of ntt_block.cuh.
 #include "launch.h"
 
 namespace hb {
 
+HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
+    return r < D ? r * (D - 1) + (j < r ? j : j - 1) : D * (D - 1) + j;
+}
+
 // ---- S1 -------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_intt1(KsDev ks, const uint64_t* t_target, uint64_t* U) {
-    extern __shared__ __align__(1024) uint64_t sm[];
-    const uint32_t j = blockIdx.x % ks.D;
-    const ModTab tab = ks.tabs[j];
-    const size_t off = (size_t)blockIdx.x * C::N;
-    ntt_inv_block<C>(sm, t_target + off, U + off, XfIdent(), OfStore1(), tab);
+struct JobIntt1 {
+    KsDev ks;
+    uint64_t* U;
+    HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
+    HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
+    HB_D OfWords of(uint32_t item) const { return OfWords{U + (size_t)item * C::N}; }
+};
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_ks_intt1(const __grid_constant__ CUtensorMap tmap, const JobIntt1<C> job,
+                                                    uint32_t n_items) {
+    ntt_persistent<C, false>(&tmap, job, n_items);
 }
 
 // ---- S2 -------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_ntt1(KsDev ks, const uint64_t* U, uint64_t* V) {
-    extern __shared__ __align__(1024) uint64_t sm[];
-    const uint32_t j = blockIdx.x % ks.D;
-    const uint32_t r = (blockIdx.x / ks.D) % ks.R;
-    const uint32_t b = blockIdx.x / (ks.D * ks.R);
-    if (j == r) return;  // S3 reads t_target for this digit
-    const uint32_t idx = (r == ks.D) ? ks.K - 1 : r;
-    const ModTab tab = ks.tabs[idx];
-    XfReduce xf = {tab.q, tab.mu};
-    ntt_fwd_block<C>(sm, U + ((size_t)b * ks.D + j) * C::N, V + (size_t)blockIdx.x * C::N, xf,
-                     OfStore16(), tab);
+struct JobNtt1 {
+    KsDev ks;
+    uint64_t* V;
+    HB_D void decode(uint32_t item, uint32_t& b, uint32_t& r, uint32_t& j) const {
+        const uint32_t D = ks.D, per = D * D;
+        b = item / per;
+        const uint32_t y = item % per;
+        if (y < D * (D - 1)) {
+            r = y / (D - 1);
+            const uint32_t jj = y % (D - 1);
+            j = jj + (jj >= r ? 1 : 0);
+        } else {
+            r = D;
+            j = y - D * (D - 1);
+        }
+    }
+    HB_D uint32_t idx_of(uint32_t item) const {
+        uint32_t b, r, j;
+        decode(item, b, r, j);
+        return r == ks.D ? ks.K - 1 : r;
+    }
+    HB_D uint32_t src_row(uint32_t item) const {
+        uint32_t b, r, j;
+        decode(item, b, r, j);
+        return (b * ks.D + j) * (C::N / 16);
+    }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[idx_of(item)]; }
+    HB_D XfReduce xf(uint32_t item) const {
+        const ModTab& t = ks.tabs[idx_of(item)];
+        return XfReduce{t.q, t.mu};
+    }
+    HB_D OfRows of(uint32_t item) const { return OfRows{V + (size_t)item * C::N}; }
+};
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap, const JobNtt1<C> job,
+                                                   uint32_t n_items) {
+    ntt_persistent<C, true>(&tmap, job, n_items);
 }
 
 // ---- S3 -------------------------------------------------------------------
@@ -59,7 +97,7 @@ k_ks_mac(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __rest
     uint64_t a0[2] = {0, 0}, a1[2] = {0, 0};
     for (uint32_t j = 0; j < ks.D; ++j) {
         const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
-                                      : V + (((size_t)b * ks.R + r) * ks.D + j) * N;
+                                      : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
         const uint64_t* k0 = ks.keys + (((size_t)j * 2 + 0) * ks.K + idx) * N;
         const uint64_t* k1 = ks.keys + (((size_t)j * 2 + 1) * ks.K + idx) * N;
         uint64_t x[2], u[2], w[2];
@@ -79,11 +117,19 @@ k_ks_mac(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __rest
 
 // ---- S4 -------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_intt2(KsDev ks, uint64_t* ACC) {
-    extern __shared__ __align__(1024) uint64_t sm[];
-    const ModTab tab = ks.tabs[ks.K - 1];
-    uint64_t* p = ACC + ((size_t)blockIdx.x * ks.R + ks.D) * C::N;  // [b][c][D]
-    ntt_inv_block<C>(sm, p, p, XfIdent(), OfStore1(), tab);
+struct JobIntt2 {
+    KsDev ks;
+    uint64_t* ACC;
+    HB_D uint32_t poly(uint32_t item) const { return item * ks.R + ks.D; }   // [b][c][D]
+    HB_D uint32_t src_row(uint32_t item) const { return poly(item) * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t) const { return ks.tabs[ks.K - 1]; }
+    HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
+    HB_D OfWords of(uint32_t item) const { return OfWords{ACC + (size_t)poly(item) * C::N}; }
+};
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_ks_intt2(const __grid_constant__ CUtensorMap tmap, const JobIntt2<C> job,
+                                                    uint32_t n_items) {
+    ntt_persistent<C, false>(&tmap, job, n_items);
 }
 
 // ---- S5 -------------------------------------------------------------------
@@ -93,7 +139,8 @@ struct OfKsFinal {
     const uint64_t* acc;   // ACC[b][c][i]
     uint64_t* result;      // result[b][c][i]
     uint64_t q, msf, msf_p;
-    HB_D void operator()(uint64_t*, uint32_t off, const uint64_t (&v)[16]) const {
+    HB_D void row(uint32_t rw, const uint64_t* v) const {
+        const uint32_t off = rw * 16;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             uint64_t a[2], r[2];
@@ -110,51 +157,81 @@ struct OfKsFinal {
         }
     }
 };
-
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_ntt2(KsDev ks, const uint64_t* ACC, uint64_t* result) {
-    extern __shared__ __align__(1024) uint64_t sm[];
-    const uint32_t i = blockIdx.x % ks.D;
-    const uint32_t bc = blockIdx.x / ks.D;  // b*2 + c
-    const ModTab tab = ks.tabs[i];
-    const uint64_t qk = ks.tabs[ks.K - 1].q;
-    const uint64_t qk_half = qk >> 1;
-    XfKsRound xf = {qk, qk_half, tab.q, tab.mu, tab.q - barrett_reduce64(qk_half, tab.q, tab.mu)};
-    OfKsFinal of = {ACC + ((size_t)bc * ks.R + i) * C::N,
-                    result + ((size_t)bc * ks.D + i) * C::N, tab.q, ks.msf[i], ks.msf_p[i]};
-    ntt_fwd_block<C>(sm, ACC + ((size_t)bc * ks.R + ks.D) * C::N, nullptr, xf, of, tab);
+struct JobNtt2 {
+    KsDev ks;
+    const uint64_t* ACC;
+    uint64_t* result;
+    HB_D uint32_t src_row(uint32_t item) const { return ((item / ks.D) * ks.R + ks.D) * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
+    HB_D XfKsRound xf(uint32_t item) const {
+        const ModTab& t = ks.tabs[item % ks.D];
+        const uint64_t qk = ks.tabs[ks.K - 1].q, h = qk >> 1;
+        return XfKsRound{qk, h, t.q, t.mu, t.q - barrett_reduce64(h, t.q, t.mu)};
+    }
+    HB_D OfKsFinal of(uint32_t item) const {
+        const uint32_t i = item % ks.D, bc = item / ks.D;
+        return OfKsFinal{ACC + ((size_t)bc * ks.R + i) * C::N, result + ((size_t)bc * ks.D + i) * C::N,
+                         ks.tabs[i].q, ks.msf[i], ks.msf_p[i]};
+    }
+};
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap, const JobNtt2<C> job,
+                                                   uint32_t n_items) {
+    ntt_persistent<C, true>(&tmap, job, n_items);
 }
 
-template <class C>
-static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target,
-                            uint64_t items, uint64_t* U, uint64_t* V, uint64_t* ACC,
-                            cudaStream_t st) {
-    const size_t smem = (size_t)C::N * sizeof(uint64_t);
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_ks_intt1<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_ks_ntt1<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_ks_intt2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    if ((e = cudaFuncSetAttribute(k_ks_ntt2<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-    k_ks_intt1<C><<<(unsigned)(items * ks.D), C::NT, smem, st>>>(ks, t_target, U);
-    k_ks_ntt1<C><<<(unsigned)(items * ks.R * ks.D), C::NT, smem, st>>>(ks, U, V);
-    dim3 g(C::N / 512, ks.R, (unsigned)items);
-    k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
-    k_ks_intt2<C><<<(unsigned)(items * 2), C::NT, smem, st>>>(ks, ACC);
-    k_ks_ntt2<C><<<(unsigned)(items * 2 * ks.D), C::NT, smem, st>>>(ks, ACC, result);
+size_t ks_scratch_words_per_item(const KsDev& ks) {
+    const size_t n = (size_t)1 << ks.logn;
+    return ((size_t)ks.D + (size_t)ks.D * ks.D + 2 * (size_t)ks.R) * n;
+}
+
+template <class K, class J>
+static cudaError_t run_persistent(K kern, int threads, size_t smem, const CUtensorMap& tmap, const J& job,
+                                  uint64_t n_items, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<persistent_grid((const void*)kern, threads, smem, n_items), threads, smem, st>>>(tmap, job,
+                                                                                           (uint32_t)n_items);
     return cudaGetLastError();
 }
 
-cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target,
-                            uint64_t items, uint64_t* U, uint64_t* V, uint64_t* ACC,
-                            cudaStream_t st) {
+template <class C>
+static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
+                            uint64_t* scratch, cudaStream_t st, int* launches) {
+    const size_t smem = ntt_smem_bytes<C>();
+    const uint64_t D = ks.D, R = ks.R;
+    uint64_t* U = scratch;
+    uint64_t* V = U + items * D * C::N;
+    uint64_t* ACC = V + items * D * D * C::N;
+    CUtensorMap m_t, m_u, m_acc;
+    cudaError_t e;
+    if ((e = make_poly_tmap(&m_t, t_target, items * D, C::LOGN))) return e;
+    if ((e = make_poly_tmap(&m_u, U, items * D, C::LOGN))) return e;
+    if ((e = make_poly_tmap(&m_acc, ACC, items * 2 * R, C::LOGN))) return e;
+    if ((e = run_persistent(k_ks_intt1<C>, C::NT, smem, m_t, JobIntt1<C>{ks, U}, items * D, st))) return e;
+    if ((e = run_persistent(k_ks_ntt1<C>, C::NT, smem, m_u, JobNtt1<C>{ks, V}, items * D * D, st))) return e;
+    dim3 g(C::N / 512, ks.R, (unsigned)items);
+    k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
+    if ((e = cudaGetLastError())) return e;
+    if ((e = run_persistent(k_ks_intt2<C>, C::NT, smem, m_acc, JobIntt2<C>{ks, ACC}, items * 2, st))) return e;
+    if ((e = run_persistent(k_ks_ntt2<C>, C::NT, smem, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, st)))
+        return e;
+    if (launches) *launches = 5;
+    return cudaSuccess;
+}
+
+cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
+                            uint64_t* scratch, cudaStream_t st, int* launches) {
+    if (launches) *launches = 0;
     if (items == 0) return cudaSuccess;
     if (items > 65535) return cudaErrorInvalidValue;  // gridDim.z of the MAC stage
     switch (ks.logn) {
-        case 10: return ks_chunk<NttCfg<10, 4>>(ks, result, t_target, items, U, V, ACC, st);
-        case 11: return ks_chunk<NttCfg<11, 4>>(ks, result, t_target, items, U, V, ACC, st);
-        case 12: return ks_chunk<NttCfg<12, 4>>(ks, result, t_target, items, U, V, ACC, st);
-        case 13: return ks_chunk<NttCfg<13, 4>>(ks, result, t_target, items, U, V, ACC, st);
-        case 14: return ks_chunk<NttCfg<14, 4>>(ks, result, t_target, items, U, V, ACC, st);
+        case 10: return ks_chunk<NttCfg<10, 4>>(ks, result, t_target, items, scratch, st, launches);
+        case 11: return ks_chunk<NttCfg<11, 4>>(ks, result, t_target, items, scratch, st, launches);
+        case 12: return ks_chunk<NttCfg<12, 4>>(ks, result, t_target, items, scratch, st, launches);
+        case 13: return ks_chunk<NttCfg<13, 4>>(ks, result, t_target, items, scratch, st, launches);
+        case 14: return ks_chunk<NttCfg<14, 5>>(ks, result, t_target, items, scratch, st, launches);
         default: return cudaErrorInvalidValue;
     }
 }

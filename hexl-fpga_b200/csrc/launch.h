@@ -1,6 +1,7 @@
 // launch.h -- host-callable launchers of the sm_100a kernels (internal; the
 // public boundary is include/hexl_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -19,22 +20,36 @@ struct KsDev {
     const uint64_t* msf_p;  // [K] Shoup factors of msf
 };
 
-// variant: 0 = LOGE 4 (16 words / thread), 1 = LOGE 5 (32 words / thread)
-cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch,
-                           int variant, cudaStream_t st);
-cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch,
-                           int variant, cudaStream_t st);
+bool ntt_shape_supported(uint32_t logn);
+// number of 16-byte entries of the packed forward / inverse twiddle tables
+size_t packed_fwd_entries(uint32_t logn, int variant);
+size_t packed_inv_entries(uint32_t logn, int variant);
+// interleave caller tables (roots/precon and/or inv_roots/precon_inv, n words
+// each, device pointers) into the packed per-group layout of ntt_core.cuh
+cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
+                                 TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
+                                 TwPair* inv_out, cudaStream_t st);
+
+// 2-D tensor map over `polys` polynomials of 2^logn words starting at `base`
+// (rows of 16 words, 128-byte swizzle), for the kernels' TMA loads
+cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn);
+
+// variant: 0 = 16 words / thread, 1 = 32 words / thread (N = 16384 only)
+cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
+                           cudaStream_t st);
+cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
+                           cudaStream_t st);
 
 cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op2, uint64_t n,
-                          const uint64_t* moduli, uint64_t n_moduli, uint64_t batch,
-                          int moduli_per_item, cudaStream_t st);
+                          const uint64_t* moduli, uint64_t n_moduli, uint64_t batch, int moduli_per_item,
+                          cudaStream_t st);
 
 // keyswitch stages over a chunk of `items` ciphertexts (scratch layouts in
-// keyswitch_kernels.cu)
-cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target,
-                            uint64_t items, uint64_t* U, uint64_t* V, uint64_t* ACC,
-                            cudaStream_t st);
+// keyswitch_kernels.cu); returns the number of kernel launches in *launches
+size_t ks_scratch_words_per_item(const KsDev& ks);
+cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
+                            uint64_t* scratch, cudaStream_t st, int* launches);
 
-bool ntt_shape_supported(uint32_t logn);
+int persistent_grid(const void* kernel, int threads, size_t smem, uint64_t items);
 
 }  // namespace hb

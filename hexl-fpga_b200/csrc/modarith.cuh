@@ -29,6 +29,14 @@ HB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #endif
 }
 
+HB_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
 // Shoup/Harvey lazy product: w*x - floor(x*wp/2^64)*q  (mod 2^64), in [0,2q)
 // when w < q and wp = floor(w*2^64/q).   tests/test_utils/ntt.hpp:87-101
 HB_HD uint64_t mul_lazy(uint64_t x, uint64_t w, uint64_t wp, uint64_t q) {
@@ -69,6 +77,124 @@ HB_HD void inv_last_bfly(uint64_t& X, uint64_t& Y, uint64_t inv_n,
     Y = y - ((y >= q) ? q : 0);
 }
 
+// ---------------------------------------------------------------------------
+// "fast" arithmetic: any-correct-algorithm path for in-contract inputs.
+//
+// The exact butterflies above reproduce the reference word for word, which only
+// matters for out-of-range inputs (the reference's ALL_MAX test).  When every
+// input word is inside the algorithm's contract the output is the canonical
+// residue, so ANY exact modular algorithm gives the same bits; the kernels
+// check the range while loading and pick per polynomial.  The fast path trims
+// the butterfly from ~28 to ~17-22 SASS instructions:
+//   * Shoup quotient from 3 instead of 4 partial products:
+//       Q'' = y1*p1 + hi32(y0*p1) + hi32(y1*p0)  in {Q-2, Q-1, Q}
+//     so  T'' = w*y - Q''*q  lies in [0, 4q)   (T in [0,2q) for any y < 2^64);
+//   * w*y + Q''*(-q) as one chain of 2 IMAD.WIDE + 4 IMAD (mod 2^64);
+//   * forward: no per-stage correction at all (values grow by < 4q per stage,
+//     bounded by 4q*(LOGN+1) < 2^64 for q < 2^58), one Barrett-style reduction
+//     at the very end;
+//   * inverse: values kept in [0,4q) with a single sign-test correction.
+// ---------------------------------------------------------------------------
+struct FastMod {
+    uint64_t q;
+    uint64_t nq;     // 2^64 - q
+    uint64_t q4;     // 4q
+    uint32_t kmul;   // floor(2^(shift+kb) / q), in (2^31, 2^32)
+    uint32_t shift;  // max(bitlen(q) - 25, 0): (v >> shift) < 2^31 for v < 64q
+    uint32_t kb;     // 56, or bitlen(q)+31 for tiny q
+    uint32_t pad;
+};
+
+HB_HD FastMod make_fastmod(uint64_t q) {
+    FastMod m;
+    m.q = q;
+    m.nq = (uint64_t)0 - q;
+    m.q4 = q << 2;
+    const int bl = 64 - clz64(q);
+    m.shift = bl > 25 ? (uint32_t)(bl - 25) : 0u;
+    m.kb = bl >= 25 ? 56u : (uint32_t)(bl + 31);
+    unsigned __int128 k = (((unsigned __int128)1) << (m.shift + m.kb)) / q;
+    m.kmul = k > 0xffffffffu ? 0xffffffffu : (uint32_t)k;
+    m.pad = 0;
+    return m;
+}
+
+// w*y - Q''*q (mod 2^64) in [0,4q) for ANY y; w < q, wp = floor(w*2^64/q).
+HB_HD uint64_t mul_shoup_approx(uint64_t y, uint64_t w, uint64_t wp, uint64_t nq) {
+    const uint32_t y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32);
+    const uint32_t p0 = (uint32_t)wp, p1 = (uint32_t)(wp >> 32);
+    const uint32_t w0 = (uint32_t)w, w1 = (uint32_t)(w >> 32);
+    const uint32_t n0 = (uint32_t)nq, n1 = (uint32_t)(nq >> 32);
+#if defined(__CUDA_ARCH__)
+    uint64_t c, d, e, t;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(c) : "r"(y0), "r"(p1));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(y1), "r"(p0));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(e) : "r"(y1), "r"(p1));
+    const uint64_t Q = e + (c >> 32) + (d >> 32);
+    const uint32_t Q0 = (uint32_t)Q, Q1 = (uint32_t)(Q >> 32);
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(w0), "r"(y0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(t) : "r"(Q0), "r"(n0));
+    uint32_t t1 = (uint32_t)(t >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(w0), "r"(y1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(w1), "r"(y0));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(Q0), "r"(n1));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(Q1), "r"(n0));
+    return ((uint64_t)t1 << 32) | (uint32_t)t;
+#else
+    (void)w0; (void)w1; (void)n0; (void)n1;
+    const uint64_t Q = (uint64_t)y1 * p1 + (((uint64_t)y0 * p1) >> 32) + (((uint64_t)y1 * p0) >> 32);
+    return w * y + Q * nq;
+#endif
+}
+
+// x - 4q if x >= 4q else x, for x < 2^63 + 4q (one sign test instead of a
+// 64-bit compare).
+HB_HD uint64_t csub(uint64_t x, uint64_t m) {
+    const uint64_t d = x - m;
+    return ((int64_t)d < 0) ? x : d;
+}
+
+// forward, lazy: X' = X + T'', Y' = X + 4q - T''   (no correction; see above)
+HB_HD void fwd_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wp, const FastMod& m) {
+    const uint64_t T = mul_shoup_approx(Y, w, wp, m.nq);
+    const uint64_t x = X;
+    X = x + T;
+    Y = x + m.q4 - T;
+}
+
+// v < 64q  ->  v mod q.  k = floor((v >> shift) * kmul / 2^kb) is floor(v/q) or
+// one or two less (truncation of v and of kmul); two conditional subtractions
+// finish the job.
+HB_HD uint64_t reduce_small_multiple(uint64_t v, const FastMod& m) {
+    const uint32_t vh = (uint32_t)(v >> m.shift);
+    const uint32_t k = (uint32_t)(((uint64_t)vh * m.kmul) >> m.kb);
+    uint64_t r = v - (uint64_t)k * m.q;
+    r = csub(r, m.q << 1);
+    r = csub(r, m.q);
+    return r;
+}
+
+// inverse, values in [0,4q):  X' = (X+Y) csub 4q,  Y' = T''(X + 4q - Y)
+HB_HD void inv_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wp, const FastMod& m) {
+    const uint64_t tx = X + Y;
+    const uint64_t ty = X + m.q4 - Y;
+    X = csub(tx, m.q4);
+    Y = mul_shoup_approx(ty, w, wp, m.nq);
+}
+
+// last inverse stage with the n^-1 scaling, canonical outputs
+HB_HD void inv_last_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t inv_n, uint64_t inv_n_p,
+                              uint64_t inv_n_w, uint64_t inv_n_w_p, const FastMod& m) {
+    const uint64_t tx = X + Y;            // < 8q: fine for the Shoup product
+    const uint64_t ty = X + m.q4 - Y;
+    uint64_t x = mul_shoup_approx(tx, inv_n, inv_n_p, m.nq);   // [0,4q)
+    uint64_t y = mul_shoup_approx(ty, inv_n_w, inv_n_w_p, m.nq);
+    x = csub(x, m.q << 1);
+    y = csub(y, m.q << 1);
+    X = csub(x, m.q);
+    Y = csub(y, m.q);
+}
+
 // x mod q for any x < 2^64 with mu = floor(2^64/q)   (q < 2^63).
 // device/keyswitch/intt1_redu.hpp:36-38 computes the same canonical value.
 HB_HD uint64_t barrett_reduce64(uint64_t x, uint64_t q, uint64_t mu) {
@@ -93,14 +219,6 @@ struct Divisor {
     uint32_t pad;
     uint64_t q;   // the modulus itself
 };
-
-HB_HD int clz64(uint64_t x) {
-#if defined(__CUDA_ARCH__)
-    return __clzll((long long)x);
-#else
-    return x ? __builtin_clzll(x) : 64;
-#endif
-}
 
 HB_HD Divisor make_divisor(uint64_t q) {
     Divisor dv;

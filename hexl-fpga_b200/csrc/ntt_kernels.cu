@@ -1,65 +1,188 @@
 // ntt_kernels.cu -- batched forward / inverse negacyclic NTT kernels (sm_100a).
-// One CTA per polynomial, polynomial resident in shared memory (see
-// ntt_core.cuh).  Replaces device/fwd_ntt.cpp:81-497 and
-// device/inv_ntt.cpp:82-442 of the reference.
+// Persistent CTAs, polynomial resident in shared memory, TMA prefetch of the
+// next polynomial (see ntt_block.cuh).  Replaces device/fwd_ntt.cpp:81-646 and
+// device/inv_ntt.cpp:82-607 of the reference.
+#include <mutex>
+
 #include "launch.h"
 
 namespace hb {
 
+// ---- plain batched transform, in place ------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_ntt_fwd(uint64_t* data, const ModTab tab) {
-    extern __shared__ __align__(1024) uint64_t sm[];
-    uint64_t* poly = data + (size_t)blockIdx.x * C::N;
-    ntt_fwd_block<C>(sm, poly, poly, XfIdent(), OfStore16(), tab);
+struct JobPlain {
+    uint64_t* data;
+    ModTab tab;
+    HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t) const { return tab; }
+    HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
+};
+template <class C>
+struct JobFwd : JobPlain<C> {
+    HB_D OfRows of(uint32_t item) const { return OfRows{this->data + (size_t)item * C::N}; }
+};
+template <class C>
+struct JobInv : JobPlain<C> {
+    HB_D OfWords of(uint32_t item) const { return OfWords{this->data + (size_t)item * C::N}; }
+};
+
+template <class C, bool ASSUME_OK>
+__global__ void __launch_bounds__(C::NT) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap, const JobFwd<C> job,
+                                                   uint32_t n_items) {
+    ntt_persistent<C, true, JobFwd<C>, ASSUME_OK>(&tmap, job, n_items);
+}
+template <class C, bool ASSUME_OK>
+__global__ void __launch_bounds__(C::NT) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
+                                                   uint32_t n_items) {
+    ntt_persistent<C, false, JobInv<C>, ASSUME_OK>(&tmap, job, n_items);
 }
 
+// ---- packed twiddle builder -------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_ntt_inv(uint64_t* data, const ModTab tab) {
-    extern __shared__ __align__(1024) uint64_t sm[];
-    uint64_t* poly = data + (size_t)blockIdx.x * C::N;
-    ntt_inv_block<C>(sm, poly, poly, XfIdent(), OfStore1(), tab);
+__global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
+                                TwPair* __restrict__ fwd_out, const uint64_t* __restrict__ inv_roots,
+                                const uint64_t* __restrict__ precon_inv, TwPair* __restrict__ inv_out) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fwd_out && e < (uint32_t)C::FWD_ENTRIES) {
+        const int s = fwd_pack_src<C>(e);
+        TwPair t = {0, 0};
+        if (s >= 0) t = TwPair{roots[s], precon[s]};
+        fwd_out[e] = t;
+    }
+    if (inv_out && e < (uint32_t)C::INV_ENTRIES) {
+        const int s = inv_pack_src<C>(e);
+        TwPair t = {0, 0};
+        if (s >= 0) t = TwPair{inv_roots[s], precon_inv[s]};
+        inv_out[e] = t;
+    }
 }
 
-template <class C, bool FWD>
+// ---- host side ---------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    const uint64_t rows_per_poly = (1ull << logn) / 16;
+    const uint64_t rows = polys * rows_per_poly;
+    if (rows == 0 || rows >> 32) return cudaErrorInvalidValue;
+    const cuuint64_t gdim[2] = {16, rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {16, (cuuint32_t)(rows_per_poly < 256 ? rows_per_poly : 256)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+int persistent_grid(const void* kernel, int threads, size_t smem, uint64_t items) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    uint64_t g = (uint64_t)sms * per_sm;
+    return (int)(items < g ? items : g);
+}
+
+template <class C, bool FWD, bool ASSUME_OK = false>
 static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch, cudaStream_t st) {
-    auto kern = FWD ? k_ntt_fwd<C> : k_ntt_inv<C>;
-    const size_t smem = (size_t)C::N * sizeof(uint64_t);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    // grid.x is limited to 2^31-1 CTAs; batches beyond that are split.
-    const uint64_t kMaxGrid = 1u << 30;
-    for (uint64_t off = 0; off < batch; off += kMaxGrid) {
-        uint64_t cnt = batch - off < kMaxGrid ? batch - off : kMaxGrid;
-        kern<<<(unsigned)cnt, C::NT, smem, st>>>(data + off * C::N, tab);
+    const size_t smem = ntt_smem_bytes<C>();
+    CUtensorMap tmap;
+    cudaError_t e;
+    // the tensor map's row coordinate is 32 bits: split enormous batches
+    const uint64_t kMaxPolys = ((1ull << 32) - 1) / (C::N / 16);
+    for (uint64_t off = 0; off < batch; off += kMaxPolys) {
+        const uint64_t cnt = batch - off < kMaxPolys ? batch - off : kMaxPolys;
+        uint64_t* base = data + off * C::N;
+        if ((e = make_poly_tmap(&tmap, base, cnt, C::LOGN)) != cudaSuccess) return e;
+        if constexpr (FWD) {
+            auto kern = k_ntt_fwd<C, ASSUME_OK>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            JobFwd<C> job;
+            job.data = base;
+            job.tab = tab;
+            kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt);
+        } else {
+            auto kern = k_ntt_inv<C, ASSUME_OK>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            JobInv<C> job;
+            job.data = base;
+            job.tab = tab;
+            kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt);
+        }
     }
     return cudaGetLastError();
 }
 
-template <bool FWD>
-static cudaError_t dispatch(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch,
-                            int variant, cudaStream_t st) {
-    if (batch == 0) return cudaSuccess;
-    switch (logn) {
-        case 10: return launch_one<NttCfg<10, 4>, FWD>(data, tab, batch, st);
-        case 11: return launch_one<NttCfg<11, 4>, FWD>(data, tab, batch, st);
-        case 12: return launch_one<NttCfg<12, 4>, FWD>(data, tab, batch, st);
-        case 13: return launch_one<NttCfg<13, 4>, FWD>(data, tab, batch, st);
-        case 14:
-            return variant == 1 ? launch_one<NttCfg<14, 5>, FWD>(data, tab, batch, st)
-                                : launch_one<NttCfg<14, 4>, FWD>(data, tab, batch, st);
-        default: return cudaErrorInvalidValue;
+#define HB_DISPATCH_CFG(logn, variant, CALL)                                   \
+    switch (logn) {                                                            \
+        case 10: { using C = NttCfg<10, 4>; CALL; } break;                     \
+        case 11: { using C = NttCfg<11, 4>; CALL; } break;                     \
+        case 12: { using C = NttCfg<12, 4>; CALL; } break;                     \
+        case 13: { using C = NttCfg<13, 4>; CALL; } break;                     \
+        case 14:                                                               \
+            if (((variant) & 1) == 1) { using C = NttCfg<14, 5>; CALL; }       \
+            else { using C = NttCfg<14, 4>; CALL; }                            \
+            break;                                                             \
+        default: break;                                                        \
     }
-}
 
 bool ntt_shape_supported(uint32_t logn) { return logn >= 10 && logn <= 14; }
 
-cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch,
-                           int variant, cudaStream_t st) {
-    return dispatch<true>(data, tab, logn, batch, variant, st);
+size_t packed_fwd_entries(uint32_t logn, int variant) {
+    HB_DISPATCH_CFG(logn, variant, return C::FWD_ENTRIES);
+    return 0;
 }
-cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch,
-                           int variant, cudaStream_t st) {
-    return dispatch<false>(data, tab, logn, batch, variant, st);
+size_t packed_inv_entries(uint32_t logn, int variant) {
+    HB_DISPATCH_CFG(logn, variant, return C::INV_ENTRIES);
+    return 0;
+}
+
+template <class C>
+static cudaError_t pack_one(const uint64_t* roots, const uint64_t* precon, TwPair* fwd_out, const uint64_t* inv_roots,
+                            const uint64_t* precon_inv, TwPair* inv_out, cudaStream_t st) {
+    const int total = C::FWD_ENTRIES > C::INV_ENTRIES ? C::FWD_ENTRIES : C::INV_ENTRIES;
+    k_pack_twiddles<C><<<(total + 255) / 256, 256, 0, st>>>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
+                                 TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
+                                 TwPair* inv_out, cudaStream_t st) {
+    HB_DISPATCH_CFG(logn, variant, return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, st));
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
+                           cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (variant & 2) { HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true, true>(data, tab, batch, st))); }
+    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true>(data, tab, batch, st)));
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
+                           cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    if (variant & 2) { HB_DISPATCH_CFG(logn, variant, return (launch_one<C, false, true>(data, tab, batch, st))); }
+    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, false>(data, tab, batch, st)));
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace hb

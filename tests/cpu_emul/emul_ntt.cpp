@@ -1,8 +1,10 @@
 // emul_ntt.cpp -- TEST INFRASTRUCTURE: replays the CUDA kernels' per-thread
 // pass functions (hexl-fpga_b200/csrc/ntt_core.cuh, compiled as plain C++) on
 // the CPU, one "thread" at a time with a barrier between passes, and compares
-// against the oracle.  Validates the index math / swizzle / twiddle indexing
-// without a GPU.  Built and run by tests/test_cpu_emul.py.
+// against the oracle.  Validates the index math / swizzle / packed-twiddle
+// layout, the exact arithmetic on garbage inputs and the fast arithmetic
+// (approximate Shoup quotient, lazy forward, small-multiple reduction) on
+// in-range inputs, without a GPU.  Built and run by tests/test_cpu_emul.py.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,34 +15,68 @@
 
 using namespace hb;
 
-struct XfIdent {
-    uint64_t operator()(uint64_t x) const { return x; }
-};
-struct OfStore16 {
-    void operator()(uint64_t* dst, uint32_t off, const uint64_t (&v)[16]) const {
-        for (int k = 0; k < 16; ++k) dst[off + k] = v[k];
-    }
-};
-struct OfStore1 {
-    void operator()(uint64_t* dst, uint32_t idx, uint64_t v) const { dst[idx] = v; }
-};
+static uint64_t ident(uint64_t x) { return x; }
 
-template <class C, int P>
-void fwd_heads(std::vector<uint64_t>& sm, const uint64_t* src, const uint64_t* roots,
-               const uint64_t* precon, uint64_t q) {
+template <class C, int P, class A>
+void fwd_mid(std::vector<uint64_t>& sm, const TwPair* tw, const A& a) {
     if constexpr (P < C::NP) {
-        for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
-            fwd_head_pass<C, P>(tid, sm.data(), src, XfIdent(), roots, precon, q, 2 * q);
-        fwd_heads<C, P + 1>(sm, src, roots, precon, q);
+        for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) fwd_head_pass<C, P>(tid, sm.data(), tw, a);
+        fwd_mid<C, P + 1>(sm, tw, a);
     }
 }
-template <class C, int P>
-void inv_heads(std::vector<uint64_t>& sm, uint64_t* dst, const uint64_t* ir,
-               const uint64_t* ip, uint64_t q, const InvScale& sc) {
-    if constexpr (P < C::NP) {
-        for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
-            inv_head_pass<C, P>(tid, sm.data(), dst, OfStore1(), ir, ip, q, 2 * q, sc);
-        inv_heads<C, P + 1>(sm, dst, ir, ip, q, sc);
+template <class C, int P, class A>
+void inv_mid(std::vector<uint64_t>& sm, const TwPair* tw, const A& a) {
+    if constexpr (P < C::NP - 1) {
+        for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) inv_head_pass<C, P>(tid, sm.data(), tw, a);
+        inv_mid<C, P + 1>(sm, tw, a);
+    }
+}
+
+// forward transform of `in` exactly as the kernel sequences it
+template <class C, class A>
+void emul_fwd(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const TwPair* tw, const A& a) {
+    using P0 = FwdPass<C, 0>;
+    std::vector<uint64_t> sm(C::N);
+    for (uint32_t i = 0; i < (uint32_t)C::N; ++i) sm[swz(i)] = in[i];   // what the swizzled TMA load does
+    std::vector<uint64_t> regs((size_t)C::NT * C::E);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
+        head_load<C, P0::R, P0::LS>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
+        fwd_head_compute<C, 0>(tid, &regs[(size_t)tid * C::E], tw, a);
+        head_store<C, P0::R, P0::LS>(tid, sm.data(), &regs[(size_t)tid * C::E]);
+    }
+    fwd_mid<C, 1>(sm, tw, a);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
+        tail_load<C>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
+        uint64_t* v = &regs[(size_t)tid * C::E];
+        fwd_tail_compute<C>(tid, v, tw, a);
+        for (int ri = 0; ri < C::E / 16; ++ri)
+            for (int k = 0; k < 16; ++k) out[(tid + ri * C::NT) * 16 + k] = v[ri * 16 + k];
+    }
+}
+
+template <class C, class A>
+void emul_inv(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const TwPair* tw, const A& a,
+              const InvScale& sc) {
+    using PL = InvPass<C, C::NP - 1>;
+    std::vector<uint64_t> sm(C::N);
+    for (uint32_t i = 0; i < (uint32_t)C::N; ++i) sm[swz(i)] = in[i];
+    std::vector<uint64_t> regs((size_t)C::NT * C::E);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
+        tail_load<C>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
+        inv_tail_compute<C>(tid, &regs[(size_t)tid * C::E], tw, a);
+        tail_store<C>(tid, sm.data(), &regs[(size_t)tid * C::E]);
+    }
+    inv_mid<C, 0>(sm, tw, a);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
+        head_load<C, PL::R, PL::LS>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
+        uint64_t* v = &regs[(size_t)tid * C::E];
+        inv_head_compute<C, C::NP - 1>(tid, v, tw, a, sc);
+        for (int gi = 0; gi < (C::E >> PL::R); ++gi)
+            for (int k = 0; k < (1 << PL::R); ++k) out[inv_last_index<C>(tid, gi, k)] = v[gi * (1 << PL::R) + k];
     }
 }
 
@@ -49,41 +85,66 @@ int run(uint64_t q, int garbage) {
     using C = NttCfg<LOGN, LOGE>;
     const uint64_t n = C::N;
     uint64_t w = ho_min_primitive_root(2 * n, q);
-    std::vector<uint64_t> roots(n), precon(n), ir(n), ip(n), a(n), ref(n), out(n), sm(n);
+    std::vector<uint64_t> roots(n), precon(n), ir(n), ip(n), a(n), ref(n), out(n);
     ho_compute_roots(n, q, w, roots.data(), precon.data(), ir.data(), ip.data());
+    std::vector<TwPair> ftw(C::FWD_ENTRIES), itw(C::INV_ENTRIES);
+    std::vector<int> used_f(n, 0), used_i(n, 0);
+    for (uint32_t e = 0; e < (uint32_t)C::FWD_ENTRIES; ++e) {
+        int s = fwd_pack_src<C>(e);
+        ftw[e] = s < 0 ? TwPair{0, 0} : TwPair{roots[s], precon[s]};
+        if (s >= 0) used_f[s]++;
+    }
+    for (uint32_t e = 0; e < (uint32_t)C::INV_ENTRIES; ++e) {
+        int s = inv_pack_src<C>(e);
+        itw[e] = s < 0 ? TwPair{0, 0} : TwPair{ir[s], ip[s]};
+        if (s >= 0) used_i[s]++;
+    }
+    int cover = 0;
+    for (uint64_t i = 1; i < n; ++i) cover += (used_f[i] != 1) + (used_i[i] != 1);
     ho_splitmix_fill(a.data(), n, 7 + LOGN, garbage ? 0 : q);
     if (garbage == 2) for (auto& x : a) x = ~(uint64_t)0;
-    // forward
-    ref = a;
-    ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
-    fwd_heads<C, 0>(sm, a.data(), roots.data(), precon.data(), q);
-    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
-        fwd_tail_pass<C>(tid, sm.data(), out.data(), OfStore16(), roots.data(), precon.data(), q, 2 * q);
-    int bad = 0;
-    for (uint64_t i = 0; i < n; ++i) bad += out[i] != ref[i];
-    // inverse of the (possibly garbage) input
+    if (garbage == 3) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 4 * q - 1 - (i % 5) : q - 1;  // edge of fwd contract
+    if (garbage == 4) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 2 * q - 1 - (i % 3) : q - 1;  // edge of inv contract
+    ExactArith ex = {q, 2 * q};
+    FastArith fa = {make_fastmod(q)};
     uint64_t inv_n = ho_inv_mod(n % q, q), inv_n_w = ho_mul_mod(inv_n, ir[n - 1], q);
     InvScale sc = {inv_n, ho_mult_factor64(inv_n, q), inv_n_w, ho_mult_factor64(inv_n_w, q)};
+    int bad = 0, badi = 0, badf = -1, badfi = -1;
+    // exact path: always matches the oracle word for word
+    ref = a;
+    ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
+    emul_fwd<C>(a, out, ftw.data(), ex);
+    for (uint64_t i = 0; i < n; ++i) bad += out[i] != ref[i];
+    const bool fwd_in_contract = (garbage == 0 || garbage == 3 || garbage == 4) && fwd_fast_modulus_ok(q, LOGN);
+    if (fwd_in_contract) {
+        emul_fwd<C>(a, out, ftw.data(), fa);
+        badf = 0;
+        for (uint64_t i = 0; i < n; ++i) badf += out[i] != ref[i];
+    }
     ref = a;
     ho_inv_ntt(ref.data(), n, q, ir.data(), ip.data(), inv_n, inv_n_w);
-    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
-        inv_tail_pass<C>(tid, sm.data(), a.data(), XfIdent(), ir.data(), ip.data(), q, 2 * q);
-    inv_heads<C, 0>(sm, out.data(), ir.data(), ip.data(), q, sc);
-    int badi = 0;
+    emul_inv<C>(a, out, itw.data(), ex, sc);
     for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
-    printf("LOGN=%d LOGE=%d q=%llu garbage=%d fwd_mismatch=%d inv_mismatch=%d\n", LOGN, LOGE,
-           (unsigned long long)q, garbage, bad, badi);
-    return bad + badi;
+    const bool inv_in_contract = (garbage == 0 || garbage == 4) && inv_fast_modulus_ok(q);
+    if (inv_in_contract) {
+        emul_inv<C>(a, out, itw.data(), fa, sc);
+        badfi = 0;
+        for (uint64_t i = 0; i < n; ++i) badfi += out[i] != ref[i];
+    }
+    printf("LOGN=%d LOGE=%d q=%llu in=%d exact fwd/inv mismatch=%d/%d fast fwd/inv mismatch=%d/%d pack_cover_err=%d\n",
+           LOGN, LOGE, (unsigned long long)q, garbage, bad, badi, badf, badfi, cover);
+    return bad + badi + (badf > 0 ? badf : 0) + (badfi > 0 ? badfi : 0) + cover;
 }
 
 template <int LOGN, int LOGE>
 int run_all() {
     uint64_t p[2];
     int rc = 0;
-    size_t bits[] = {20, 51, 61};
+    size_t bits[] = {12, 20, 30, 51, 57, 59, 61};
     for (size_t b : bits) {
-        ho_generate_primes(p, 1, b, (size_t)1 << LOGN);
-        for (int g = 0; g < 3; ++g) rc += run<LOGN, LOGE>(p[0], g);
+        if (((size_t)1 << b) < ((size_t)2 << LOGN)) continue;
+        if (ho_generate_primes(p, 1, b, (size_t)1 << LOGN) != 1) continue;
+        for (int g = 0; g < 5; ++g) rc += run<LOGN, LOGE>(p[0], g);
     }
     return rc;
 }
@@ -98,7 +159,26 @@ int main() {
     rc += run_all<14, 5>();
     rc += run_all<13, 5>();
     rc += run_all<12, 5>();
-    // divisor arithmetic
+    // fast-arithmetic unit properties
+    {
+        uint64_t qs[] = {12289, 1073153, 2251799814045697ULL, (1ULL << 57) + 0x1234567ULL * 2 + 1, (1ULL << 60) - 93};
+        uint64_t s = 4242, r[3];
+        int fbad = 0;
+        for (uint64_t q : qs) {
+            FastMod m = make_fastmod(q);
+            for (int it = 0; it < 200000; ++it) {
+                s = ho_splitmix_fill(r, 3, s, 0);
+                uint64_t w = r[0] % q, wp = ho_mult_factor64(w, q), y = it & 1 ? r[1] : r[1] % (60 * q > q ? 60 * q : q);
+                uint64_t t = mul_shoup_approx(y, w, wp, m.nq);
+                if (t >= 4 * q || t % q != ho_mul_mod(w, y % q, q)) ++fbad;
+                uint64_t v = (q < (1ULL << 58)) ? r[2] % (60 * q) : r[2] % q;
+                if (reduce_small_multiple(v, m) != v % q) ++fbad;
+            }
+        }
+        printf("fast arithmetic property failures=%d\n", fbad);
+        rc += fbad;
+    }
+    // divisor arithmetic (dyadic kernel)
     uint64_t qs[] = {1, 2, 10, 20, 1000003, 2251799814045697ULL, (1ULL << 63) + 5, ~0ULL};
     uint64_t s = 99;
     std::vector<uint64_t> r(4);
