@@ -186,16 +186,22 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
     if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "ntt_fwd: modulus must be in [2, 2^62)");
     if (batch == 0) return 0;
     const int variant = g_ntt_variant.load();
-    hb::TwPair* packed = nullptr;
-    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20), (void**)&packed);
-    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: twiddle scratch");
-    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr,
+    // per-stream scratch: [0,512K) packed forward twiddles, [512K,1M) packed
+    // inverse twiddles, then two deferred lists of 1 + batch words
+    uint8_t* scratch = nullptr;
+    const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20) + 2 * list_bytes, (void**)&scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: scratch");
+    hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch);
+    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (1u << 20));
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr, list,
                                  (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack twiddles");
     hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn);
-    e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, variant, (cudaStream_t)stream);
+    int launches = 1;
+    e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd launch");
-    g_launches += 2;
+    g_launches += launches;
     return 0;
 }
 
@@ -214,18 +220,21 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
         return fail(HEXL_B200_EINVAL, "ntt_inv: inv_n / inv_n_w must be reduced mod q");
     if (batch == 0) return 0;
     const int variant = g_ntt_variant.load();
-    hb::TwPair* packed = nullptr;
-    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20), (void**)&packed);
-    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: twiddle scratch");
-    // second half of the scratch, so a forward and an inverse call may be queued back to back
-    packed += (1u << 19) / sizeof(hb::TwPair);
+    uint8_t* scratch = nullptr;
+    const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20) + 2 * list_bytes, (void**)&scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: scratch");
+    // second halves, so a forward and an inverse call may be queued back to back
+    hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch + (1u << 19));
+    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (1u << 20) + list_bytes);
     e = hb::launch_pack_twiddles((uint32_t)logn, variant, nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed,
-                                 (cudaStream_t)stream);
+                                 list, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack twiddles");
     hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn);
-    e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, variant, (cudaStream_t)stream);
+    int launches = 1;
+    e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv launch");
-    g_launches += 2;
+    g_launches += launches;
     return 0;
 }
 
@@ -323,7 +332,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     for (uint64_t i = 0; i < K && e == cudaSuccess; ++i) {
         const uint64_t* d = d_raw + i * 4 * n;
         hb::TwPair* pk = p->d_packed + i * (fe + ie);
-        e = hb::launch_pack_twiddles((uint32_t)logn, ks_variant, d, d + n, pk, d + 2 * n, d + 3 * n, pk + fe, 0);
+        e = hb::launch_pack_twiddles((uint32_t)logn, ks_variant, d, d + n, pk, d + 2 * n, d + 3 * n, pk + fe, nullptr, 0);
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(d_raw);
@@ -340,6 +349,10 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         return cleanup(cuda_fail(e, "upload divisors"));
     g_h2d += (K * 4 * n + D * 2 * K * n + 2 * K) * 8;
 
+    p->dev.fast_ok = 1;
+    for (uint64_t i = 0; i < K; ++i)
+        if (!h_tabs[i].fwd_fast_ok || !h_tabs[i].inv_fast_ok) p->dev.fast_ok = 0;
+    p->dev.pad = 0;
     p->dev.logn = (uint32_t)logn;
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;

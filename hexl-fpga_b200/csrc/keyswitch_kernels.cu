@@ -35,12 +35,12 @@ struct JobIntt1 {
     HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
-    HB_D OfWords of(uint32_t item) const { return OfWords{U + (size_t)item * C::N}; }
+    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{U + (size_t)item * C::N}; }
 };
-template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_intt1(const __grid_constant__ CUtensorMap tmap, const JobIntt1<C> job,
-                                                    uint32_t n_items) {
-    ntt_persistent<C, false>(&tmap, job, n_items);
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT) k_ks_intt1(const __grid_constant__ CUtensorMap tmap,
+        const __grid_constant__ CUtensorMap smap, const JobIntt1<C> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, false, MODE>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S2 -------------------------------------------------------------------
@@ -76,12 +76,14 @@ struct JobNtt1 {
         const ModTab& t = ks.tabs[idx_of(item)];
         return XfReduce{t.q, t.mu};
     }
-    HB_D OfRows of(uint32_t item) const { return OfRows{V + (size_t)item * C::N}; }
+    HB_D OfRows of(uint32_t item, const CUtensorMap* smap) const {
+        return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
+    }
 };
-template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap, const JobNtt1<C> job,
-                                                   uint32_t n_items) {
-    ntt_persistent<C, true>(&tmap, job, n_items);
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
+        const __grid_constant__ CUtensorMap smap, const JobNtt1<C> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S3 -------------------------------------------------------------------
@@ -124,12 +126,12 @@ struct JobIntt2 {
     HB_D uint32_t src_row(uint32_t item) const { return poly(item) * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t) const { return ks.tabs[ks.K - 1]; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
-    HB_D OfWords of(uint32_t item) const { return OfWords{ACC + (size_t)poly(item) * C::N}; }
+    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{ACC + (size_t)poly(item) * C::N}; }
 };
-template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_intt2(const __grid_constant__ CUtensorMap tmap, const JobIntt2<C> job,
-                                                    uint32_t n_items) {
-    ntt_persistent<C, false>(&tmap, job, n_items);
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT) k_ks_intt2(const __grid_constant__ CUtensorMap tmap,
+        const __grid_constant__ CUtensorMap smap, const JobIntt2<C> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, false, MODE>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S5 -------------------------------------------------------------------
@@ -139,7 +141,8 @@ struct OfKsFinal {
     const uint64_t* acc;   // ACC[b][c][i]
     uint64_t* result;      // result[b][c][i]
     uint64_t q, msf, msf_p;
-    HB_D void row(uint32_t rw, const uint64_t* v) const {
+    template <class C>
+    HB_D void store(uint32_t rw, const uint64_t* v) const {
         const uint32_t off = rw * 16;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -169,30 +172,31 @@ struct JobNtt2 {
         const uint64_t qk = ks.tabs[ks.K - 1].q, h = qk >> 1;
         return XfKsRound{qk, h, t.q, t.mu, t.q - barrett_reduce64(h, t.q, t.mu)};
     }
-    HB_D OfKsFinal of(uint32_t item) const {
+    HB_D OfKsFinal of(uint32_t item, const CUtensorMap*) const {
         const uint32_t i = item % ks.D, bc = item / ks.D;
         return OfKsFinal{ACC + ((size_t)bc * ks.R + i) * C::N, result + ((size_t)bc * ks.D + i) * C::N,
                          ks.tabs[i].q, ks.msf[i], ks.msf_p[i]};
     }
 };
-template <class C>
-__global__ void __launch_bounds__(C::NT) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap, const JobNtt2<C> job,
-                                                   uint32_t n_items) {
-    ntt_persistent<C, true>(&tmap, job, n_items);
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap,
+        const __grid_constant__ CUtensorMap smap, const JobNtt2<C> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }
 
 size_t ks_scratch_words_per_item(const KsDev& ks) {
     const size_t n = (size_t)1 << ks.logn;
-    return ((size_t)ks.D + (size_t)ks.D * ks.D + 2 * (size_t)ks.R) * n;
+    // U + V + ACC, plus room for the deferred list of stage S1 (D entries and the count)
+    return ((size_t)ks.D + (size_t)ks.D * ks.D + 2 * (size_t)ks.R) * n + ks.D + 1;
 }
 
 template <class K, class J>
-static cudaError_t run_persistent(K kern, int threads, size_t smem, const CUtensorMap& tmap, const J& job,
-                                  uint64_t n_items, cudaStream_t st) {
+static cudaError_t run_persistent(K kern, int threads, size_t smem, const CUtensorMap& tmap, const CUtensorMap& smap,
+                                  const J& job, uint64_t n_items, uint32_t* list, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<persistent_grid((const void*)kern, threads, smem, n_items), threads, smem, st>>>(tmap, job,
-                                                                                           (uint32_t)n_items);
+    kern<<<persistent_grid((const void*)kern, threads, smem, n_items), threads, smem, st>>>(tmap, smap, job,
+                                                                                           (uint32_t)n_items, list);
     return cudaGetLastError();
 }
 
@@ -204,20 +208,39 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     uint64_t* U = scratch;
     uint64_t* V = U + items * D * C::N;
     uint64_t* ACC = V + items * D * D * C::N;
-    CUtensorMap m_t, m_u, m_acc;
+    CUtensorMap m_t, m_u, m_acc, m_vs;
     cudaError_t e;
     if ((e = make_poly_tmap(&m_t, t_target, items * D, C::LOGN))) return e;
     if ((e = make_poly_tmap(&m_u, U, items * D, C::LOGN))) return e;
     if ((e = make_poly_tmap(&m_acc, ACC, items * 2 * R, C::LOGN))) return e;
-    if ((e = run_persistent(k_ks_intt1<C>, C::NT, smem, m_t, JobIntt1<C>{ks, U}, items * D, st))) return e;
-    if ((e = run_persistent(k_ks_ntt1<C>, C::NT, smem, m_u, JobNtt1<C>{ks, V}, items * D * D, st))) return e;
+    if ((e = make_poly_tmap(&m_vs, V, items * D * D, C::LOGN, 32))) return e;   // staged stores of S2
+    uint32_t* list = reinterpret_cast<uint32_t*>(ACC + items * 2 * R * C::N);
+    int nl = 0;
+    if (ks.fast_ok) {
+        // S1 sees caller data: vote + deferred exact pass; the later stages read
+        // words this pipeline produced (reduced by their load transforms)
+        if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<C, kFastVote>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt1<C, kFastTrust>, C::NT, smem, m_u, m_vs, JobNtt1<C>{ks, V}, items * D * D, list, st))) return e;
+        nl += 3;
+    } else {
+        if ((e = run_persistent(k_ks_intt1<C, kExactAll>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt1<C, kExactAll>, C::NT, smem, m_u, m_vs, JobNtt1<C>{ks, V}, items * D * D, list, st))) return e;
+        nl += 2;
+    }
     dim3 g(C::N / 512, ks.R, (unsigned)items);
     k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
-    if ((e = run_persistent(k_ks_intt2<C>, C::NT, smem, m_acc, JobIntt2<C>{ks, ACC}, items * 2, st))) return e;
-    if ((e = run_persistent(k_ks_ntt2<C>, C::NT, smem, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, st)))
-        return e;
-    if (launches) *launches = 5;
+    if (ks.fast_ok) {
+        if ((e = run_persistent(k_ks_intt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+    } else {
+        if ((e = run_persistent(k_ks_intt2<C, kExactAll>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt2<C, kExactAll>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+    }
+    nl += 3;
+    if (launches) *launches = nl;
     return cudaSuccess;
 }
 

@@ -13,6 +13,8 @@ namespace hb {
 // the device-resident constants a plan owns.
 struct KsDev {
     uint32_t logn, D, K, R;
+    uint32_t fast_ok;       // every modulus admits the fast arithmetic (q < 2^58)
+    uint32_t pad;
     const ModTab* tabs;     // [K]
     const Divisor* divs;    // [K]
     const uint64_t* keys;   // [D][2][K][N]  == k_switch_keys[j][(c*K+i)*N + l]
@@ -28,17 +30,21 @@ size_t packed_inv_entries(uint32_t logn, int variant);
 // each, device pointers) into the packed per-group layout of ntt_core.cuh
 cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
                                  TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
-                                 TwPair* inv_out, cudaStream_t st);
+                                 TwPair* inv_out, uint32_t* zero_count, cudaStream_t st);
 
 // 2-D tensor map over `polys` polynomials of 2^logn words starting at `base`
 // (rows of 16 words, 128-byte swizzle), for the kernels' TMA loads
-cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn);
+// box_rows = 0: the load box (min(256, rows per polynomial)); 32: the per-warp store box
+cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn,
+                           uint32_t box_rows = 0);
 
-// variant: 0 = 16 words / thread, 1 = 32 words / thread (N = 16384 only)
+// variant bit 0: 32 words / thread at N = 16384 (else 16); bit 1: trust the
+// caller about the input range (no vote).  `list`: 1 + batch words of device
+// scratch, word 0 zero on entry (the deferred list of out-of-contract items).
 cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
-                           cudaStream_t st);
+                           uint32_t* list, cudaStream_t st, int* launches);
 cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
-                           cudaStream_t st);
+                           uint32_t* list, cudaStream_t st, int* launches);
 
 cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op2, uint64_t n,
                           const uint64_t* moduli, uint64_t n_moduli, uint64_t batch, int moduli_per_item,

@@ -163,15 +163,13 @@ HB_HD void fwd_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wp, cons
 }
 
 // v < 64q  ->  v mod q.  k = floor((v >> shift) * kmul / 2^kb) is floor(v/q) or
-// one or two less (truncation of v and of kmul); two conditional subtractions
-// finish the job.
+// one less: the truncations of v and kmul lose less than 2^-22 of the quotient,
+// so r = v - k*q lies in [0, 2q) and one conditional subtraction finishes.
 HB_HD uint64_t reduce_small_multiple(uint64_t v, const FastMod& m) {
     const uint32_t vh = (uint32_t)(v >> m.shift);
     const uint32_t k = (uint32_t)(((uint64_t)vh * m.kmul) >> m.kb);
-    uint64_t r = v - (uint64_t)k * m.q;
-    r = csub(r, m.q << 1);
-    r = csub(r, m.q);
-    return r;
+    const uint64_t r = v - (uint64_t)k * m.q;
+    return csub(r, m.q);
 }
 
 // inverse, values in [0,4q):  X' = (X+Y) csub 4q,  Y' = T''(X + 4q - Y)

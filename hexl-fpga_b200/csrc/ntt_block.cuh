@@ -45,12 +45,26 @@ struct XfKsRound {
 };
 
 // ---- output functors ----
-struct OfRows {  // forward: 16 contiguous words of row `row` -> 8 x 16-byte stores
-    uint64_t* dst;
-    HB_D void row(uint32_t r, const uint64_t* v) const {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) st2(dst + r * 16 + 2 * c, v[2 * c], v[2 * c + 1]);
-    }
+// Shared-memory plan of a transform CTA:
+//   [ W: N words, the polynomial ][ staging: one 4 KiB slice per warp ][ mbarrier ]
+// The staging slices exist when they fit (kStagedStore): forward results then
+// leave through per-warp TMA tensor stores (coalesced by the copy engine)
+// instead of 16-byte stores at a 128-byte lane stride.
+template <class C>
+struct SmemPlan {
+    static constexpr bool kStagedStore = ((size_t)C::N * 8 + (size_t)(C::NT / 32) * 4096 + 64) <= 227u * 1024u;
+    static constexpr uint32_t STAGE_WORDS = kStagedStore ? (C::NT / 32) * 512 : 0;
+    static constexpr uint32_t BAR_WORD = C::N + STAGE_WORDS;
+    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2) * 8;
+};
+
+// forward output: the 16 contiguous words of one row per thread
+struct OfRows {
+    uint64_t* dst;               // direct path: polynomial base in global memory
+    const CUtensorMap* smap;     // staged path: store map (box 16 words x 32 rows, 128B swizzle)
+    uint32_t row0;               //   first tensor-map row of the output polynomial
+    template <class C>
+    HB_D void store(uint32_t row, const uint64_t* v) const;
 };
 struct OfWords {  // inverse: one word at its natural index (coalesced along lo)
     uint64_t* dst;
@@ -94,6 +108,16 @@ HB_D void tma_load_rows(void* smem_dst, const CUtensorMap* map, uint64_t* bar, u
         : "memory");
 }
 
+// 2-D tensor TMA store of one staged box back to global memory (bulk async group)
+HB_D void tma_store_rows(const CUtensorMap* map, const void* smem_src, uint32_t row) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
+                 "r"(smem_u32(smem_src)), "r"(0), "r"(row)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all earlier bulk stores of this thread have finished READING shared memory
+HB_D void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // One polynomial = N/16 rows of 128 bytes; a TMA box holds at most 256 rows.
 template <class C>
 struct TmaGeom {
@@ -133,10 +157,32 @@ struct Prefetch {
         if (row != kNoPrefetch) {
             uint64_t* W = smem_poly<C>();
             fence_proxy_async();
-            issue_poly_load<C>(W, map, W + C::N, row);
+            issue_poly_load<C>(W, map, W + SmemPlan<C>::BAR_WORD, row);
         }
     }
 };
+
+template <class C>
+HB_D void OfRows::store(uint32_t row, const uint64_t* v) const {
+    if constexpr (SmemPlan<C>::kStagedStore) {
+        // rows of a warp are consecutive: stage them in the warp's slice (same
+        // chunk swizzle as the polynomial buffer) and let one lane hand the
+        // 4 KiB box to the TMA store engine
+        const uint32_t lane = threadIdx.x & 31u;
+        uint64_t* slice = smem_poly<C>() + C::N + (threadIdx.x >> 5) * 512;
+        if (lane == 0) tma_store_wait_read();   // previous box of this slice has left
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_rows(smap, slice, row0 + row);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st2(dst + row * 16 + 2 * c, v[2 * c], v[2 * c + 1]);
+    }
+}
 
 // ---------------------------------------------------------------------------
 // forward transform of the polynomial in W
@@ -150,57 +196,72 @@ HB_D void fwd_mid_passes(uint32_t tid, uint64_t* W, const TwPair* tw, const A& a
     }
 }
 
-template <class C, class A, class Of>
-HB_D void fwd_rest(uint32_t tid, uint64_t* W, uint64_t* v, const TwPair* tw, const A& a, const Of& of,
-                   const Prefetch& pf) {
+// How a kernel treats the input contract (modarith.cuh):
+//   kFastVote   fast arithmetic; the range check rides on the first barrier and
+//               an out-of-contract polynomial is left untouched and appended to
+//               the deferred list for the exact kernel
+//   kFastTrust  fast arithmetic, inputs are in range by construction (internal
+//               keyswitch stages, whose load transform reduces every word)
+//   kExactAll   reference op sequence for every item
+//   kExactList  reference op sequence for the items of the deferred list
+enum NttMode { kFastVote = 0, kFastTrust = 1, kExactAll = 2, kExactList = 3 };
+
+// deferred list: word 0 = count, words 1.. = item indices
+HB_D void defer_item(uint32_t* list, uint32_t item) {
+    const uint32_t slot = atomicAdd(list, 1u);
+    list[1 + slot] = item;
+}
+
+// Range vote on the freshly loaded words: nonzero when some word may be >=
+// bound.  For bounds above 2^32 only the high words are compared (one max per
+// word): conservative -- words in [hi32(bound)*2^32, bound) are flagged too and
+// merely take the exact kernel, which is always right -- and canonical inputs
+// (< q, and bound >= 2q) never trip it.
+template <int E>
+HB_D int out_of_range(const uint64_t* v, uint64_t bound) {
+    const uint32_t bh = (uint32_t)(bound >> 32);
+    if (bh != 0) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) m = max(m, (uint32_t)(v[e] >> 32));
+        return m >= bh;
+    }
+    int bad = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) bad |= (v[e] >= bound);
+    return bad;
+}
+
+// returns false when the polynomial was deferred (fast-vote mode only)
+template <class C, int MODE, class A, class Xf, class Of>
+HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, const Of& of, const Prefetch& pf) {
     using P0 = FwdPass<C, 0>;
-    fwd_head_compute<C, 0>(tid, v, tw, a);
+    const uint32_t tid = threadIdx.x;
+    uint64_t v[C::E];
+    head_load<C, P0::R, P0::LS>(tid, W, v, xf);
+    int bad = 0;
+    if constexpr (MODE == kFastVote) {
+        // forward contract: every word < 4q (tests/test_utils/ntt.cpp:483-486)
+        bad = out_of_range<C::E>(v, t.fm.q4);
+    }
+    fwd_head_compute<C, 0>(tid, v, t.ftw, a);
     head_store<C, P0::R, P0::LS>(tid, W, v);
-    __syncthreads();
-    fwd_mid_passes<C, 1>(tid, W, tw, a);
+    if constexpr (MODE == kFastVote) {
+        if (__syncthreads_or(bad)) {   // global memory still holds the untouched input
+            pf.template issue<C>();
+            return false;
+        }
+    } else {
+        __syncthreads();
+    }
+    fwd_mid_passes<C, 1>(tid, W, t.ftw, a);
     tail_load<C>(tid, W, v, XfIdent());
     __syncthreads();        // every word of W is in registers now
     pf.template issue<C>(); // ... so the buffer can take the next polynomial
-    fwd_tail_compute<C>(tid, v, tw, a);
+    fwd_tail_compute<C>(tid, v, t.ftw, a);
 #pragma unroll
-    for (int ri = 0; ri < C::E / 16; ++ri) of.row(tid + ri * C::NT, v + ri * 16);
-}
-
-// reference op sequence for polynomials with out-of-contract words (rare):
-// its own function so its register needs do not leak into the fast path.
-// Re-reads the input from W (nothing has been stored yet).
-template <class C, class Xf, class Of>
-__device__ __noinline__ void fwd_exact_cta(uint64_t* W, const ModTab* t, Xf xf, Of of, Prefetch pf) {
-    using P0 = FwdPass<C, 0>;
-    const uint32_t tid = threadIdx.x;
-    uint64_t v[C::E];
-    head_load<C, P0::R, P0::LS>(tid, W, v, xf);
-    const ExactArith a = {t->q, t->twoq};
-    fwd_rest<C>(tid, W, v, t->ftw, a, of, pf);
-}
-
-// W holds the input (natural order, swizzled rows); output bit-reversed, [0,q)
-template <class C, bool ASSUME_OK, class Xf, class Of>
-HB_D void ntt_fwd_cta(uint64_t* W, const ModTab& t, const Xf& xf, const Of& of, const Prefetch& pf) {
-    using P0 = FwdPass<C, 0>;
-    const uint32_t tid = threadIdx.x;
-    uint64_t v[C::E];
-    head_load<C, P0::R, P0::LS>(tid, W, v, xf);
-    if constexpr (ASSUME_OK) {   // perf-exploration knob: caller guarantees the contract
-        const FastArith a = {t.fm};
-        fwd_rest<C>(tid, W, v, t.ftw, a, of, pf);
-        return;
-    }
-    // forward contract: every word < 4q (tests/test_utils/ntt.cpp:483-486)
-    int bad = 0;
-#pragma unroll
-    for (int e = 0; e < C::E; ++e) bad |= (v[e] >= t.fm.q4);
-    if (__syncthreads_or(bad) != 0 || !t.fwd_fast_ok) {
-        fwd_exact_cta<C>(W, &t, xf, of, pf);
-    } else {
-        const FastArith a = {t.fm};
-        fwd_rest<C>(tid, W, v, t.ftw, a, of, pf);
-    }
+    for (int ri = 0; ri < C::E / 16; ++ri) of.template store<C>(tid + ri * C::NT, v + ri * 16);
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -215,13 +276,27 @@ HB_D void inv_mid_passes(uint32_t tid, uint64_t* W, const TwPair* tw, const A& a
     }
 }
 
-template <class C, class A, class Of>
-HB_D void inv_rest(uint32_t tid, uint64_t* W, uint64_t* v, const ModTab& t, const A& a, const Of& of,
-                   const Prefetch& pf) {
+template <class C, int MODE, class A, class Xf, class Of>
+HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, const Of& of, const Prefetch& pf) {
     using PL = InvPass<C, C::NP - 1>;
+    const uint32_t tid = threadIdx.x;
+    uint64_t v[C::E];
+    tail_load<C>(tid, W, v, xf);
+    int bad = 0;
+    if constexpr (MODE == kFastVote) {
+        // inverse contract: every word < 2q (ntt.cpp:600-606)
+        bad = out_of_range<C::E>(v, t.twoq);
+    }
     inv_tail_compute<C>(tid, v, t.itw, a);
     tail_store<C>(tid, W, v);
-    __syncthreads();
+    if constexpr (MODE == kFastVote) {
+        if (__syncthreads_or(bad)) {
+            pf.template issue<C>();
+            return false;
+        }
+    } else {
+        __syncthreads();
+    }
     inv_mid_passes<C, 0>(tid, W, t.itw, a);
     head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
     __syncthreads();
@@ -231,38 +306,7 @@ HB_D void inv_rest(uint32_t tid, uint64_t* W, uint64_t* v, const ModTab& t, cons
     for (int gi = 0; gi < (C::E >> PL::R); ++gi)
 #pragma unroll
         for (int k = 0; k < (1 << PL::R); ++k) of.word(inv_last_index<C>(tid, gi, k), v[gi * (1 << PL::R) + k]);
-}
-
-template <class C, class Xf, class Of>
-__device__ __noinline__ void inv_exact_cta(uint64_t* W, const ModTab* t, Xf xf, Of of, Prefetch pf) {
-    const uint32_t tid = threadIdx.x;
-    uint64_t v[C::E];
-    tail_load<C>(tid, W, v, xf);
-    const ExactArith a = {t->q, t->twoq};
-    inv_rest<C>(tid, W, v, *t, a, of, pf);
-}
-
-// W holds the input (bit-reversed order); output natural order, [0,q)
-template <class C, bool ASSUME_OK, class Xf, class Of>
-HB_D void ntt_inv_cta(uint64_t* W, const ModTab& t, const Xf& xf, const Of& of, const Prefetch& pf) {
-    const uint32_t tid = threadIdx.x;
-    uint64_t v[C::E];
-    tail_load<C>(tid, W, v, xf);
-    if constexpr (ASSUME_OK) {
-        const FastArith a = {t.fm};
-        inv_rest<C>(tid, W, v, t, a, of, pf);
-        return;
-    }
-    // inverse contract: every word < 2q (ntt.cpp:600-606)
-    int bad = 0;
-#pragma unroll
-    for (int e = 0; e < C::E; ++e) bad |= (v[e] >= t.twoq);
-    if (__syncthreads_or(bad) != 0 || !t.inv_fast_ok) {
-        inv_exact_cta<C>(W, &t, xf, of, pf);
-    } else {
-        const FastArith a = {t.fm};
-        inv_rest<C>(tid, W, v, t, a, of, pf);
-    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -271,40 +315,58 @@ HB_D void ntt_inv_cta(uint64_t* W, const ModTab& t, const Xf& xf, const Of& of, 
 // Job concept:
 //   uint32_t src_row(item)            first tensor-map row of the item's input
 //   const ModTab& mod(item)
-//   Xf xf(item), Of of(item)
-template <class C, bool FWD, class Job, bool ASSUME_OK = false>
-HB_D void ntt_persistent(const CUtensorMap* tmap, const Job& job, uint32_t n_items) {
+//   Xf xf(item), Of of(item, store_map)
+// `list`: the deferred list (written in kFastVote, read in kExactList mode).
+template <class C, bool FWD, int MODE, class Job>
+HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
+                         uint32_t* list) {
     // The 128-byte TMA swizzle needs the buffer 1024-byte aligned; the dynamic
     // shared window of a kernel without static shared memory starts aligned.
     uint64_t* W = smem_poly<C>();
-    uint64_t* bar = W + C::N;
+    uint64_t* bar = W + SmemPlan<C>::BAR_WORD;
     const uint32_t tid = threadIdx.x;
+    if constexpr (MODE == kExactList) n_items = list[0];
+    auto item_of = [&](uint32_t i) -> uint32_t {
+        if constexpr (MODE == kExactList) return list[1 + i];
+        return i;
+    };
     if (tid == 0) {
         if (smem_u32(W) & 1023u) __trap();
         mbar_init(bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
-    uint32_t item = blockIdx.x;
-    if (tid == 0 && item < n_items) issue_poly_load<C>(W, tmap, bar, job.src_row(item));
+    uint32_t i = blockIdx.x;
+    if (tid == 0 && i < n_items) issue_poly_load<C>(W, tmap, bar, job.src_row(item_of(i)));
     uint32_t parity = 0;
-    for (; item < n_items; item += gridDim.x) {
-        const uint32_t next = item + gridDim.x;
+    for (; i < n_items; i += gridDim.x) {
+        const uint32_t item = item_of(i);
+        const uint32_t next = i + gridDim.x;
         Prefetch pf;
         pf.map = tmap;
-        pf.row = (tid == 0 && next < n_items) ? job.src_row(next) : kNoPrefetch;
+        pf.row = (tid == 0 && next < n_items) ? job.src_row(item_of(next)) : kNoPrefetch;
         mbar_wait(bar, parity);
         parity ^= 1;
-        if constexpr (FWD)
-            ntt_fwd_cta<C, ASSUME_OK>(W, job.mod(item), job.xf(item), job.of(item), pf);
-        else
-            ntt_inv_cta<C, ASSUME_OK>(W, job.mod(item), job.xf(item), job.of(item), pf);
+        const ModTab& t = job.mod(item);
+        bool done;
+        if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+            const FastArith a = {t.fm};
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else {
+            const ExactArith a = {t.q, t.twoq};
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        }
+        if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
     }
+    // staged TMA stores read shared memory asynchronously: drain before exit
+    if (FWD && SmemPlan<C>::kStagedStore && (tid & 31u) == 0) tma_store_wait_read();
 }
 
 template <class C>
 constexpr size_t ntt_smem_bytes() {
-    return (size_t)C::N * 8 + 16 /* mbarrier */;
+    return SmemPlan<C>::BYTES;
 }
 
 }  // namespace hb

@@ -19,30 +19,35 @@ struct JobPlain {
 };
 template <class C>
 struct JobFwd : JobPlain<C> {
-    HB_D OfRows of(uint32_t item) const { return OfRows{this->data + (size_t)item * C::N}; }
+    HB_D OfRows of(uint32_t item, const CUtensorMap* smap) const {
+        return OfRows{this->data + (size_t)item * C::N, smap, item * (C::N / 16)};
+    }
 };
 template <class C>
 struct JobInv : JobPlain<C> {
-    HB_D OfWords of(uint32_t item) const { return OfWords{this->data + (size_t)item * C::N}; }
+    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
 };
 
-template <class C, bool ASSUME_OK>
-__global__ void __launch_bounds__(C::NT) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap, const JobFwd<C> job,
-                                                   uint32_t n_items) {
-    ntt_persistent<C, true, JobFwd<C>, ASSUME_OK>(&tmap, job, n_items);
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap,
+                                                   const __grid_constant__ CUtensorMap smap, const JobFwd<C> job,
+                                                   uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }
-template <class C, bool ASSUME_OK>
+template <class C, int MODE>
 __global__ void __launch_bounds__(C::NT) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
-                                                   uint32_t n_items) {
-    ntt_persistent<C, false, JobInv<C>, ASSUME_OK>(&tmap, job, n_items);
+                                                   uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, false, MODE>(&tmap, nullptr, job, n_items, list);
 }
 
 // ---- packed twiddle builder -------------------------------------------------
 template <class C>
 __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
                                 TwPair* __restrict__ fwd_out, const uint64_t* __restrict__ inv_roots,
-                                const uint64_t* __restrict__ precon_inv, TwPair* __restrict__ inv_out) {
+                                const uint64_t* __restrict__ precon_inv, TwPair* __restrict__ inv_out,
+                                uint32_t* __restrict__ zero_count) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (zero_count && e == 0) *zero_count = 0;   // reset the deferred list of the call that follows
     if (fwd_out && e < (uint32_t)C::FWD_ENTRIES) {
         const int s = fwd_pack_src<C>(e);
         TwPair t = {0, 0};
@@ -75,7 +80,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn) {
+cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return cudaErrorNotSupported;
     const uint64_t rows_per_poly = (1ull << logn) / 16;
@@ -83,7 +88,8 @@ cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, u
     if (rows == 0 || rows >> 32) return cudaErrorInvalidValue;
     const cuuint64_t gdim[2] = {16, rows};
     const cuuint64_t gstride[1] = {128};
-    const cuuint32_t box[2] = {16, (cuuint32_t)(rows_per_poly < 256 ? rows_per_poly : 256)};
+    if (box_rows == 0) box_rows = (uint32_t)(rows_per_poly < 256 ? rows_per_poly : 256);
+    const cuuint32_t box[2] = {16, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -101,34 +107,56 @@ int persistent_grid(const void* kernel, int threads, size_t smem, uint64_t items
     return (int)(items < g ? items : g);
 }
 
-template <class C, bool FWD, bool ASSUME_OK = false>
-static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch, cudaStream_t st) {
+template <class C, bool FWD, int MODE>
+static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap, uint64_t* base, const ModTab& tab,
+                               uint64_t cnt, uint32_t* list, cudaStream_t st) {
     const size_t smem = ntt_smem_bytes<C>();
-    CUtensorMap tmap;
     cudaError_t e;
-    // the tensor map's row coordinate is 32 bits: split enormous batches
-    const uint64_t kMaxPolys = ((1ull << 32) - 1) / (C::N / 16);
-    for (uint64_t off = 0; off < batch; off += kMaxPolys) {
-        const uint64_t cnt = batch - off < kMaxPolys ? batch - off : kMaxPolys;
-        uint64_t* base = data + off * C::N;
-        if ((e = make_poly_tmap(&tmap, base, cnt, C::LOGN)) != cudaSuccess) return e;
-        if constexpr (FWD) {
-            auto kern = k_ntt_fwd<C, ASSUME_OK>;
-            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            JobFwd<C> job;
-            job.data = base;
-            job.tab = tab;
-            kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt);
-        } else {
-            auto kern = k_ntt_inv<C, ASSUME_OK>;
-            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            JobInv<C> job;
-            job.data = base;
-            job.tab = tab;
-            kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt);
-        }
+    if constexpr (FWD) {
+        auto kern = k_ntt_fwd<C, MODE>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        JobFwd<C> job;
+        job.data = base;
+        job.tab = tab;
+        kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, smap, job, (uint32_t)cnt,
+                                                                                       list);
+    } else {
+        auto kern = k_ntt_inv<C, MODE>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        JobInv<C> job;
+        job.data = base;
+        job.tab = tab;
+        kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt, list);
     }
     return cudaGetLastError();
+}
+
+// `list`: device scratch of 1 + batch words whose first word is zero on entry
+// (launch_pack_twiddles resets it); `trust` skips the input-range vote.
+template <class C, bool FWD>
+static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch, bool trust, uint32_t* list,
+                              cudaStream_t st, int* launches) {
+    CUtensorMap tmap, smap;
+    cudaError_t e;
+    // the tensor map's row coordinate is 32 bits
+    const uint64_t kMaxPolys = ((1ull << 32) - 1) / (C::N / 16);
+    if (batch > kMaxPolys) return cudaErrorInvalidValue;
+    if ((e = make_poly_tmap(&tmap, data, batch, C::LOGN)) != cudaSuccess) return e;
+    if ((e = make_poly_tmap(&smap, data, batch, C::LOGN, 32)) != cudaSuccess) return e;
+    const bool fast = FWD ? tab.fwd_fast_ok : tab.inv_fast_ok;
+    if (!fast) {
+        *launches += 1;
+        return launch_mode<C, FWD, kExactAll>(tmap, smap, data, tab, batch, list, st);
+    }
+    if (trust) {
+        *launches += 1;
+        return launch_mode<C, FWD, kFastTrust>(tmap, smap, data, tab, batch, list, st);
+    }
+    if ((e = launch_mode<C, FWD, kFastVote>(tmap, smap, data, tab, batch, list, st))) return e;
+    // polynomials with out-of-contract words (none in normal use): exact pass
+    // over the deferred list; exits at once when the list is empty
+    *launches += 2;
+    return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
 }
 
 #define HB_DISPATCH_CFG(logn, variant, CALL)                                   \
@@ -157,31 +185,33 @@ size_t packed_inv_entries(uint32_t logn, int variant) {
 
 template <class C>
 static cudaError_t pack_one(const uint64_t* roots, const uint64_t* precon, TwPair* fwd_out, const uint64_t* inv_roots,
-                            const uint64_t* precon_inv, TwPair* inv_out, cudaStream_t st) {
+                            const uint64_t* precon_inv, TwPair* inv_out, uint32_t* zero_count, cudaStream_t st) {
     const int total = C::FWD_ENTRIES > C::INV_ENTRIES ? C::FWD_ENTRIES : C::INV_ENTRIES;
-    k_pack_twiddles<C><<<(total + 255) / 256, 256, 0, st>>>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out);
+    k_pack_twiddles<C><<<(total + 255) / 256, 256, 0, st>>>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out,
+                                                            zero_count);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
                                  TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
-                                 TwPair* inv_out, cudaStream_t st) {
-    HB_DISPATCH_CFG(logn, variant, return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, st));
+                                 TwPair* inv_out, uint32_t* zero_count, cudaStream_t st) {
+    HB_DISPATCH_CFG(logn, variant,
+                    return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, zero_count, st));
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
-                           cudaStream_t st) {
+                           uint32_t* list, cudaStream_t st, int* launches) {
     if (batch == 0) return cudaSuccess;
-    if (variant & 2) { HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true, true>(data, tab, batch, st))); }
-    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true>(data, tab, batch, st)));
+    const bool trust = (variant & 2) != 0;
+    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true>(data, tab, batch, trust, list, st, launches)));
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
-                           cudaStream_t st) {
+                           uint32_t* list, cudaStream_t st, int* launches) {
     if (batch == 0) return cudaSuccess;
-    if (variant & 2) { HB_DISPATCH_CFG(logn, variant, return (launch_one<C, false, true>(data, tab, batch, st))); }
-    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, false>(data, tab, batch, st)));
+    const bool trust = (variant & 2) != 0;
+    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, false>(data, tab, batch, trust, list, st, launches)));
     return cudaErrorInvalidValue;
 }
 
