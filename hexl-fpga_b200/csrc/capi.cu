@@ -102,6 +102,7 @@ struct hexl_b200_ks_plan {
     hb::KsDev dev{};
     hb::TwPair* d_packed = nullptr; // K * (FWD_ENTRIES + INV_ENTRIES) packed twiddles
     uint64_t* d_keys = nullptr;     // D * 2 * K * n
+    hb::TwPair* d_keys_sh = nullptr;  // same, with Shoup factors (fast path)
     uint64_t* d_small = nullptr;    // msf, msf_p
     hb::ModTab* d_tabs = nullptr;
     hb::Divisor* d_divs = nullptr;
@@ -357,13 +358,22 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;
     p->dev.msf = p->d_small; p->dev.msf_p = p->d_small + K;
+    p->dev.keys_sh = nullptr;
+    if (p->dev.fast_ok) {
+        if ((e = cudaMalloc(&p->d_keys_sh, D * 2 * K * n * sizeof(hb::TwPair))))
+            return cleanup(cuda_fail(e, "cudaMalloc Shoup keys"));
+        if ((e = hb::launch_ks_prepare_keys(p->dev, p->d_keys_sh, 0)) || (e = cudaDeviceSynchronize()))
+            return cleanup(cuda_fail(e, "prepare keys"));
+        p->dev.keys_sh = p->d_keys_sh;
+        g_launches += 1;
+    }
     *out = p;
     return 0;
 }
 
 int hexl_b200_ks_plan_destroy(hexl_b200_ks_plan* p) {
     if (!p) return 0;
-    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_small);
+    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_keys_sh); cudaFree(p->d_small);
     cudaFree(p->d_tabs); cudaFree(p->d_divs); cudaFree(p->ws);
     delete p;
     return 0;

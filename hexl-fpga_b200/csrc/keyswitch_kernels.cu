@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(C::NT) k_ks_ntt1(const __grid_constant__ CUten
 
 // ---- S3 -------------------------------------------------------------------
 // grid: (N / (256*2), R, items); each thread owns two adjacent coefficients.
+// Generic version (any modulus): exact 2-by-1 division per product.
 __global__ void __launch_bounds__(256)
 k_ks_mac(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
          uint64_t* __restrict__ ACC) {
@@ -117,6 +118,59 @@ k_ks_mac(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __rest
     st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, a1[0], a1[1]);
 }
 
+// Fast version (all moduli < 2^58): the keys carry their Shoup factors
+// (keys_sh[j][c][i][l] = {key mod q_i, floor(key * 2^64 / q_i)}), every product is
+// the 9-IMAD approximate Shoup product in [0,4q), the D products are summed
+// without reduction (< 4q*D <= 60q) and reduced once.
+__global__ void __launch_bounds__(256)
+k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
+              uint64_t* __restrict__ ACC) {
+    const uint32_t N = 1u << ks.logn;
+    const uint32_t l = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const uint32_t r = blockIdx.y, b = blockIdx.z;
+    const uint32_t idx = (r == ks.D) ? ks.K - 1 : r;
+    const FastMod fm = ks.tabs[idx].fm;
+    uint64_t a0[2] = {0, 0}, a1[2] = {0, 0};
+    for (uint32_t j = 0; j < ks.D; ++j) {
+        const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
+                                      : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
+        const TwPair* k0 = ks.keys_sh + (((size_t)j * 2 + 0) * ks.K + idx) * N + l;
+        const TwPair* k1 = ks.keys_sh + (((size_t)j * 2 + 1) * ks.K + idx) * N + l;
+        uint64_t x[2];
+        ld2(op + l, x[0], x[1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const TwPair u = ldpair(k0 + e), w = ldpair(k1 + e);
+            a0[e] += mul_shoup_approx(x[e], u.w, u.wp, fm.nq);
+            a1[e] += mul_shoup_approx(x[e], w.w, w.wp, fm.nq);
+        }
+    }
+    st2(ACC + (((size_t)b * 2 + 0) * ks.R + r) * N + l, reduce_small_multiple(a0[0], fm),
+        reduce_small_multiple(a0[1], fm));
+    st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, reduce_small_multiple(a1[0], fm),
+        reduce_small_multiple(a1[1], fm));
+}
+
+// one-time per plan: keys_sh from the raw keys
+__global__ void k_ks_prepare_keys(KsDev ks, TwPair* __restrict__ out) {
+    const uint32_t N = 1u << ks.logn;
+    const size_t total = (size_t)ks.D * 2 * ks.K * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)((e / N) % ks.K);
+        const uint64_t q = ks.tabs[i].q;
+        const uint64_t k = ks.keys[e] % q;
+        TwPair t;
+        t.w = k;
+        t.wp = (uint64_t)((((unsigned __int128)k) << 64) / q);
+        out[e] = t;
+    }
+}
+
+cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st) {
+    k_ks_prepare_keys<<<148 * 4, 256, 0, st>>>(ks, out);
+    return cudaGetLastError();
+}
+
 // ---- S4 -------------------------------------------------------------------
 template <class C>
 struct JobIntt2 {
@@ -141,22 +195,41 @@ struct OfKsFinal {
     const uint64_t* acc;   // ACC[b][c][i]
     uint64_t* result;      // result[b][c][i]
     uint64_t q, msf, msf_p;
+    HB_D uint64_t finish(uint64_t a, uint64_t w, uint64_t r) const {
+        const uint64_t d = sub_mod(a, w, q);
+        uint64_t o = mul_lazy(d, msf, msf_p, q);
+        o -= (o >= q) ? q : 0;
+        return add_mod(r, o, q);
+    }
     template <class C>
     HB_D void store(uint32_t rw, const uint64_t* v) const {
-        const uint32_t off = rw * 16;
+        if constexpr (SmemPlan<C>::kStagedStore) {
+            // transpose through the warp's staging slice so that acc / result are
+            // touched with coalesced 8-byte accesses (lanes along the words)
+            const uint32_t lane = threadIdx.x & 31u;
+            uint64_t* slice = smem_poly<C>() + C::N + (threadIdx.x >> 5) * 512;
+            __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint64_t a[2], r[2];
-            ld2(acc + off + 2 * c, a[0], a[1]);
-            ld2(result + off + 2 * c, r[0], r[1]);
+            for (int c = 0; c < 8; ++c)
+                st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
+            __syncwarp();
+            const uint32_t base = (rw - lane) * 16;   // first word of the warp's 32 rows
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const uint64_t d = sub_mod(a[e], v[2 * c + e], q);
-                uint64_t o = mul_lazy(d, msf, msf_p, q);
-                o -= (o >= q) ? q : 0;
-                r[e] = add_mod(r[e], o, q);
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t w = lane + 32u * i;
+                const uint32_t row = w >> 4, ch = (w >> 1) & 7u;
+                const uint64_t x = slice[row * 16 + ((ch ^ (row & 7u)) << 1) + (w & 1u)];
+                result[base + w] = finish(acc[base + w], x, result[base + w]);
             }
-            st2(result + off + 2 * c, r[0], r[1]);
+        } else {
+            const uint32_t off = rw * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint64_t a[2], r[2];
+                ld2(acc + off + 2 * c, a[0], a[1]);
+                ld2(result + off + 2 * c, r[0], r[1]);
+                st2(result + off + 2 * c, finish(a[0], v[2 * c], r[0]), finish(a[1], v[2 * c + 1], r[1]));
+            }
         }
     }
 };
@@ -230,7 +303,10 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         nl += 2;
     }
     dim3 g(C::N / 512, ks.R, (unsigned)items);
-    k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
+    if (ks.fast_ok && ks.keys_sh)
+        k_ks_mac_fast<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
+    else
+        k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
     if (ks.fast_ok) {
         if ((e = run_persistent(k_ks_intt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;

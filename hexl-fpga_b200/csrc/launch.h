@@ -18,6 +18,7 @@ struct KsDev {
     const ModTab* tabs;     // [K]
     const Divisor* divs;    // [K]
     const uint64_t* keys;   // [D][2][K][N]  == k_switch_keys[j][(c*K+i)*N + l]
+    const TwPair* keys_sh;  // same index space: {key mod q_i, Shoup factor}; null if !fast_ok
     const uint64_t* msf;    // [K] modswitch_factors[i] mod q_i
     const uint64_t* msf_p;  // [K] Shoup factors of msf
 };
@@ -53,6 +54,7 @@ cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op
 // keyswitch stages over a chunk of `items` ciphertexts (scratch layouts in
 // keyswitch_kernels.cu); returns the number of kernel launches in *launches
 size_t ks_scratch_words_per_item(const KsDev& ks);
+cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);
 cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
                             uint64_t* scratch, cudaStream_t st, int* launches);
 
