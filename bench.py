@@ -222,9 +222,9 @@ def run_ours(args, rank, world, local_rank):
         tab_np = np.stack([t.roots, t.precon, t.inv_roots, t.precon_inv])
     tabs = gpu_tensor(tab_np, dev) if rank == 0 else torch.empty((4, N), dtype=torch.int64, device=dev)
     scal = torch.tensor([t.inv_n, t.inv_n_w] if rank == 0 else [0, 0], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(tabs, 0)
-        dist.broadcast(scal, 0)
+    from sharding import replicate
+
+    replicate([tabs, scal])        # NCCL broadcast over NVLink when world > 1
     roots, precon, inv_roots, precon_inv = tabs[0], tabs[1], tabs[2], tabs[3]
     inv_n, inv_n_w = int(scal[0]), int(scal[1])
 
@@ -292,6 +292,7 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": peak_src, "traffic": ncu_traffic("ntt_fwd"),
                      "algorithmic_bytes_per_launch": BATCH * NTT_BYTES, "launch_s": fwd_s},
         "clocks": clocks,
+        "kernel_variant": "persistent TMA-fed CTAs, 32 words/thread, fast lazy path with range vote + deferred exact list",
     }
     if rank == 0:
         line.update(extras(args, hb, ob, dev, hbm_peak, world))

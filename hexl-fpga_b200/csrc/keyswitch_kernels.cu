@@ -121,34 +121,50 @@ k_ks_mac(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __rest
 // Fast version (all moduli < 2^58): the keys carry their Shoup factors
 // (keys_sh[j][c][i][l] = {key mod q_i, floor(key * 2^64 / q_i)}), every product is
 // the 9-IMAD approximate Shoup product in [0,4q), the D products are summed
-// without reduction (< 4q*D <= 60q) and reduced once.
+// without reduction (< 4q*D <= 60q) and reduced once.  Each thread serves
+// kMacItems items with one load of the key words: the keys (29 MB per key set
+// at D=7, K=8) would otherwise be re-read from L2 for every item.
+constexpr int kMacItems = 4;
 __global__ void __launch_bounds__(256)
 k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
-              uint64_t* __restrict__ ACC) {
+              uint64_t* __restrict__ ACC, uint32_t items) {
     const uint32_t N = 1u << ks.logn;
     const uint32_t l = (blockIdx.x * 256 + threadIdx.x) * 2;
-    const uint32_t r = blockIdx.y, b = blockIdx.z;
+    const uint32_t r = blockIdx.y, b0 = blockIdx.z * kMacItems;
     const uint32_t idx = (r == ks.D) ? ks.K - 1 : r;
     const FastMod fm = ks.tabs[idx].fm;
-    uint64_t a0[2] = {0, 0}, a1[2] = {0, 0};
+    uint64_t a0[kMacItems][2], a1[kMacItems][2];
+#pragma unroll
+    for (int it = 0; it < kMacItems; ++it) a0[it][0] = a0[it][1] = a1[it][0] = a1[it][1] = 0;
     for (uint32_t j = 0; j < ks.D; ++j) {
-        const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
-                                      : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
         const TwPair* k0 = ks.keys_sh + (((size_t)j * 2 + 0) * ks.K + idx) * N + l;
         const TwPair* k1 = ks.keys_sh + (((size_t)j * 2 + 1) * ks.K + idx) * N + l;
-        uint64_t x[2];
-        ld2(op + l, x[0], x[1]);
+        const TwPair u0 = ldpair(k0), u1 = ldpair(k0 + 1), w0 = ldpair(k1), w1 = ldpair(k1 + 1);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const TwPair u = ldpair(k0 + e), w = ldpair(k1 + e);
-            a0[e] += mul_shoup_approx(x[e], u.w, u.wp, fm.nq);
-            a1[e] += mul_shoup_approx(x[e], w.w, w.wp, fm.nq);
+        for (int it = 0; it < kMacItems; ++it) {
+            const uint32_t b = b0 + it;
+            if (b < items) {
+                const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
+                                              : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
+                uint64_t x0, x1;
+                ld2(op + l, x0, x1);
+                a0[it][0] += mul_shoup_approx(x0, u0.w, u0.wp, fm.nq);
+                a0[it][1] += mul_shoup_approx(x1, u1.w, u1.wp, fm.nq);
+                a1[it][0] += mul_shoup_approx(x0, w0.w, w0.wp, fm.nq);
+                a1[it][1] += mul_shoup_approx(x1, w1.w, w1.wp, fm.nq);
+            }
         }
     }
-    st2(ACC + (((size_t)b * 2 + 0) * ks.R + r) * N + l, reduce_small_multiple(a0[0], fm),
-        reduce_small_multiple(a0[1], fm));
-    st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, reduce_small_multiple(a1[0], fm),
-        reduce_small_multiple(a1[1], fm));
+#pragma unroll
+    for (int it = 0; it < kMacItems; ++it) {
+        const uint32_t b = b0 + it;
+        if (b < items) {
+            st2(ACC + (((size_t)b * 2 + 0) * ks.R + r) * N + l, reduce_small_multiple(a0[it][0], fm),
+                reduce_small_multiple(a0[it][1], fm));
+            st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, reduce_small_multiple(a1[it][0], fm),
+                reduce_small_multiple(a1[it][1], fm));
+        }
+    }
 }
 
 // one-time per plan: keys_sh from the raw keys
@@ -303,9 +319,10 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         nl += 2;
     }
     dim3 g(C::N / 512, ks.R, (unsigned)items);
-    if (ks.fast_ok && ks.keys_sh)
-        k_ks_mac_fast<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
-    else
+    if (ks.fast_ok && ks.keys_sh) {
+        dim3 gf(C::N / 512, ks.R, (unsigned)((items + kMacItems - 1) / kMacItems));
+        k_ks_mac_fast<<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
+    } else
         k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
     if (ks.fast_ok) {
