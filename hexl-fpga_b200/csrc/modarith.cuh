@@ -126,20 +126,34 @@ HB_HD uint64_t mul_shoup_approx(uint64_t y, uint64_t w, uint64_t wp, uint64_t nq
     const uint32_t w0 = (uint32_t)w, w1 = (uint32_t)(w >> 32);
     const uint32_t n0 = (uint32_t)nq, n1 = (uint32_t)(nq >> 32);
 #if defined(__CUDA_ARCH__)
-    uint64_t c, d, e, t;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(c) : "r"(y0), "r"(p1));
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(y1), "r"(p0));
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(e) : "r"(y1), "r"(p1));
-    const uint64_t Q = e + (c >> 32) + (d >> 32);
-    const uint32_t Q0 = (uint32_t)Q, Q1 = (uint32_t)(Q >> 32);
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(w0), "r"(y0));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(t) : "r"(Q0), "r"(n0));
-    uint32_t t1 = (uint32_t)(t >> 32);
+    // Q'' with explicit 32-bit carry chains: keeps the two small additions on the
+    // ALU pipe (ptxas otherwise zero-extends hi32(c) into a register pair to ride
+    // on an IMAD.WIDE addend, i.e. two moves on the busier FMA pipe).
+    uint32_t Q0, Q1, t0, t1;
+    asm("{\n\t"
+        ".reg .u32 c0, c1, d0, d1, e0, e1;\n\t"
+        ".reg .u64 c, d, e, t;\n\t"
+        "mul.wide.u32 c, %4, %7;\n\t"
+        "mul.wide.u32 d, %5, %6;\n\t"
+        "mul.wide.u32 e, %5, %7;\n\t"
+        "mov.b64 {c0, c1}, c;\n\t"
+        "mov.b64 {d0, d1}, d;\n\t"
+        "mov.b64 {e0, e1}, e;\n\t"
+        "add.cc.u32 e0, e0, c1;\n\t"
+        "addc.u32 e1, e1, 0;\n\t"
+        "add.cc.u32 %0, e0, d1;\n\t"
+        "addc.u32 %1, e1, 0;\n\t"
+        "mul.wide.u32 t, %8, %4;\n\t"
+        "mad.wide.u32 t, %0, %9, t;\n\t"
+        "mov.b64 {%2, %3}, t;\n\t"
+        "}"
+        : "=&r"(Q0), "=&r"(Q1), "=r"(t0), "=r"(t1)
+        : "r"(y0), "r"(y1), "r"(p0), "r"(p1), "r"(w0), "r"(n0));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(w0), "r"(y1));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(w1), "r"(y0));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(Q0), "r"(n1));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t1) : "r"(Q1), "r"(n0));
-    return ((uint64_t)t1 << 32) | (uint32_t)t;
+    return ((uint64_t)t1 << 32) | t0;
 #else
     (void)w0; (void)w1; (void)n0; (void)n1;
     const uint64_t Q = (uint64_t)y1 * p1 + (((uint64_t)y0 * p1) >> 32) + (((uint64_t)y1 * p0) >> 32);

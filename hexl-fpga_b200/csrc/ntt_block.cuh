@@ -55,6 +55,7 @@ struct SmemPlan {
     static constexpr bool kStagedStore = ((size_t)C::N * 8 + (size_t)(C::NT / 32) * 4096 + 64) <= 227u * 1024u;
     static constexpr uint32_t STAGE_WORDS = kStagedStore ? (C::NT / 32) * 512 : 0;
     static constexpr uint32_t BAR_WORD = C::N + STAGE_WORDS;
+    static constexpr uint32_t FLAG_WORD = BAR_WORD + 1;   // range-vote flag (fast-vote kernels)
     static constexpr size_t BYTES = (size_t)(BAR_WORD + 2) * 8;
 };
 
@@ -232,6 +233,23 @@ HB_D int out_of_range(const uint64_t* v, uint64_t bound) {
     return bad;
 }
 
+// Block-wide "some word out of range?" without a reduction barrier: warps that
+// saw a bad word raise a shared flag before the pass barrier that is there
+// anyway; everybody reads the flag after it.  Returns true (after clearing the
+// flag for the next polynomial) when the polynomial must be deferred.
+template <class C>
+HB_D void vote_raise(int bad) {
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) smem_poly<C>()[SmemPlan<C>::FLAG_WORD] = 1;
+}
+template <class C>
+HB_D bool vote_read() {
+    uint64_t* flag = smem_poly<C>() + SmemPlan<C>::FLAG_WORD;
+    if (*flag == 0) return false;
+    __syncthreads();                 // everyone has seen it
+    if (threadIdx.x == 0) *flag = 0;
+    return true;
+}
+
 // returns false when the polynomial was deferred (fast-vote mode only)
 template <class C, int MODE, class A, class Xf, class Of>
 HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, const Of& of, const Prefetch& pf) {
@@ -244,15 +262,15 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         // forward contract: every word < 4q (tests/test_utils/ntt.cpp:483-486)
         bad = out_of_range<C::E>(v, t.fm.q4);
     }
+    if constexpr (MODE == kFastVote) vote_raise<C>(bad);
     fwd_head_compute<C, 0>(tid, v, t.ftw, a);
     head_store<C, P0::R, P0::LS>(tid, W, v);
+    __syncthreads();
     if constexpr (MODE == kFastVote) {
-        if (__syncthreads_or(bad)) {   // global memory still holds the untouched input
+        if (vote_read<C>()) {          // global memory still holds the untouched input
             pf.template issue<C>();
             return false;
         }
-    } else {
-        __syncthreads();
     }
     fwd_mid_passes<C, 1>(tid, W, t.ftw, a);
     tail_load<C>(tid, W, v, XfIdent());
@@ -287,15 +305,15 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         // inverse contract: every word < 2q (ntt.cpp:600-606)
         bad = out_of_range<C::E>(v, t.twoq);
     }
+    if constexpr (MODE == kFastVote) vote_raise<C>(bad);
     inv_tail_compute<C>(tid, v, t.itw, a);
     tail_store<C>(tid, W, v);
+    __syncthreads();
     if constexpr (MODE == kFastVote) {
-        if (__syncthreads_or(bad)) {
+        if (vote_read<C>()) {
             pf.template issue<C>();
             return false;
         }
-    } else {
-        __syncthreads();
     }
     inv_mid_passes<C, 0>(tid, W, t.itw, a);
     head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
@@ -333,6 +351,7 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     if (tid == 0) {
         if (smem_u32(W) & 1023u) __trap();
         mbar_init(bar, 1);
+        W[SmemPlan<C>::FLAG_WORD] = 0;
         fence_barrier_init();
     }
     __syncthreads();
