@@ -189,10 +189,14 @@ class KsPlan:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().hexl_b200_ks_plan_destroy(self._h)
+            try:
+                lib().hexl_b200_ks_plan_destroy(self._h)
+            except Exception:      # interpreter shutdown
+                pass
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        self.close()
 
 
 # --------------------------------------------------------------------------

@@ -102,12 +102,20 @@ Tables make_tables(uint64_t n, uint64_t q) {
 Tables tables_from_keyswitch_block(uint64_t n, uint64_t q, const uint64_t* blk) {
     Tables t;
     t.q = q;
+    t.root = 0;  // unknown; not needed
     t.roots.assign(blk + 2 * n, blk + 3 * n);
     t.roots[0] = 1;
     t.inv_roots.assign(n, 0);
-    t.inv_roots[0] = 1;
-    for (uint64_t i = 0; i + 1 < n; ++i) t.inv_roots[i + 1] = blk[i];
-    t.root = 0;  // unknown; not needed
+    // Two layouts of the inverse table are in circulation: the FPGA's 0-based
+    // one (host/src/twiddle-factors.cpp:46-55: first stage twiddle at [0],
+    // [n-1] == 0) and intel-hexl's 1-based one ([0] == 1, what
+    // GetInvRootOfUnityPowers returns).  [0] == 1 can only be the latter.
+    if (blk[0] == 1 && blk[n - 1] != 0) {
+        t.inv_roots.assign(blk, blk + n);
+    } else {
+        t.inv_roots[0] = 1;
+        for (uint64_t i = 0; i + 1 < n; ++i) t.inv_roots[i + 1] = blk[i];
+    }
     finish(t, n);
     return t;
 }
