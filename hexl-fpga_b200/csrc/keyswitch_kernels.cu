@@ -196,7 +196,10 @@ struct JobIntt2 {
     HB_D uint32_t src_row(uint32_t item) const { return poly(item) * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t) const { return ks.tabs[ks.K - 1]; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
-    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{ACC + (size_t)poly(item) * C::N}; }
+    HB_D OfWordsRound of(uint32_t item, const CUtensorMap*) const {
+        const uint64_t qk = ks.tabs[ks.K - 1].q;
+        return OfWordsRound{ACC + (size_t)poly(item) * C::N, qk, qk >> 1};
+    }
 };
 template <class C, int MODE>
 __global__ void __launch_bounds__(C::NT) k_ks_intt2(const __grid_constant__ CUtensorMap tmap,
@@ -216,6 +219,17 @@ struct OfKsFinal {
         uint64_t o = mul_lazy(d, msf, msf_p, q);
         o -= (o >= q) ? q : 0;
         return add_mod(r, o, q);
+    }
+    // pull this thread's share of acc / result (one 128-byte line per row and
+    // array) towards L2 while the transform runs; they come from HBM
+    template <class C>
+    HB_D void prefetch(uint32_t tid) const {
+#pragma unroll
+        for (int ri = 0; ri < C::E / 16; ++ri) {
+            const uint32_t off = (tid + ri * C::NT) * 16;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(acc + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(result + off));
+        }
     }
     template <class C>
     HB_D void store(uint32_t rw, const uint64_t* v) const {
@@ -256,10 +270,10 @@ struct JobNtt2 {
     uint64_t* result;
     HB_D uint32_t src_row(uint32_t item) const { return ((item / ks.D) * ks.R + ks.D) * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
-    HB_D XfKsRound xf(uint32_t item) const {
+    HB_D XfKsConvert xf(uint32_t item) const {
         const ModTab& t = ks.tabs[item % ks.D];
         const uint64_t qk = ks.tabs[ks.K - 1].q, h = qk >> 1;
-        return XfKsRound{qk, h, t.q, t.mu, t.q - barrett_reduce64(h, t.q, t.mu)};
+        return XfKsConvert{t.q, t.mu, t.q - barrett_reduce64(h, t.q, t.mu), (qk < 2 * t.q) ? 1u : 0u};
     }
     HB_D OfKsFinal of(uint32_t item, const CUtensorMap*) const {
         const uint32_t i = item % ks.D, bc = item / ks.D;

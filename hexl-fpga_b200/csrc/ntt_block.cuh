@@ -32,14 +32,16 @@ struct XfReduce {
     uint64_t q, mu;
     HB_D uint64_t operator()(uint64_t x) const { return barrett_reduce64(x, q, mu); }
 };
-// keyswitch rounding + base conversion (device/keyswitch/intt2_redu.hpp:24-51):
-// v = (x + floor(qk/2)) mod qk ; out = (v mod qi + fix_i) mod qi
-struct XfKsRound {
-    uint64_t qk, qk_half, q, mu, fix;
-    HB_D uint64_t operator()(uint64_t x) const {
-        uint64_t v = x + qk_half;
-        v -= (v >= qk) ? qk : 0;
-        uint64_t r = barrett_reduce64(v, q, mu) + fix;
+// keyswitch base conversion after the rounding (device/keyswitch/intt2_redu.hpp:
+// 24-51): the stage-S4 output is already v = (x + floor(qk/2)) mod qk; here
+// out = (v mod qi + fix_i) mod qi.  When qk < 2*qi (same-size primes, the common
+// case) "v mod qi" is one conditional subtraction instead of a Barrett product.
+struct XfKsConvert {
+    uint64_t q, mu, fix;
+    uint32_t small;   // qk < 2*q
+    HB_D uint64_t operator()(uint64_t v) const {
+        uint64_t r = small ? (v - ((v >= q) ? q : 0)) : barrett_reduce64(v, q, mu);
+        r += fix;
         return r - ((r >= q) ? q : 0);
     }
 };
@@ -66,10 +68,22 @@ struct OfRows {
     uint32_t row0;               //   first tensor-map row of the output polynomial
     template <class C>
     HB_D void store(uint32_t row, const uint64_t* v) const;
+    template <class C>
+    HB_D void prefetch(uint32_t) const {}
 };
 struct OfWords {  // inverse: one word at its natural index (coalesced along lo)
     uint64_t* dst;
     HB_D void word(uint32_t idx, uint64_t x) const { dst[idx] = x; }
+};
+// inverse output with the keyswitch rounding v = (x + floor(qk/2)) mod qk
+// (device/keyswitch/intt2_redu.hpp:24-25,43) applied once per special-prime word
+struct OfWordsRound {
+    uint64_t* dst;
+    uint64_t qk, half;
+    HB_D void word(uint32_t idx, uint64_t x) const {
+        const uint64_t v = x + half;
+        dst[idx] = v - ((v >= qk) ? qk : 0);
+    }
 };
 
 // ---------------------------------------------------------------------------
@@ -257,6 +271,7 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     const uint32_t tid = threadIdx.x;
     uint64_t v[C::E];
     head_load<C, P0::R, P0::LS>(tid, W, v, xf);
+    of.template prefetch<C>(tid);     // epilogue operands (keyswitch) towards L2 early
     int bad = 0;
     if constexpr (MODE == kFastVote) {
         // forward contract: every word < 4q (tests/test_utils/ntt.cpp:483-486)

@@ -38,7 +38,7 @@ elif op == "dyadic":
     for _ in range(3):
         hb.dyadic_multiply(res, op1, op2, n, gpu(moduli), M, B)
 elif op == "keyswitch":
-    n, D, K, B = 16384, 7, 8, 64
+    n, D, K, B = 16384, 7, 8, batch if len(sys.argv) > 3 else 64
     p = KsProblem(n, D, K, 1, 51)
     plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
     res = gpu(p.result).repeat(B, 1).contiguous()
