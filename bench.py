@@ -389,6 +389,45 @@ def extras(args, hb, ob, dev, hbm_peak, world):
                      "note": "compute-bound by construction: 72 NTT-equivalents per 4.4 MiB"}}
     del res, tt
     plan.close()
+    # keyswitch end to end through the reference-facing host API (pinned host buffers)
+    eb = 256
+    h_res = torch.empty((eb, 2 * KS_D * N), dtype=torch.int64).pin_memory()
+    h_t = torch.empty((eb, KS_D * N), dtype=torch.int64).pin_memory()
+    for j in range(KS_D):
+        q = int(p.moduli[j])
+        h_t[:, j * N:(j + 1) * N] = torch.randint(0, q, (eb, N), dtype=torch.int64)
+        for c in range(2):
+            o = (c * KS_D + j) * N
+            h_res[:, o:o + N] = torch.randint(0, q, (eb, N), dtype=torch.int64)
+    keys = hb.KeyArray(p.keys)
+    hb.acquire_FPGA_resources()
+    try:
+        def ks_step():
+            hb.set_worksize_KeySwitch(eb)
+            hb.KeySwitch_many(h_res.data_ptr(), h_t.data_ptr(), eb, N, KS_D, KS_K, KS_D + 1, 2, p.moduli, keys, p.msf)
+            hb.KeySwitchCompleted()
+        ks_step()
+        hb.reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            ks_step()
+        ks_e2e_s = (time.perf_counter() - t0) / 2
+        st = hb.get_stats()
+    finally:
+        hb.release_FPGA_resources()
+    out["keyswitch"]["e2e"] = {"value": eb / ks_e2e_s, "unit": "KeySwitch/s", "batch": eb,
+                               "h2d_bytes_per_step": st["h2d_bytes"] // 2, "d2h_bytes_per_step": st["d2h_bytes"] // 2,
+                               "api": "hexl_b200_host_keyswitch (+set_worksize/completed), pinned host buffers"}
+    # CPU baseline for keyswitch: the oracle port (intel-hexl's KeySwitch is unvendored)
+    threads = host_threads()
+    cb = max(2, threads)
+    c_res = np.ascontiguousarray(np.resize(p.result, (cb, 2 * KS_D * N)))
+    c_t = np.ascontiguousarray(np.resize(p.t_target, (cb, KS_D * N)))
+    t0 = time.perf_counter()
+    ob.keyswitch(c_res.reshape(-1), c_t.reshape(-1), N, KS_D, KS_K, p.moduli, p.keys, p.msf, cb, threads=threads)
+    ks_cpu_s = time.perf_counter() - t0
+    out["keyswitch"]["cpu_baseline"] = {"value": cb / ks_cpu_s, "unit": "KeySwitch/s", "cores": threads, "kind": "port",
+                                        "sample": f"{cb} items, oracle restatement (scalar), tables rebuilt per call"}
     # -- dyadic multiply, BASELINE configs[2] --
     moduli = np.array(ob.primes(DY_M, 51, DY_N), dtype=np.uint64)
     op1 = torch.randint(0, int(moduli[0]), (DY_BATCH, 2 * DY_M * DY_N), dtype=torch.int64, device=dev)

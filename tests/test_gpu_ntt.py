@@ -156,3 +156,53 @@ def test_host_api_ntt_intt(acquired):
     one = data[0].copy()
     hb.NTT(one, t.roots, t.precon, q, N)
     assert np.array_equal(one, ob.fwd_ntt(data[0], t))
+
+
+@pytest.mark.parametrize("n,batch", [(16384, 1), (16384, 149), (16384, 300), (1024, 1000), (4096, 777)])
+def test_persistent_loop_remainders(hb, n, batch):
+    """Batches that are not a multiple of the persistent grid (148 CTAs x occupancy),
+    a mix of in-contract and garbage polynomials (deferred exact list), checked
+    against the oracle on a sample of positions and by the inverse round trip."""
+    import torch
+
+    q = ob.primes(1, 51, n)[0]
+    t = ob.Tables(n, q)
+    g = torch.Generator(device="cuda").manual_seed(batch)
+    x = torch.randint(0, q, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    garbage_rows = sorted({0, batch // 2, batch - 1})
+    for r in garbage_rows[1:] if batch > 1 else []:
+        x[r] = torch.from_numpy(ob.splitmix(n, r + 1, 0).view(np.int64)).cuda()
+    x0 = x.clone()
+    hb.ntt_fwd(x, to_gpu(t.roots), to_gpu(t.precon), q, n)
+    for r in sorted(set(garbage_rows + [1 % batch, batch // 3])):
+        assert np.array_equal(to_np(x[r]), ob.fwd_ntt(to_np(x0[r]), t)), r
+    clean = [r for r in range(batch) if r not in garbage_rows[1:]] if batch > 1 else [0]
+    hb.ntt_inv(x, to_gpu(t.inv_roots), to_gpu(t.precon_inv), q, t.inv_n, t.inv_n_w, n)
+    idx = torch.tensor(clean, device="cuda")
+    assert torch.equal(x[idx], x0[idx])
+
+
+def test_empty_batch_and_bad_arguments(hb):
+    import torch
+
+    n, q = 16384, 2251799814045697
+    t = ob.Tables(n, q)
+    x = torch.zeros((1, n), dtype=torch.int64, device="cuda")
+    r, p = to_gpu(t.roots), to_gpu(t.precon)
+    assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, n, 0, None) == 0   # batch 0: no-op
+    assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr() + 8, r.data_ptr(), p.data_ptr(), q, n, 1, None) == -1  # misaligned
+    assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, 32768, 1, None) == -1  # n too large
+    assert hb.lib().hexl_b200_ntt_inv(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, q, 0, n, 1, None) == -1  # inv_n >= q
+
+
+@pytest.mark.parametrize("bits", [58, 59, 61])
+def test_large_moduli_take_the_exact_kernels(hb, bits):
+    """q >= 2^58 has no lazy forward path, q >= 2^60 no fast inverse: kExactAll."""
+    q = ob.primes(1, bits, N)[0]
+    t = ob.Tables(N, q)
+    polys = [stimulus(k, N, q, 3 + i) for i, k in enumerate(["random", "ramp", "garbage"])]
+    got = run_fwd(hb, polys, t)
+    goti = run_inv(hb, polys, t)
+    for i in range(3):
+        assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t))
+        assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t))
