@@ -301,7 +301,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         hexl_b200_ks_plan_destroy(p);
         return rc;
     };
-    const int ks_variant = 1;   // keyswitch_kernels.cu uses NttCfg<14,5> at N = 16384
+    const int ks_variant = hb::ks_variant_for((uint32_t)logn);
     const size_t fe = hb::packed_fwd_entries((uint32_t)logn, ks_variant), ie = hb::packed_inv_entries((uint32_t)logn, ks_variant);
     uint64_t* d_raw = nullptr;      // raw tables, only needed while packing
     if ((e = cudaMalloc(&p->d_packed, K * (fe + ie) * sizeof(hb::TwPair)))) return cleanup(cuda_fail(e, "cudaMalloc tables"));

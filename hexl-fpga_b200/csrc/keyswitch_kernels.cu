@@ -38,7 +38,7 @@ struct JobIntt1 {
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{U + (size_t)item * C::N}; }
 };
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT) k_ks_intt1(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobIntt1<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, false, MODE>(&tmap, &smap, job, n_items, list);
 }
@@ -81,7 +81,7 @@ struct JobNtt1 {
     }
 };
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobNtt1<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }
@@ -202,7 +202,7 @@ struct JobIntt2 {
     }
 };
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT) k_ks_intt2(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt2(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobIntt2<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, false, MODE>(&tmap, &smap, job, n_items, list);
 }
@@ -282,7 +282,7 @@ struct JobNtt2 {
     }
 };
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobNtt2<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }

@@ -24,6 +24,8 @@ struct KsDev {
 };
 
 bool ntt_shape_supported(uint32_t logn);
+// the NttCfg variant the keyswitch kernels are instantiated with (their packed tables must match)
+inline int ks_variant_for(uint32_t logn) { return logn == 14 ? 1 : 0; }
 // number of 16-byte entries of the packed forward / inverse twiddle tables
 size_t packed_fwd_entries(uint32_t logn, int variant);
 size_t packed_inv_entries(uint32_t logn, int variant);

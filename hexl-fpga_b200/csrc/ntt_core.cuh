@@ -44,6 +44,8 @@ template <int LOGN_, int LOGE_>
 struct NttCfg {
     static constexpr int LOGN = LOGN_, LOGE = LOGE_;
     static constexpr int N = 1 << LOGN, E = 1 << LOGE, NT = N / E;
+    // CTAs per SM the register allocation must allow (launch bounds)
+    static constexpr int MIN_CTAS = (NT * 128 <= 32768) ? (65536 / (NT * 128) > 4 ? 4 : 65536 / (NT * 128)) : 1;
     static constexpr int HEAD = LOGN - 4;                 // stages outside the 16-word tail
     static constexpr int NP = (HEAD + LOGE - 1) / LOGE;   // number of head passes
     static constexpr int BASE = HEAD / NP, REM = HEAD % NP;

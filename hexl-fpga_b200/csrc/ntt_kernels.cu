@@ -29,13 +29,13 @@ struct JobInv : JobPlain<C> {
 };
 
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap,
                                                    const __grid_constant__ CUtensorMap smap, const JobFwd<C> job,
                                                    uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }
 template <class C, int MODE>
-__global__ void __launch_bounds__(C::NT) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
                                                    uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, false, MODE>(&tmap, nullptr, job, n_items, list);
 }
@@ -164,7 +164,10 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
         case 10: { using C = NttCfg<10, 4>; CALL; } break;                     \
         case 11: { using C = NttCfg<11, 4>; CALL; } break;                     \
         case 12: { using C = NttCfg<12, 4>; CALL; } break;                     \
-        case 13: { using C = NttCfg<13, 4>; CALL; } break;                     \
+        case 13:                                                               \
+            if (((variant) & 1) == 1) { using C = NttCfg<13, 5>; CALL; }       \
+            else { using C = NttCfg<13, 4>; CALL; }                            \
+            break;                                                             \
         case 14:                                                               \
             if (((variant) & 1) == 1) { using C = NttCfg<14, 5>; CALL; }       \
             else { using C = NttCfg<14, 4>; CALL; }                            \

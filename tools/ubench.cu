@@ -34,6 +34,20 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, uint32_t seed, unsig
             }
             if (KIND == 8) asm volatile("add.cc.u32 %0, %0, %1; addc.u32 %2, %2, %3;" : "+r"(a[i]), "+r"(b) : "r"(c), "r"(seed));
             if (KIND == 9) asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+            if (KIND == 10) {  // IMAD.WIDE + independent 3-input add
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(b), "r"(c));
+                asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(a[i]) : "r"(b), "r"(c));
+            }
+            if (KIND == 11) {  // 1 IMAD.WIDE : 2 adds
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(b), "r"(c));
+                asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+                asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[(i + 1) % ILP]) : "r"(c));
+            }
+            if (KIND == 12) {  // 2 IMAD : 1 LOP3
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(b), "r"(c));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[(i + 3) % ILP]) : "r"(b), "r"(c));
+            }
         }
     }
     unsigned long long t1 = clock64();
@@ -50,6 +64,7 @@ __global__ void __launch_bounds__(1024, 1) kb(uint64_t* out, uint64_t q, uint64_
                                                unsigned long long* cyc) {
     uint64_t X[ILP], Y[ILP];
     const uint64_t twoq = 2 * q;
+    const hb::FastMod fm = hb::make_fastmod(q);
 #pragma unroll
     for (int i = 0; i < ILP; ++i) { X[i] = (threadIdx.x * 77 + i) % q; Y[i] = (threadIdx.x * 131 + 5 * i) % q; }
     __syncthreads();
@@ -59,6 +74,8 @@ __global__ void __launch_bounds__(1024, 1) kb(uint64_t* out, uint64_t q, uint64_
         for (int i = 0; i < ILP; ++i) {
             if (VAR == 0) hb::fwd_bfly(X[i], Y[i], w, wp, q, twoq);
             if (VAR == 1) hb::inv_bfly(X[i], Y[i], w, wp, q, twoq);
+            if (VAR == 3) hb::fwd_bfly_fast(X[i], Y[i], w, wp, fm);
+            if (VAR == 4) hb::inv_bfly_fast(X[i], Y[i], w, wp, fm);
             if (VAR == 2) {  // lazy: no per-stage correction
                 uint64_t T = hb::mul_lazy(Y[i], w, wp, q);
                 uint64_t x = X[i];
@@ -83,9 +100,10 @@ int main() {
     cudaMalloc(&cyc, blocks * 8);
     unsigned long long h[148];
     const char* names[] = {"IMAD.lo32", "IMAD.WIDE.U32", "IMAD.HI.U32", "IADD x2", "LOP3", "mul.hi.u64", "mul.lo.u64",
-                           "IMAD+LOP3 pair", "add.cc+addc", "SHF"};
-    const double ops_per_iter[] = {1, 1, 1, 2, 1, 1, 1, 2, 2, 1};
-    for (int kind = 0; kind < 10; ++kind) {
+                           "IMAD+LOP3 pair", "add.cc+addc", "SHF", "IMAD.WIDE+IADD3", "IMAD.WIDE+add.cc+addc",
+                           "IMAD+IMAD.WIDE+LOP3"};
+    const double ops_per_iter[] = {1, 1, 1, 2, 1, 1, 1, 2, 2, 1, 2, 3, 3};
+    for (int kind = 0; kind < 13; ++kind) {
         for (int rep = 0; rep < 2; ++rep) {
             switch (kind) {
                 case 0: k<0><<<blocks, threads>>>(out, 12345, cyc); break;
@@ -98,6 +116,9 @@ int main() {
                 case 7: k<7><<<blocks, threads>>>(out, 12345, cyc); break;
                 case 8: k<8><<<blocks, threads>>>(out, 12345, cyc); break;
                 case 9: k<9><<<blocks, threads>>>(out, 12345, cyc); break;
+                case 10: k<10><<<blocks, threads>>>(out, 12345, cyc); break;
+                case 11: k<11><<<blocks, threads>>>(out, 12345, cyc); break;
+                case 12: k<12><<<blocks, threads>>>(out, 12345, cyc); break;
             }
             cudaDeviceSynchronize();
         }
@@ -108,8 +129,8 @@ int main() {
     }
     const uint64_t q = 2251799814045697ull, w = 1111640190223217ull;
     const uint64_t wp = (uint64_t)((((unsigned __int128)w) << 64) / q);
-    const char* bn[] = {"fwd_bfly exact", "inv_bfly exact", "fwd_bfly lazy"};
-    for (int v = 0; v < 3; ++v) {
+    const char* bn[] = {"fwd_bfly exact", "inv_bfly exact", "fwd_bfly lazy", "fwd_bfly_fast", "inv_bfly_fast"};
+    for (int v = 0; v < 5; ++v) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         float ms = 0;
         for (int rep = 0; rep < 2; ++rep) {
@@ -117,6 +138,8 @@ int main() {
             if (v == 0) kb<0><<<blocks, threads>>>((uint64_t*)out, q, w, wp, cyc);
             if (v == 1) kb<1><<<blocks, threads>>>((uint64_t*)out, q, w, wp, cyc);
             if (v == 2) kb<2><<<blocks, threads>>>((uint64_t*)out, q, w, wp, cyc);
+            if (v == 3) kb<3><<<blocks, threads>>>((uint64_t*)out, q, w, wp, cyc);
+            if (v == 4) kb<4><<<blocks, threads>>>((uint64_t*)out, q, w, wp, cyc);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             cudaEventElapsedTime(&ms, e0, e1);
         }
