@@ -23,7 +23,7 @@ namespace hexl_b200 {
 static thread_local std::string g_err = "";
 std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
 static std::atomic<int> g_ntt_variant{1};   // 1: 32 words/thread at N=16384 (default), 0: 16
-static std::atomic<int64_t> g_ks_workspace_mb{1024};
+static std::atomic<int64_t> g_ks_workspace_mb{4096};   // scratch budget of one keyswitch plan (180 GB HBM: be generous, fewer chunk tails)
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -139,6 +139,11 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "ks_workspace_mb")) {
         if (value < 16) return fail(HEXL_B200_EINVAL, "ks_workspace_mb must be >= 16");
         g_ks_workspace_mb = value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_mac_items")) {
+        if (value != 4 && value != 8) return fail(HEXL_B200_EINVAL, "ks_mac_items must be 4 or 8");
+        hb::g_ks_mac_items = (int)value;
         return 0;
     }
     return fail(HEXL_B200_EINVAL, "unknown option '%s'", name);

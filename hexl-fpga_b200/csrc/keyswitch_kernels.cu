@@ -23,6 +23,8 @@
 
 namespace hb {
 
+int g_ks_mac_items = 4;   // items served per key load in the MAC stage (4 or 8)
+
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
     return r < D ? r * (D - 1) + (j < r ? j : j - 1) : D * (D - 1) + j;
 }
@@ -124,8 +126,17 @@ k_ks_mac(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __rest
 // without reduction (< 4q*D <= 60q) and reduced once.  Each thread serves
 // kMacItems items with one load of the key words: the keys (29 MB per key set
 // at D=7, K=8) would otherwise be re-read from L2 for every item.
-constexpr int kMacItems = 4;
-__global__ void __launch_bounds__(256)
+
+// 32-byte load of two adjacent {key, Shoup factor} pairs, kept in L2 with
+// priority (the key set is re-read by every group of items while V streams by)
+HB_D void ld_keys2(const TwPair* p, TwPair& a, TwPair& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(a.w), "=l"(a.wp), "=l"(b.w), "=l"(b.wp)
+                 : "l"(p));
+}
+
+template <int kMacItems>
+__global__ void __launch_bounds__(256, kMacItems > 4 ? 2 : 4)
 k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
               uint64_t* __restrict__ ACC, uint32_t items) {
     const uint32_t N = 1u << ks.logn;
@@ -139,7 +150,9 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
     for (uint32_t j = 0; j < ks.D; ++j) {
         const TwPair* k0 = ks.keys_sh + (((size_t)j * 2 + 0) * ks.K + idx) * N + l;
         const TwPair* k1 = ks.keys_sh + (((size_t)j * 2 + 1) * ks.K + idx) * N + l;
-        const TwPair u0 = ldpair(k0), u1 = ldpair(k0 + 1), w0 = ldpair(k1), w1 = ldpair(k1 + 1);
+        TwPair u0, u1, w0, w1;
+        ld_keys2(k0, u0, u1);
+        ld_keys2(k1, w0, w1);
 #pragma unroll
         for (int it = 0; it < kMacItems; ++it) {
             const uint32_t b = b0 + it;
@@ -334,8 +347,13 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     }
     dim3 g(C::N / 512, ks.R, (unsigned)items);
     if (ks.fast_ok && ks.keys_sh) {
-        dim3 gf(C::N / 512, ks.R, (unsigned)((items + kMacItems - 1) / kMacItems));
-        k_ks_mac_fast<<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
+        if (g_ks_mac_items == 8) {
+            dim3 gf(C::N / 512, ks.R, (unsigned)((items + 7) / 8));
+            k_ks_mac_fast<8><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
+        } else {
+            dim3 gf(C::N / 512, ks.R, (unsigned)((items + 3) / 4));
+            k_ks_mac_fast<4><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
+        }
     } else
         k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
