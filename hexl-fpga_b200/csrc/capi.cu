@@ -46,8 +46,10 @@ static int ilog2_exact(uint64_t n) {
 }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+static std::atomic<int> g_small_path{1};   // use the 32-bit kernels for q < 2^30 (option "small_path")
+
 hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
-                       const hb::TwPair* itw, int logn) {
+                       const hb::TwPair* itw, int logn, const hb::Tw32* ftw32, const hb::Tw32* itw32) {
     hb::ModTab t;
     t.q = q;
     t.twoq = q << 1;
@@ -61,6 +63,11 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.itw = itw;
     t.fwd_fast_ok = hb::fwd_fast_modulus_ok(q, logn) ? 1u : 0u;
     t.inv_fast_ok = hb::inv_fast_modulus_ok(q) ? 1u : 0u;
+    t.sm32 = hb::make_small32(q, t.sc);
+    t.ftw32 = ftw32;
+    t.itw32 = itw32;
+    t.small_ok = (hb::small_modulus_ok(q) && (ftw32 || itw32)) ? 1u : 0u;
+    t.pad = 0;
     return t;
 }
 
@@ -141,6 +148,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         g_ks_workspace_mb = value;
         return 0;
     }
+    if (!strcmp(name, "small_path")) {
+        g_small_path = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "ks_mac_items")) {
         if (value != 4 && value != 8) return fail(HEXL_B200_EINVAL, "ks_mac_items must be 4 or 8");
         hb::g_ks_mac_items = (int)value;
@@ -203,8 +214,15 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
     e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr, list,
                                  (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack twiddles");
-    hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn);
+    hb::Tw32* packed32 = nullptr;
     int launches = 1;
+    if (g_small_path.load() && hb::small_modulus_ok(q) && hb::small_path_available((uint32_t)logn, variant)) {
+        packed32 = reinterpret_cast<hb::Tw32*>(scratch + 300 * 1024);
+        e = hb::launch_pack_twiddles32(d_roots, d_precon, packed32, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack 32-bit twiddles");
+        ++launches;
+    }
+    hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn, packed32, nullptr);
     e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd launch");
     g_launches += launches;
@@ -236,8 +254,16 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
     e = hb::launch_pack_twiddles((uint32_t)logn, variant, nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed,
                                  list, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack twiddles");
-    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn);
+    hb::Tw32* packed32 = nullptr;
     int launches = 1;
+    if (g_small_path.load() && hb::small_modulus_ok(q) && hb::small_path_available((uint32_t)logn, variant)) {
+        packed32 = reinterpret_cast<hb::Tw32*>(scratch + (1u << 19) + 300 * 1024);
+        e = hb::launch_pack_twiddles32(nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed32,
+                                       (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack 32-bit twiddles");
+        ++launches;
+    }
+    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn, nullptr, packed32);
     e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv launch");
     g_launches += launches;

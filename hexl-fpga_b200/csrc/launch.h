@@ -35,6 +35,14 @@ cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roo
                                  TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
                                  TwPair* inv_out, uint32_t* zero_count, cudaStream_t st);
 
+// small-modulus (q < 2^30) 32-bit kernels: available for N = 16384 with the 32-word configuration
+bool small_path_available(uint32_t logn, int variant);
+size_t packed32_fwd_entries();
+size_t packed32_inv_entries();
+cudaError_t launch_pack_twiddles32(const uint64_t* roots, const uint64_t* precon, Tw32* fwd_out,
+                                   const uint64_t* inv_roots, const uint64_t* precon_inv, Tw32* inv_out,
+                                   cudaStream_t st);
+
 // 2-D tensor map over `polys` polynomials of 2^logn words starting at `base`
 // (rows of 16 words, 128-byte swizzle), for the kernels' TMA loads
 // box_rows = 0: the load box (min(256, rows per polynomial)); 32: the per-warp store box

@@ -20,6 +20,12 @@ struct ModTab {
     const TwPair* itw;      // packed inverse twiddles  (NttCfg::INV_ENTRIES)
     uint32_t fwd_fast_ok;   // modulus small enough for the lazy forward path
     uint32_t inv_fast_ok;
+    // small-modulus (q < 2^30) 32-bit path, when available for the shape
+    Small32 sm32;
+    const Tw32* ftw32;
+    const Tw32* itw32;
+    uint32_t small_ok;
+    uint32_t pad;
 };
 
 // ---- load transforms (applied to each word as it enters the transform) ----
@@ -334,7 +340,7 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
     __syncthreads();
     pf.template issue<C>();
-    inv_head_compute<C, C::NP - 1>(tid, v, t.itw, a, t.sc);
+    inv_head_compute<C, C::NP - 1>(tid, v, t.itw, a);
 #pragma unroll
     for (int gi = 0; gi < (C::E >> PL::R); ++gi)
 #pragma unroll
@@ -384,11 +390,11 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         const ModTab& t = job.mod(item);
         bool done;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
-            const FastArith a = {t.fm};
+            const FastArith a = {t.fm, t.sc};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else {
-            const ExactArith a = {t.q, t.twoq};
+            const ExactArith a = {t.q, t.twoq, t.sc};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
         }
@@ -396,6 +402,194 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     }
     // staged TMA stores read shared memory asynchronously: drain before exit
     if (FWD && SmemPlan<C>::kStagedStore && (tid & 31u) == 0) tma_store_wait_read();
+}
+
+// ---------------------------------------------------------------------------
+// small-modulus (q < 2^30) path: uint32 registers and a uint32 working buffer
+// ---------------------------------------------------------------------------
+// Shared memory: [ W: N uint64 (TMA landing) ][ S: N uint32 (working copy) ][ mbarrier, flag ]
+// The landing buffer is free again as soon as the first pass has narrowed the
+// words into S, so the next polynomial is prefetched right after the first
+// barrier, a whole transform ahead of its use.
+template <class C32>
+struct SmallPlan {
+    static constexpr uint32_t S_WORD = C32::N;                 // in uint64 words from the base
+    static constexpr uint32_t BAR_WORD = C32::N + C32::N / 2;
+    static constexpr uint32_t FLAG_WORD = BAR_WORD + 1;
+    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2) * 8;
+};
+
+// narrow a landed word to 32 bits while collecting the range vote
+struct XfNarrowVote {
+    uint32_t* hi_or;
+    uint32_t* lo_max;
+    HB_D uint32_t operator()(uint64_t x) const {
+        *hi_or |= (uint32_t)(x >> 32);
+        *lo_max = max(*lo_max, (uint32_t)x);
+        return (uint32_t)x;
+    }
+};
+struct XfSame32 {
+    HB_D uint32_t operator()(uint32_t x) const { return x; }
+};
+
+template <class C32>
+HB_D void small_vote_raise(int bad, uint64_t* base) {
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) base[SmallPlan<C32>::FLAG_WORD] = 1;
+}
+template <class C32>
+HB_D bool small_vote_read(uint64_t* base) {
+    uint64_t* flag = base + SmallPlan<C32>::FLAG_WORD;
+    if (*flag == 0) return false;
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = 0;
+    return true;
+}
+
+struct PrefetchSmall {
+    const CUtensorMap* map;
+    uint32_t row;
+    template <class C64, class C32>
+    HB_D void issue(uint64_t* base) const {
+        if (row != kNoPrefetch) {
+            fence_proxy_async();
+            issue_poly_load<C64>(base, map, base + SmallPlan<C32>::BAR_WORD, row);
+        }
+    }
+};
+
+template <class C32, int P, class A>
+HB_D void fwd_mid_passes32(uint32_t tid, uint32_t* S, const Tw32* tw, const A& a) {
+    if constexpr (P < C32::NP) {
+        fwd_head_pass<C32, P>(tid, S, tw, a);
+        __syncthreads();
+        fwd_mid_passes32<C32, P + 1>(tid, S, tw, a);
+    }
+}
+template <class C32, int P, class A>
+HB_D void inv_mid_passes32(uint32_t tid, uint32_t* S, const Tw32* tw, const A& a) {
+    if constexpr (P < C32::NP - 1) {
+        inv_head_pass<C32, P>(tid, S, tw, a);
+        __syncthreads();
+        inv_mid_passes32<C32, P + 1>(tid, S, tw, a);
+    }
+}
+
+// 32 output words (one uint32 row widened) -> 8 x 32-byte stores
+HB_D void st_row32_as_u64(uint64_t* dst, const uint32_t* v) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "l"((uint64_t)v[4 * c]),
+                     "l"((uint64_t)v[4 * c + 1]), "l"((uint64_t)v[4 * c + 2]), "l"((uint64_t)v[4 * c + 3])
+                     : "memory");
+}
+
+// forward, small modulus: base -> dst (bit-reversed order, [0,q)); false = deferred
+template <class C64, class C32, int MODE>
+HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf) {
+    using P0 = FwdPass<C32, 0>;
+    const uint32_t tid = threadIdx.x;
+    uint32_t* S = reinterpret_cast<uint32_t*>(base + SmallPlan<C32>::S_WORD);
+    const SmallArith a = {t.sm32};
+    uint32_t v[C32::E];
+    uint32_t hi_or = 0, lo_max = 0;
+    head_load<C32, P0::R, P0::LS>(tid, base, v, XfNarrowVote{&hi_or, &lo_max});
+    if constexpr (MODE == kFastVote)   // forward contract: every word < 4q
+        small_vote_raise<C32>((hi_or != 0) | (lo_max >= 2u * t.sm32.twoq), base);
+    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a);
+    head_store<C32, P0::R, P0::LS>(tid, S, v);
+    __syncthreads();
+    pf.template issue<C64, C32>(base);       // the landing buffer is free from here on
+    if constexpr (MODE == kFastVote) {
+        if (small_vote_read<C32>(base)) return false;
+    }
+    fwd_mid_passes32<C32, 1>(tid, S, t.ftw32, a);
+    tail_load<C32>(tid, S, v, XfSame32());
+    __syncthreads();                          // S may be overwritten by the next polynomial's first pass
+    fwd_tail_compute<C32>(tid, v, t.ftw32, a);
+#pragma unroll
+    for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
+        st_row32_as_u64(dst + (size_t)(tid + ri * C32::NT) * C32::ROW, v + ri * C32::ROW);
+    return true;
+}
+
+// inverse, small modulus: base (bit-reversed order) -> dst (natural order, [0,q))
+template <class C64, class C32, int MODE>
+HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf) {
+    using PL = InvPass<C32, C32::NP - 1>;
+    const uint32_t tid = threadIdx.x;
+    uint32_t* S = reinterpret_cast<uint32_t*>(base + SmallPlan<C32>::S_WORD);
+    const SmallArith a = {t.sm32};
+    uint32_t v[C32::E];
+    uint32_t hi_or = 0, lo_max = 0;
+    const XfNarrowVote xf = {&hi_or, &lo_max};
+    // a row of 32 words = two 16-word rows of the uint64 landing buffer
+#pragma unroll
+    for (int ri = 0; ri < C32::E / C32::ROW; ++ri) {
+        const uint32_t row64 = (tid + ri * C32::NT) * 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint64_t x, y;
+                ld2(base + (row64 + h) * 16 + (((uint32_t)c ^ ((row64 + h) & 7u)) << 1), x, y);
+                v[ri * C32::ROW + h * 16 + 2 * c] = xf(x);
+                v[ri * C32::ROW + h * 16 + 2 * c + 1] = xf(y);
+            }
+    }
+    if constexpr (MODE == kFastVote)   // inverse contract: every word < 2q
+        small_vote_raise<C32>((hi_or != 0) | (lo_max >= t.sm32.twoq), base);
+    inv_tail_compute<C32>(tid, v, t.itw32, a);
+    tail_store<C32>(tid, S, v);
+    __syncthreads();
+    pf.template issue<C64, C32>(base);
+    if constexpr (MODE == kFastVote) {
+        if (small_vote_read<C32>(base)) return false;
+    }
+    inv_mid_passes32<C32, 0>(tid, S, t.itw32, a);
+    head_load<C32, PL::R, PL::LS>(tid, S, v, XfSame32());
+    __syncthreads();
+    inv_head_compute<C32, C32::NP - 1>(tid, v, t.itw32, a);
+#pragma unroll
+    for (int gi = 0; gi < (C32::E >> PL::R); ++gi)
+#pragma unroll
+        for (int k = 0; k < (1 << PL::R); ++k) dst[inv_last_index<C32>(tid, gi, k)] = v[gi * (1 << PL::R) + k];
+    return true;
+}
+
+// persistent skeleton of the small-modulus kernels (plain in-place batches)
+template <class C64, class C32, bool FWD, int MODE>
+HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const ModTab& t, uint32_t n_items,
+                               uint32_t* list) {
+    uint64_t* base = smem_poly<C64>();
+    uint64_t* bar = base + SmallPlan<C32>::BAR_WORD;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t ROWS = C64::N / 16;
+    if (tid == 0) {
+        if (smem_u32(base) & 1023u) __trap();
+        mbar_init(bar, 1);
+        base[SmallPlan<C32>::FLAG_WORD] = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t item = blockIdx.x;
+    if (tid == 0 && item < n_items) issue_poly_load<C64>(base, tmap, bar, item * ROWS);
+    uint32_t parity = 0;
+    for (; item < n_items; item += gridDim.x) {
+        const uint32_t next = item + gridDim.x;
+        PrefetchSmall pf;
+        pf.map = tmap;
+        pf.row = (tid == 0 && next < n_items) ? next * ROWS : kNoPrefetch;
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        uint64_t* dst = data + (size_t)item * C64::N;
+        bool done;
+        if constexpr (FWD) done = ntt_fwd_small_cta<C64, C32, MODE>(base, t, dst, pf);
+        else done = ntt_inv_small_cta<C64, C32, MODE>(base, t, dst, pf);
+        if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
+        // the next transform's first pass writes S: everyone must have left this one
+        // (its last reads of S are followed by a block barrier inside the cta functions)
+    }
 }
 
 template <class C>

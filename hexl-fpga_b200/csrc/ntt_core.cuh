@@ -40,32 +40,37 @@
 
 namespace hb {
 
-template <int LOGN_, int LOGE_>
+// LOGROW_ = log2(words per 128-byte shared-memory row): 4 for uint64 words, 5
+// for the uint32 small-modulus path.  The "tail" pass owns the last LOGROW
+// stages (one full row per thread), the head passes the first LOGN - LOGROW.
+template <int LOGN_, int LOGE_, int LOGROW_ = 4>
 struct NttCfg {
-    static constexpr int LOGN = LOGN_, LOGE = LOGE_;
-    static constexpr int N = 1 << LOGN, E = 1 << LOGE, NT = N / E;
+    static constexpr int LOGN = LOGN_, LOGE = LOGE_, LOGROW = LOGROW_;
+    static constexpr int N = 1 << LOGN, E = 1 << LOGE, NT = N / E, ROW = 1 << LOGROW;
+    using elem = typename std::conditional<LOGROW_ == 4, uint64_t, uint32_t>::type;
     // CTAs per SM the register allocation must allow (launch bounds)
     static constexpr int MIN_CTAS = (NT * 128 <= 32768) ? (65536 / (NT * 128) > 4 ? 4 : 65536 / (NT * 128)) : 1;
-    static constexpr int HEAD = LOGN - 4;                 // stages outside the 16-word tail
+    static constexpr int HEAD = LOGN - LOGROW;            // stages outside the one-row tail
     static constexpr int NP = (HEAD + LOGE - 1) / LOGE;   // number of head passes
     static constexpr int BASE = HEAD / NP, REM = HEAD % NP;
-    static_assert(LOGE >= 4 && LOGN >= LOGE + 4, "unsupported NTT shape");
+    static_assert(LOGROW == 4 || LOGROW == 5, "rows hold 16 uint64 or 32 uint32 words");
+    static_assert(LOGE >= LOGROW && LOGN >= LOGE + LOGROW, "unsupported NTT shape");
     static constexpr int pass_r(int p) { return BASE + (p < REM ? 1 : 0); }
     static constexpr int pass_s0(int p) {
         int s = 0;
         for (int i = 0; i < p; ++i) s += pass_r(i);
         return s;
     }
-    // ---- packed twiddle table geometry (entries of 16 bytes) ----
-    // forward: head pass P owns 2^S0 groups of 2^R entries, then N/16 tail rows of 16
+    // ---- packed twiddle table geometry (entries) ----
+    // forward: head pass P owns 2^S0 groups of 2^R entries, then N/ROW tail rows of ROW
     static constexpr int fwd_off(int p) {  // p == NP -> tail
         int o = 0;
         for (int i = 0; i < p; ++i) o += 1 << (pass_s0(i) + pass_r(i));
         return o;
     }
     static constexpr int FWD_ENTRIES = fwd_off(NP) + N;
-    // inverse: N/16 tail rows of 16 first, then head pass P: (N >> (U0+R)) groups of 2^R
-    static constexpr int inv_u0(int p) { return 4 + pass_s0(p); }
+    // inverse: N/ROW tail rows of ROW first, then head pass P: (N >> (U0+R)) groups of 2^R
+    static constexpr int inv_u0(int p) { return LOGROW + pass_s0(p); }
     static constexpr int inv_off(int p) {
         int o = N;
         for (int i = 0; i < p; ++i) o += N >> inv_u0(i);
@@ -74,7 +79,13 @@ struct NttCfg {
     static constexpr int INV_ENTRIES = inv_off(NP);
 };
 
-HB_HD uint32_t swz(uint32_t idx) { return idx ^ (((idx >> 4) & 7u) << 1); }
+// 16-byte chunk c of 128-byte row r lives at chunk c ^ (r & 7)
+HB_HD uint32_t swz(uint32_t idx) { return idx ^ (((idx >> 4) & 7u) << 1); }          // uint64 words
+HB_HD uint32_t swz32(uint32_t idx) { return idx ^ (((idx >> 5) & 7u) << 2); }        // uint32 words
+template <class T>
+HB_HD uint32_t swz_t(uint32_t idx) {
+    return sizeof(T) == 8 ? swz(idx) : swz32(idx);
+}
 
 // compile-time loop: f(std::integral_constant<int, I>) for I in [0, COUNT).
 // (#pragma unroll does not reliably flatten loops whose bounds depend on an
@@ -129,13 +140,13 @@ template <class C>
 HB_HD int fwd_pack_src(uint32_t e) {
     int s0 = 0;
     for (int p = 0; p <= C::NP; ++p) {
-        const int r = (p == C::NP) ? 4 : C::pass_r(p);
+        const int r = (p == C::NP) ? C::LOGROW : C::pass_r(p);
         const uint32_t count = 1u << (s0 + r);
         if (e < count) {
             uint32_t hi = e >> r, slot = e & ((1u << r) - 1);
             if (p == C::NP) {  // tail: [row/32][slot][row%32] so a warp's loads coalesce
-                slot = (e >> 5) & 15u;
-                hi = ((e >> 9) << 5) | (e & 31u);
+                slot = (e >> 5) & (C::ROW - 1);
+                hi = ((e >> (5 + C::LOGROW)) << 5) | (e & 31u);
             }
             if (slot == 0) return -1;
             const int d = ilog2_u32(slot);
@@ -153,13 +164,13 @@ HB_HD int inv_pack_src(uint32_t e) {
     constexpr uint32_t N = C::N;
     int u0 = 0;
     for (int p = -1; p < C::NP; ++p) {   // p == -1: tail
-        const int r = (p < 0) ? 4 : C::pass_r(p);
+        const int r = (p < 0) ? C::LOGROW : C::pass_r(p);
         const uint32_t count = N >> u0;  // groups (N >> (u0+r)) * 2^r
         if (e < count) {
             uint32_t hi = e >> r, slot = e & ((1u << r) - 1);
             if (p < 0) {  // tail: [row/32][slot][row%32]
-                slot = (e >> 5) & 15u;
-                hi = ((e >> 9) << 5) | (e & 31u);
+                slot = (e >> 5) & (C::ROW - 1);
+                hi = ((e >> (5 + C::LOGROW)) << 5) | (e & 31u);
             }
             if (slot == 0) return -1;
             const int ee = ilog2_u32(slot);          // = R-1-d
@@ -174,7 +185,7 @@ HB_HD int inv_pack_src(uint32_t e) {
 }
 
 // ---------------------------------------------------------------------------
-// arithmetic policies
+// arithmetic policies: element type, twiddle type, butterflies
 // ---------------------------------------------------------------------------
 struct InvScale {
     uint64_t inv_n, inv_n_p, inv_n_w, inv_n_w_p;
@@ -182,7 +193,11 @@ struct InvScale {
 
 // reference op sequence, bit-exact even on out-of-range words
 struct ExactArith {
+    using elem = uint64_t;
+    using Tw = TwPair;
     uint64_t q, twoq;
+    InvScale sc;
+    HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly(X, Y, t.w, t.wp, q, twoq); }
     HB_HD uint64_t fwd_final(uint64_t x) const {      // ntt.cpp:535-546
         x -= (x >= twoq) ? twoq : 0;
@@ -190,21 +205,100 @@ struct ExactArith {
         return x;
     }
     HB_HD void inv(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv_bfly(X, Y, t.w, t.wp, q, twoq); }
-    HB_HD void inv_last(uint64_t& X, uint64_t& Y, const InvScale& s) const {
-        inv_last_bfly(X, Y, s.inv_n, s.inv_n_p, s.inv_n_w, s.inv_n_w_p, q, twoq);
+    HB_HD void inv_last(uint64_t& X, uint64_t& Y) const {
+        inv_last_bfly(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, q, twoq);
     }
 };
 
 // any-correct-algorithm path for in-contract inputs (modarith.cuh)
 struct FastArith {
+    using elem = uint64_t;
+    using Tw = TwPair;
     FastMod m;
+    InvScale sc;
+    HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly_fast(X, Y, t.w, t.wp, m); }
     HB_HD uint64_t fwd_final(uint64_t x) const { return reduce_small_multiple(x, m); }
     HB_HD void inv(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv_bfly_fast(X, Y, t.w, t.wp, m); }
-    HB_HD void inv_last(uint64_t& X, uint64_t& Y, const InvScale& s) const {
-        inv_last_bfly_fast(X, Y, s.inv_n, s.inv_n_p, s.inv_n_w, s.inv_n_w_p, m);
+    HB_HD void inv_last(uint64_t& X, uint64_t& Y) const {
+        inv_last_bfly_fast(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, m);
     }
 };
+
+// Small-modulus path (q < 2^30): every word of a lazy Harvey transform stays
+// below 4q < 2^32, so the whole butterfly runs in 32-bit arithmetic -- one
+// IMAD.WIDE (high half = Shoup quotient), two IMAD and four ALU instructions
+// instead of ~18 -- on uint32 registers and a uint32 shared buffer.  Twiddles
+// are {w, floor(w*2^32/q)} = {w, hi32 of the caller's 64-bit factor}.
+struct Tw32 {
+    uint32_t w, wp;
+};
+struct Small32 {
+    uint32_t q, nq, twoq;              // nq = 2^32 - q
+    uint32_t inv_n, inv_n_p, inv_n_w, inv_n_w_p;
+};
+HB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    // IMAD.WIDE (full rate) and keep the high half; IMAD.HI runs at half rate on sm_100
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    (void)lo;
+    return hi;
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+HB_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+// w*y - floor(y*wp/2^32)*q in [0,2q) for ANY y < 2^32 (w < q < 2^31)
+HB_HD uint32_t mul_lazy32(uint32_t y, uint32_t w, uint32_t wp, uint32_t nq) {
+    return w * y + mulhi32(y, wp) * nq;
+}
+struct SmallArith {
+    using elem = uint32_t;
+    using Tw = Tw32;
+    Small32 m;
+    HB_HD Tw ld(const Tw* p) const {
+#if defined(__CUDA_ARCH__)
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        return Tw32{t.x, t.y};
+#else
+        return *p;
+#endif
+    }
+    // x - 2q if x >= 2q (x < 4q): the wrapped difference is huge when x < 2q
+    HB_HD uint32_t csub32(uint32_t x, uint32_t b) const { return umin32(x, x - b); }
+    HB_HD void fwd(uint32_t& X, uint32_t& Y, const Tw32& t) const {
+        const uint32_t tx = csub32(X, m.twoq);
+        const uint32_t T = mul_lazy32(Y, t.w, t.wp, m.nq);
+        X = tx + T;
+        Y = tx + m.twoq - T;
+    }
+    HB_HD uint32_t fwd_final(uint32_t x) const { return csub32(csub32(x, m.twoq), m.q); }
+    HB_HD void inv(uint32_t& X, uint32_t& Y, const Tw32& t) const {   // values in [0,2q)
+        const uint32_t tx = X + Y;
+        const uint32_t ty = X + m.twoq - Y;
+        X = csub32(tx, m.twoq);
+        Y = mul_lazy32(ty, t.w, t.wp, m.nq);
+    }
+    HB_HD void inv_last(uint32_t& X, uint32_t& Y) const {
+        const uint32_t tx = csub32(X + Y, m.twoq);
+        const uint32_t ty = X + m.twoq - Y;
+        X = csub32(mul_lazy32(tx, m.inv_n, m.inv_n_p, m.nq), m.q);
+        Y = csub32(mul_lazy32(ty, m.inv_n_w, m.inv_n_w_p, m.nq), m.q);
+    }
+};
+HB_HD bool small_modulus_ok(uint64_t q) { return q < ((uint64_t)1 << 30); }
+HB_HD Small32 make_small32(uint64_t q, const InvScale& sc) {
+    Small32 m;
+    m.q = (uint32_t)q;
+    m.nq = 0u - (uint32_t)q;
+    m.twoq = (uint32_t)(q << 1);
+    m.inv_n = (uint32_t)sc.inv_n;
+    m.inv_n_p = (uint32_t)(sc.inv_n_p >> 32);      // floor(x*2^32/q) = hi32(floor(x*2^64/q))
+    m.inv_n_w = (uint32_t)sc.inv_n_w;
+    m.inv_n_w_p = (uint32_t)(sc.inv_n_w_p >> 32);
+    return m;
+}
 
 // forward fast path is valid when every input word < 4q and 4q*(LOGN+1) < 2^64;
 // inverse when every input word < 2q and 8q < 2^64.
@@ -215,8 +309,11 @@ HB_HD bool inv_fast_modulus_ok(uint64_t q) { return q < ((uint64_t)1 << 60); }
 
 // tail twiddles are stored [row/32][slot][row%32]: entry of (row, slot) is
 // tail_tw_base(row) + 32*slot, so the 32 lanes of a warp (32 consecutive rows)
-// read 512 contiguous bytes per slot
-HB_HD uint32_t tail_tw_base(uint32_t row) { return ((row >> 5) << 9) | (row & 31u); }
+// read one contiguous run per slot
+template <class C>
+HB_HD uint32_t tail_tw_base(uint32_t row) {
+    return ((row >> 5) << (5 + C::LOGROW)) | (row & 31u);
+}
 
 // ---------------------------------------------------------------------------
 // register-resident groups
@@ -226,16 +323,13 @@ HB_HD uint32_t tail_tw_base(uint32_t row) { return ((row >> 5) << 9) | (row & 31
 // k with k + 2^(R-1-d) inside blocks of 2^(R-d); its twiddle
 // roots[2^s + (idx >> (LOGN-s))] (ntt.cpp:494-500) is packed at slot 2^d + blk.
 template <int R, int TS, class A>
-HB_HD void fwd_group(uint64_t* v, const TwPair* g, const A& a) {
+HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
     static_for<0, R>([&](auto dc) {
         constexpr int d = decltype(dc)::value;
         constexpr int half = 1 << (R - 1 - d);
-        if constexpr (TS > 1 && d + 1 < R) {   // tail: pull the next stage's twiddles into L1
-            static_for<0, (2 << d)>([&](auto pc) { prefetch_pair(g + ((2 << d) + decltype(pc)::value) * TS); });
-        }
         static_for<0, (1 << d)>([&](auto bc) {
             constexpr int blk = decltype(bc)::value;
-            const TwPair t = ldpair(g + ((1 << d) + blk) * TS);
+            const typename A::Tw t = a.ld(g + ((1 << d) + blk) * TS);
             static_for<0, half>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 a.fwd(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
@@ -249,23 +343,19 @@ HB_HD void fwd_group(uint64_t* v, const TwPair* g, const A& a) {
 // inv_roots[1 + N - (N >> u) + (idx >> (u+1))] (ntt.cpp:600-636) is packed at
 // slot 2^(R-1-d) + blk.  When LAST, the final stage is the inv_n-fused one.
 template <int R, bool LAST, int TS, class A>
-HB_HD void inv_group(uint64_t* v, const TwPair* g, const A& a, const InvScale& sc) {
+HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
     static_for<0, R>([&](auto dc) {
         constexpr int d = decltype(dc)::value;
         constexpr int half = 1 << d;
-        if constexpr (TS > 1 && d + 1 < R) {   // tail: next stage has 2^(R-d-2) twiddles at slots 2^(R-d-2)..
-            static_for<0, (1 << (R - d - 2))>(
-                [&](auto pc) { prefetch_pair(g + ((1 << (R - d - 2)) + decltype(pc)::value) * TS); });
-        }
         static_for<0, (1 << (R - d - 1))>([&](auto bc) {
             constexpr int blk = decltype(bc)::value;
             if constexpr (LAST && d == R - 1) {
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    a.inv_last(v[blk * 2 * half + j], v[blk * 2 * half + j + half], sc);
+                    a.inv_last(v[blk * 2 * half + j], v[blk * 2 * half + j + half]);
                 });
             } else {
-                const TwPair t = ldpair(g + ((1 << (R - 1 - d)) + blk) * TS);
+                const typename A::Tw t = a.ld(g + ((1 << (R - 1 - d)) + blk) * TS);
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     a.inv(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
@@ -276,7 +366,7 @@ HB_HD void inv_group(uint64_t* v, const TwPair* g, const A& a, const InvScale& s
 }
 
 // ---------------------------------------------------------------------------
-// 16-byte accessors (two words)
+// 16-byte accessors
 // ---------------------------------------------------------------------------
 HB_HD void ld2(const uint64_t* p, uint64_t& a, uint64_t& b) {
 #if defined(__CUDA_ARCH__)
@@ -296,6 +386,24 @@ HB_HD void st2(uint64_t* p, uint64_t a, uint64_t b) {
     p[1] = b;
 #endif
 }
+// one 16-byte chunk = 2 uint64 or 4 uint32 words, to / from registers
+HB_HD void ld_chunk(const uint64_t* p, uint64_t* v) { ld2(p, v[0], v[1]); }
+HB_HD void st_chunk(uint64_t* p, const uint64_t* v) { st2(p, v[0], v[1]); }
+HB_HD void ld_chunk(const uint32_t* p, uint32_t* v) {
+#if defined(__CUDA_ARCH__)
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+#else
+    v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+#endif
+}
+HB_HD void st_chunk(uint32_t* p, const uint32_t* v) {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+#else
+    p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3];
+#endif
+}
 
 // ---------------------------------------------------------------------------
 // head-pass geometry shared by forward and inverse
@@ -312,55 +420,60 @@ struct HeadGeom {
     }
 };
 
-// load all E words of a head pass from the (swizzled) shared buffer
-template <class C, int R, int LS, class Xf>
-HB_HD void head_load(uint32_t tid, const uint64_t* sm, uint64_t* v, const Xf& xf) {
+// load all E words of a head pass from a (swizzled) shared buffer of S-typed
+// words into T-typed registers through xf
+template <class C, int R, int LS, class S, class T, class Xf>
+HB_HD void head_load(uint32_t tid, const S* sm, T* v, const Xf& xf) {
     using Gm = HeadGeom<C, R, LS>;
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t b = Gm::base(tid + gi * C::NT);
         static_for<0, (1 << R)>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            v[gi * (1 << R) + k] = xf(sm[swz(b + ((uint32_t)k << LS))]);
+            v[gi * (1 << R) + k] = xf(sm[swz_t<S>(b + ((uint32_t)k << LS))]);
         });
     });
 }
-template <class C, int R, int LS>
-HB_HD void head_store(uint32_t tid, uint64_t* sm, const uint64_t* v) {
+template <class C, int R, int LS, class T>
+HB_HD void head_store(uint32_t tid, T* sm, const T* v) {
     using Gm = HeadGeom<C, R, LS>;
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t b = Gm::base(tid + gi * C::NT);
         static_for<0, (1 << R)>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            sm[swz(b + ((uint32_t)k << LS))] = v[gi * (1 << R) + k];
+            sm[swz_t<T>(b + ((uint32_t)k << LS))] = v[gi * (1 << R) + k];
         });
     });
 }
 
-// tail rows: thread tid owns rows tid + ri*NT, 16 contiguous words each
+// tail rows: thread tid owns rows tid + ri*NT of ROW contiguous words (128 bytes)
 template <class C, class Xf>
-HB_HD void tail_load(uint32_t tid, const uint64_t* sm, uint64_t* v, const Xf& xf) {
-    static_for<0, C::E / 16>([&](auto rc) {
+HB_HD void tail_load(uint32_t tid, const typename C::elem* sm, typename C::elem* v, const Xf& xf) {
+    constexpr int PER = 16 / sizeof(typename C::elem);   // words per 16-byte chunk
+    static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tid + ri * C::NT;
         static_for<0, 8>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
-            uint64_t a, b;
-            ld2(sm + row * 16 + (((uint32_t)c ^ (row & 7u)) << 1), a, b);
-            v[ri * 16 + 2 * c] = xf(a);
-            v[ri * 16 + 2 * c + 1] = xf(b);
+            typename C::elem t[PER];
+            ld_chunk(sm + row * C::ROW + (((uint32_t)c ^ (row & 7u)) * PER), t);
+            static_for<0, PER>([&](auto ec) {
+                constexpr int e = decltype(ec)::value;
+                v[ri * C::ROW + c * PER + e] = xf(t[e]);
+            });
         });
     });
 }
 template <class C>
-HB_HD void tail_store(uint32_t tid, uint64_t* sm, const uint64_t* v) {
-    static_for<0, C::E / 16>([&](auto rc) {
+HB_HD void tail_store(uint32_t tid, typename C::elem* sm, const typename C::elem* v) {
+    constexpr int PER = 16 / sizeof(typename C::elem);
+    static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tid + ri * C::NT;
         static_for<0, 8>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
-            st2(sm + row * 16 + (((uint32_t)c ^ (row & 7u)) << 1), v[ri * 16 + 2 * c], v[ri * 16 + 2 * c + 1]);
+            st_chunk(sm + row * C::ROW + (((uint32_t)c ^ (row & 7u)) * PER), v + ri * C::ROW + c * PER);
         });
     });
 }
@@ -371,12 +484,12 @@ HB_HD void tail_store(uint32_t tid, uint64_t* sm, const uint64_t* v) {
 template <class C, int P>
 struct FwdPass {
     static constexpr int R = C::pass_r(P), S0 = C::pass_s0(P), LS = C::LOGN - S0 - R;
-    static_assert(LS >= 4, "head pass stride must cover a 128-byte row");
+    static_assert(LS >= C::LOGROW, "head pass stride must cover a 128-byte row");
 };
 
 // butterflies of head pass P on registers v[E] (loaded by head_load)
 template <class C, int P, class A>
-HB_HD void fwd_head_compute(uint32_t tid, uint64_t* v, const TwPair* tw, const A& a) {
+HB_HD void fwd_head_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
     using Ps = FwdPass<C, P>;
     using Gm = HeadGeom<C, Ps::R, Ps::LS>;
     static_for<0, Gm::G>([&](auto gc) {
@@ -388,25 +501,26 @@ HB_HD void fwd_head_compute(uint32_t tid, uint64_t* v, const TwPair* tw, const A
 
 // in-place head pass P > 0
 template <class C, int P, class A>
-HB_HD void fwd_head_pass(uint32_t tid, uint64_t* sm, const TwPair* tw, const A& a) {
+HB_HD void fwd_head_pass(uint32_t tid, typename A::elem* sm, const typename A::Tw* tw, const A& a) {
     using Ps = FwdPass<C, P>;
-    uint64_t v[C::E];
-    auto ident = [](uint64_t x) { return x; };
+    using T = typename A::elem;
+    T v[C::E];
+    auto ident = [](T x) { return x; };
     head_load<C, Ps::R, Ps::LS>(tid, sm, v, ident);
     fwd_head_compute<C, P>(tid, v, tw, a);
     head_store<C, Ps::R, Ps::LS>(tid, sm, v);
 }
 
-// tail: last four stages + final reduction on registers v[E] (from tail_load)
+// tail: last LOGROW stages + final reduction on registers v[E] (from tail_load)
 template <class C, class A>
-HB_HD void fwd_tail_compute(uint32_t tid, uint64_t* v, const TwPair* tw, const A& a) {
-    static_for<0, C::E / 16>([&](auto rc) {
+HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
+    static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tid + ri * C::NT;
-        fwd_group<4, 32>(v + ri * 16, tw + C::fwd_off(C::NP) + tail_tw_base(row), a);
-        static_for<0, 16>([&](auto kc) {
+        fwd_group<C::LOGROW, 32>(v + ri * C::ROW, tw + C::fwd_off(C::NP) + tail_tw_base<C>(row), a);
+        static_for<0, C::ROW>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            v[ri * 16 + k] = a.fwd_final(v[ri * 16 + k]);
+            v[ri * C::ROW + k] = a.fwd_final(v[ri * C::ROW + k]);
         });
     });
 }
@@ -421,38 +535,37 @@ struct InvPass {
     static_assert(!LAST || (LS + R == C::LOGN), "pass schedule broken");
 };
 
-// first inverse pass: stages t = 1,2,4,8 on rows (registers from tail_load)
+// first inverse pass: stages t = 1 .. ROW/2 on rows (registers from tail_load)
 template <class C, class A>
-HB_HD void inv_tail_compute(uint32_t tid, uint64_t* v, const TwPair* tw, const A& a) {
-    const InvScale none = {0, 0, 0, 0};
-    static_for<0, C::E / 16>([&](auto rc) {
+HB_HD void inv_tail_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
+    static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tid + ri * C::NT;
-        inv_group<4, false, 32>(v + ri * 16, tw + tail_tw_base(row), a, none);
+        inv_group<C::LOGROW, false, 32>(v + ri * C::ROW, tw + tail_tw_base<C>(row), a);
     });
 }
 
 template <class C, int P, class A>
-HB_HD void inv_head_compute(uint32_t tid, uint64_t* v, const TwPair* tw, const A& a, const InvScale& sc) {
+HB_HD void inv_head_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
     using Ps = InvPass<C, P>;
     using Gm = HeadGeom<C, Ps::R, Ps::LS>;
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t hi = Gm::hi(tid + gi * C::NT);
-        inv_group<Ps::R, Ps::LAST, 1>(v + gi * (1 << Ps::R), tw + C::inv_off(P) + (hi << Ps::R), a, sc);
+        inv_group<Ps::R, Ps::LAST, 1>(v + gi * (1 << Ps::R), tw + C::inv_off(P) + (hi << Ps::R), a);
     });
 }
 
 // in-place inverse head pass (not the last one)
 template <class C, int P, class A>
-HB_HD void inv_head_pass(uint32_t tid, uint64_t* sm, const TwPair* tw, const A& a) {
+HB_HD void inv_head_pass(uint32_t tid, typename A::elem* sm, const typename A::Tw* tw, const A& a) {
     using Ps = InvPass<C, P>;
+    using T = typename A::elem;
     static_assert(!Ps::LAST, "the last pass goes to global memory");
-    const InvScale none = {0, 0, 0, 0};
-    uint64_t v[C::E];
-    auto ident = [](uint64_t x) { return x; };
+    T v[C::E];
+    auto ident = [](T x) { return x; };
     head_load<C, Ps::R, Ps::LS>(tid, sm, v, ident);
-    inv_head_compute<C, P>(tid, v, tw, a, none);
+    inv_head_compute<C, P>(tid, v, tw, a);
     head_store<C, Ps::R, Ps::LS>(tid, sm, v);
 }
 

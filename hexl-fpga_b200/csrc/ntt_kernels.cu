@@ -40,6 +40,13 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_con
     ntt_persistent<C, false, MODE>(&tmap, nullptr, job, n_items, list);
 }
 
+// small-modulus kernels (q < 2^30): uint32 arithmetic, see ntt_block.cuh
+template <class C64, class C32, bool FWD, int MODE>
+__global__ void __launch_bounds__(C32::NT, 1) k_ntt_small(const __grid_constant__ CUtensorMap tmap, uint64_t* data,
+                                                         const ModTab tab, uint32_t n_items, uint32_t* list) {
+    ntt_persistent_small<C64, C32, FWD, MODE>(&tmap, data, tab, n_items, list);
+}
+
 // ---- packed twiddle builder -------------------------------------------------
 template <class C>
 __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
@@ -58,6 +65,25 @@ __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64
         const int s = inv_pack_src<C>(e);
         TwPair t = {0, 0};
         if (s >= 0) t = TwPair{inv_roots[s], precon_inv[s]};
+        inv_out[e] = t;
+    }
+}
+
+template <class C32>
+__global__ void k_pack_twiddles32(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
+                                  Tw32* __restrict__ fwd_out, const uint64_t* __restrict__ inv_roots,
+                                  const uint64_t* __restrict__ precon_inv, Tw32* __restrict__ inv_out) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fwd_out && e < (uint32_t)C32::FWD_ENTRIES) {
+        const int s = fwd_pack_src<C32>(e);
+        Tw32 t = {0, 0};
+        if (s >= 0) t = Tw32{(uint32_t)roots[s], (uint32_t)(precon[s] >> 32)};
+        fwd_out[e] = t;
+    }
+    if (inv_out && e < (uint32_t)C32::INV_ENTRIES) {
+        const int s = inv_pack_src<C32>(e);
+        Tw32 t = {0, 0};
+        if (s >= 0) t = Tw32{(uint32_t)inv_roots[s], (uint32_t)(precon_inv[s] >> 32)};
         inv_out[e] = t;
     }
 }
@@ -148,6 +174,29 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
         *launches += 1;
         return launch_mode<C, FWD, kExactAll>(tmap, smap, data, tab, batch, list, st);
     }
+    if constexpr (C::LOGN == 14 && C::LOGE == 5) {
+        // q < 2^30: the 32-bit kernels (out-of-contract items still go to the
+        // 64-bit exact kernel through the deferred list)
+        if (tab.small_ok) {
+            using C32 = NttCfg<14, 5, 5>;
+            const size_t smem = SmallPlan<C32>::BYTES;
+            if (trust) {
+                auto kern = k_ntt_small<C, C32, FWD, kFastTrust>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+                kern<<<persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st>>>(
+                    tmap, data, tab, (uint32_t)batch, list);
+                *launches += 1;
+                return cudaGetLastError();
+            }
+            auto kern = k_ntt_small<C, C32, FWD, kFastVote>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+            kern<<<persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st>>>(
+                tmap, data, tab, (uint32_t)batch, list);
+            if ((e = cudaGetLastError())) return e;
+            *launches += 2;
+            return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+        }
+    }
     if (trust) {
         *launches += 1;
         return launch_mode<C, FWD, kFastTrust>(tmap, smap, data, tab, batch, list, st);
@@ -201,6 +250,18 @@ cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roo
     HB_DISPATCH_CFG(logn, variant,
                     return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, zero_count, st));
     return cudaErrorInvalidValue;
+}
+
+bool small_path_available(uint32_t logn, int variant) { return logn == 14 && (variant & 1) == 1; }
+size_t packed32_fwd_entries() { return NttCfg<14, 5, 5>::FWD_ENTRIES; }
+size_t packed32_inv_entries() { return NttCfg<14, 5, 5>::INV_ENTRIES; }
+cudaError_t launch_pack_twiddles32(const uint64_t* roots, const uint64_t* precon, Tw32* fwd_out,
+                                   const uint64_t* inv_roots, const uint64_t* precon_inv, Tw32* inv_out,
+                                   cudaStream_t st) {
+    using C32 = NttCfg<14, 5, 5>;
+    const int total = C32::FWD_ENTRIES > C32::INV_ENTRIES ? C32::FWD_ENTRIES : C32::INV_ENTRIES;
+    k_pack_twiddles32<C32><<<(total + 255) / 256, 256, 0, st>>>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,

@@ -15,32 +15,45 @@
 
 using namespace hb;
 
-static uint64_t ident(uint64_t x) { return x; }
+struct Ident {
+    template <class T>
+    T operator()(T x) const { return x; }
+};
+static Ident ident;
+struct Narrow {   // uint64 word -> uint32 register (small-modulus path)
+    uint32_t operator()(uint64_t x) const { return (uint32_t)x; }
+};
 
 template <class C, int P, class A>
-void fwd_mid(std::vector<uint64_t>& sm, const TwPair* tw, const A& a) {
+void fwd_mid(std::vector<typename A::elem>& sm, const typename A::Tw* tw, const A& a) {
     if constexpr (P < C::NP) {
         for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) fwd_head_pass<C, P>(tid, sm.data(), tw, a);
         fwd_mid<C, P + 1>(sm, tw, a);
     }
 }
 template <class C, int P, class A>
-void inv_mid(std::vector<uint64_t>& sm, const TwPair* tw, const A& a) {
+void inv_mid(std::vector<typename A::elem>& sm, const typename A::Tw* tw, const A& a) {
     if constexpr (P < C::NP - 1) {
         for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) inv_head_pass<C, P>(tid, sm.data(), tw, a);
         inv_mid<C, P + 1>(sm, tw, a);
     }
 }
 
-// forward transform of `in` exactly as the kernel sequences it
-template <class C, class A>
-void emul_fwd(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const TwPair* tw, const A& a) {
+// forward transform of `in` exactly as the kernel sequences it.  C64 describes
+// the uint64 landing buffer (TMA), C the working configuration (== C64 for the
+// 64-bit paths; the uint32 configuration for the small-modulus path).
+template <class C64, class C, class A>
+void emul_fwd(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const typename A::Tw* tw, const A& a) {
+    using T = typename A::elem;
     using P0 = FwdPass<C, 0>;
-    std::vector<uint64_t> sm(C::N);
-    for (uint32_t i = 0; i < (uint32_t)C::N; ++i) sm[swz(i)] = in[i];   // what the swizzled TMA load does
-    std::vector<uint64_t> regs((size_t)C::NT * C::E);
-    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
-        head_load<C, P0::R, P0::LS>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
+    std::vector<uint64_t> W(C::N);
+    for (uint32_t i = 0; i < (uint32_t)C::N; ++i) W[swz(i)] = in[i];   // what the swizzled TMA load does
+    std::vector<T> sm(C::N);
+    std::vector<T> regs((size_t)C::NT * C::E);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
+        if constexpr (sizeof(T) == 8) head_load<C, P0::R, P0::LS>(tid, W.data(), &regs[(size_t)tid * C::E], ident);
+        else head_load<C, P0::R, P0::LS>(tid, W.data(), &regs[(size_t)tid * C::E], Narrow());
+    }
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
         fwd_head_compute<C, 0>(tid, &regs[(size_t)tid * C::E], tw, a);
         head_store<C, P0::R, P0::LS>(tid, sm.data(), &regs[(size_t)tid * C::E]);
@@ -49,22 +62,32 @@ void emul_fwd(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
         tail_load<C>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
-        uint64_t* v = &regs[(size_t)tid * C::E];
+        T* v = &regs[(size_t)tid * C::E];
         fwd_tail_compute<C>(tid, v, tw, a);
-        for (int ri = 0; ri < C::E / 16; ++ri)
-            for (int k = 0; k < 16; ++k) out[(tid + ri * C::NT) * 16 + k] = v[ri * 16 + k];
+        for (int ri = 0; ri < C::E / C::ROW; ++ri)
+            for (int k = 0; k < C::ROW; ++k) out[(tid + ri * C::NT) * C::ROW + k] = v[ri * C::ROW + k];
     }
 }
 
-template <class C, class A>
-void emul_inv(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const TwPair* tw, const A& a,
-              const InvScale& sc) {
+// inverse: the first pass reads rows.  For the small-modulus path the kernel
+// reads each 32-word row as two 16-word rows of the uint64 landing buffer.
+template <class C64, class C, class A>
+void emul_inv(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const typename A::Tw* tw, const A& a) {
+    using T = typename A::elem;
     using PL = InvPass<C, C::NP - 1>;
-    std::vector<uint64_t> sm(C::N);
-    for (uint32_t i = 0; i < (uint32_t)C::N; ++i) sm[swz(i)] = in[i];
-    std::vector<uint64_t> regs((size_t)C::NT * C::E);
-    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
-        tail_load<C>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
+    std::vector<uint64_t> W(C::N);
+    for (uint32_t i = 0; i < (uint32_t)C::N; ++i) W[swz(i)] = in[i];
+    std::vector<T> sm(C::N);
+    std::vector<T> regs((size_t)C::NT * C::E);
+    for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
+        if constexpr (sizeof(T) == 8) {
+            tail_load<C>(tid, W.data(), &regs[(size_t)tid * C::E], ident);
+        } else {
+            for (int ri = 0; ri < C::E / C::ROW; ++ri)
+                for (int k = 0; k < C::ROW; ++k)
+                    regs[(size_t)tid * C::E + ri * C::ROW + k] = (T)W[swz((tid + ri * C::NT) * C::ROW + k)];
+        }
+    }
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
         inv_tail_compute<C>(tid, &regs[(size_t)tid * C::E], tw, a);
         tail_store<C>(tid, sm.data(), &regs[(size_t)tid * C::E]);
@@ -73,8 +96,8 @@ void emul_inv(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid)
         head_load<C, PL::R, PL::LS>(tid, sm.data(), &regs[(size_t)tid * C::E], ident);
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
-        uint64_t* v = &regs[(size_t)tid * C::E];
-        inv_head_compute<C, C::NP - 1>(tid, v, tw, a, sc);
+        T* v = &regs[(size_t)tid * C::E];
+        inv_head_compute<C, C::NP - 1>(tid, v, tw, a);
         for (int gi = 0; gi < (C::E >> PL::R); ++gi)
             for (int k = 0; k < (1 << PL::R); ++k) out[inv_last_index<C>(tid, gi, k)] = v[gi * (1 << PL::R) + k];
     }
@@ -105,35 +128,95 @@ int run(uint64_t q, int garbage) {
     if (garbage == 2) for (auto& x : a) x = ~(uint64_t)0;
     if (garbage == 3) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 4 * q - 1 - (i % 5) : q - 1;  // edge of fwd contract
     if (garbage == 4) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 2 * q - 1 - (i % 3) : q - 1;  // edge of inv contract
-    ExactArith ex = {q, 2 * q};
-    FastArith fa = {make_fastmod(q)};
     uint64_t inv_n = ho_inv_mod(n % q, q), inv_n_w = ho_mul_mod(inv_n, ir[n - 1], q);
     InvScale sc = {inv_n, ho_mult_factor64(inv_n, q), inv_n_w, ho_mult_factor64(inv_n_w, q)};
+    ExactArith ex = {q, 2 * q, sc};
+    FastArith fa = {make_fastmod(q), sc};
     int bad = 0, badi = 0, badf = -1, badfi = -1;
     // exact path: always matches the oracle word for word
     ref = a;
     ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
-    emul_fwd<C>(a, out, ftw.data(), ex);
+    emul_fwd<C, C>(a, out, ftw.data(), ex);
     for (uint64_t i = 0; i < n; ++i) bad += out[i] != ref[i];
     const bool fwd_in_contract = (garbage == 0 || garbage == 3 || garbage == 4) && fwd_fast_modulus_ok(q, LOGN);
     if (fwd_in_contract) {
-        emul_fwd<C>(a, out, ftw.data(), fa);
+        emul_fwd<C, C>(a, out, ftw.data(), fa);
         badf = 0;
         for (uint64_t i = 0; i < n; ++i) badf += out[i] != ref[i];
     }
     ref = a;
     ho_inv_ntt(ref.data(), n, q, ir.data(), ip.data(), inv_n, inv_n_w);
-    emul_inv<C>(a, out, itw.data(), ex, sc);
+    emul_inv<C, C>(a, out, itw.data(), ex);
     for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
     const bool inv_in_contract = (garbage == 0 || garbage == 4) && inv_fast_modulus_ok(q);
     if (inv_in_contract) {
-        emul_inv<C>(a, out, itw.data(), fa, sc);
+        emul_inv<C, C>(a, out, itw.data(), fa);
         badfi = 0;
         for (uint64_t i = 0; i < n; ++i) badfi += out[i] != ref[i];
     }
     printf("LOGN=%d LOGE=%d q=%llu in=%d exact fwd/inv mismatch=%d/%d fast fwd/inv mismatch=%d/%d pack_cover_err=%d\n",
            LOGN, LOGE, (unsigned long long)q, garbage, bad, badi, badf, badfi, cover);
     return bad + badi + (badf > 0 ? badf : 0) + (badfi > 0 ? badfi : 0) + cover;
+}
+
+// small-modulus (uint32) path: configuration with 32-word rows
+template <int LOGN, int LOGE>
+int run_small(uint64_t q, int kind) {
+    using C64 = NttCfg<LOGN, LOGE>;
+    using C = NttCfg<LOGN, LOGE, 5>;
+    const uint64_t n = C::N;
+    uint64_t w = ho_min_primitive_root(2 * n, q);
+    std::vector<uint64_t> roots(n), precon(n), ir(n), ip(n), a(n), ref(n), out(n);
+    ho_compute_roots(n, q, w, roots.data(), precon.data(), ir.data(), ip.data());
+    std::vector<Tw32> ftw(C::FWD_ENTRIES), itw(C::INV_ENTRIES);
+    int cover = 0;
+    std::vector<int> uf(n, 0), ui(n, 0);
+    for (uint32_t e = 0; e < (uint32_t)C::FWD_ENTRIES; ++e) {
+        int s = fwd_pack_src<C>(e);
+        ftw[e] = s < 0 ? Tw32{0, 0} : Tw32{(uint32_t)roots[s], (uint32_t)(precon[s] >> 32)};
+        if (s >= 0) uf[s]++;
+    }
+    for (uint32_t e = 0; e < (uint32_t)C::INV_ENTRIES; ++e) {
+        int s = inv_pack_src<C>(e);
+        itw[e] = s < 0 ? Tw32{0, 0} : Tw32{(uint32_t)ir[s], (uint32_t)(ip[s] >> 32)};
+        if (s >= 0) ui[s]++;
+    }
+    for (uint64_t i = 1; i < n; ++i) cover += (uf[i] != 1) + (ui[i] != 1);
+    ho_splitmix_fill(a.data(), n, 31 + LOGN, q);
+    if (kind == 1) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 4 * q - 1 - (i % 5) : q - 1;   // edge of fwd contract
+    if (kind == 2) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 2 * q - 1 - (i % 3) : q - 1;   // edge of inv contract
+    uint64_t inv_n = ho_inv_mod(n % q, q), inv_n_w = ho_mul_mod(inv_n, ir[n - 1], q);
+    InvScale sc = {inv_n, ho_mult_factor64(inv_n, q), inv_n_w, ho_mult_factor64(inv_n_w, q)};
+    SmallArith sa = {make_small32(q, sc)};
+    int bad = 0, badi = -1;
+    ref = a;
+    ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
+    emul_fwd<C64, C>(a, out, ftw.data(), sa);
+    for (uint64_t i = 0; i < n; ++i) bad += out[i] != ref[i];
+    if (kind != 1) {
+        ref = a;
+        ho_inv_ntt(ref.data(), n, q, ir.data(), ip.data(), inv_n, inv_n_w);
+        emul_inv<C64, C>(a, out, itw.data(), sa);
+        badi = 0;
+        for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
+    }
+    printf("SMALL LOGN=%d LOGE=%d q=%llu in=%d fwd/inv mismatch=%d/%d pack_cover_err=%d\n", LOGN, LOGE,
+           (unsigned long long)q, kind, bad, badi, cover);
+    return bad + (badi > 0 ? badi : 0) + cover;
+}
+
+template <int LOGN, int LOGE>
+int run_small_all() {
+    uint64_t p[1];
+    int rc = 0;
+    size_t bits[] = {16, 20, 27, 29};
+    for (size_t b : bits) {
+        if (((size_t)1 << b) < ((size_t)2 << LOGN)) continue;
+        if (ho_generate_primes(p, 1, b, (size_t)1 << LOGN) != 1) continue;
+        for (int k = 0; k < 3; ++k) rc += run_small<LOGN, LOGE>(p[0], k);
+    }
+    rc += run_small<LOGN, LOGE>(136314881ULL % ((2ULL << LOGN)) == 1 ? 136314881ULL : p[0], 0);   // the reference's bench prime
+    return rc;
 }
 
 template <int LOGN, int LOGE>
@@ -159,6 +242,8 @@ int main() {
     rc += run_all<14, 5>();
     rc += run_all<13, 5>();
     rc += run_all<12, 5>();
+    rc += run_small_all<14, 5>();
+    rc += run_small_all<13, 5>();
     // fast-arithmetic unit properties
     {
         uint64_t qs[] = {12289, 1073153, 2251799814045697ULL, (1ULL << 57) + 0x1234567ULL * 2 + 1, (1ULL << 60) - 93};

@@ -206,3 +206,26 @@ def test_large_moduli_take_the_exact_kernels(hb, bits):
     for i in range(3):
         assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t))
         assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t))
+
+
+@pytest.mark.parametrize("q", [136314881, None, 65537])
+def test_small_modulus_32bit_path(hb, q):
+    """q < 2^30 runs the uint32 kernels (N = 16384); same stimuli, incl. garbage
+    (deferred to the exact 64-bit kernel) and the edge of the contract; results
+    must be identical with the path switched off."""
+    q = q or ob.primes(1, 29, N)[0]
+    t = ob.Tables(N, q)
+    polys = [stimulus(k, N, q, 200 + i) for i, k in enumerate(STIMULI)]
+    polys.append(np.where(np.arange(N) % 2 == 0, 4 * q - 1, q - 1).astype(np.uint64))     # fwd contract edge
+    polys.append(np.where(np.arange(N) % 2 == 0, 2 * q - 1, 0).astype(np.uint64))         # inv contract edge
+    polys.append(np.full(N, 2**32 + 5, dtype=np.uint64))                                  # high word set
+    for small in (1, 0):
+        hb.set_option("small_path", small)
+        try:
+            got = run_fwd(hb, polys, t)
+            goti = run_inv(hb, polys, t)
+        finally:
+            hb.set_option("small_path", 1)
+        for i in range(len(polys)):
+            assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t)), (small, i)
+            assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t)), (small, i)
