@@ -428,6 +428,31 @@ def extras(args, hb, ob, dev, hbm_peak, world):
     ks_cpu_s = time.perf_counter() - t0
     out["keyswitch"]["cpu_baseline"] = {"value": cb / ks_cpu_s, "unit": "KeySwitch/s", "cores": threads, "kind": "port",
                                         "sample": f"{cb} items, oracle restatement (scalar), tables rebuilt per call"}
+    # -- the reference's own NTT benchmark modulus (benchmark/bench_fwd_ntt.cpp:29-30: q = 136314881,
+    #    28 bits): q < 2^30 takes the uint32 kernels --
+    q28 = 136314881
+    t28 = ob.Tables(N, q28)
+    x28 = torch.randint(0, q28, (BATCH, N), dtype=torch.int64, device=dev)
+    r28, p28 = gpu_tensor(t28.roots, dev), gpu_tensor(t28.precon, dev)
+    ir28, ip28 = gpu_tensor(t28.inv_roots, dev), gpu_tensor(t28.precon_inv, dev)
+    for _ in range(3):
+        hb.ntt_fwd(x28, r28, p28, q28, N)
+        hb.ntt_inv(x28, ir28, ip28, q28, t28.inv_n, t28.inv_n_w, N)
+    ef, ei = [], []
+    for _ in range(10):
+        a0, a1 = event_pair(); a0.record(); hb.ntt_fwd(x28, r28, p28, q28, N); a1.record(); ef.append((a0, a1))
+        b0, b1 = event_pair(); b0.record(); hb.ntt_inv(x28, ir28, ip28, q28, t28.inv_n, t28.inv_n_w, N); b1.record(); ei.append((b0, b1))
+    torch.cuda.synchronize()
+    f_s = float(np.mean([a.elapsed_time(b) for a, b in ef])) * 1e-3
+    i_s = float(np.mean([a.elapsed_time(b) for a, b in ei])) * 1e-3
+    out["ntt_28bit_modulus"] = {
+        "note": "same workload with the reference benchmark's modulus q=136314881 (benchmark/bench_fwd_ntt.cpp:30); "
+                "q < 2^30 runs the uint32 small-modulus kernels",
+        "fwd_per_s": BATCH / f_s, "inv_per_s": BATCH / i_s, "value": 2 * BATCH / (f_s + i_s), "unit": "NTT/s",
+        "roofline": {"bound": "hbm", "kernel": "k_ntt_small (forward)", "achieved": BATCH * NTT_BYTES / f_s / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": BATCH * NTT_BYTES / f_s / 1e9 / hbm_peak,
+                     "frac_inverse": BATCH * NTT_BYTES / i_s / 1e9 / hbm_peak}}
+    del x28
     # -- dyadic multiply, BASELINE configs[2] --
     moduli = np.array(ob.primes(DY_M, 51, DY_N), dtype=np.uint64)
     op1 = torch.randint(0, int(moduli[0]), (DY_BATCH, 2 * DY_M * DY_N), dtype=torch.int64, device=dev)

@@ -475,13 +475,29 @@ HB_D void inv_mid_passes32(uint32_t tid, uint32_t* S, const Tw32* tw, const A& a
     }
 }
 
-// 32 output words (one uint32 row widened) -> 8 x 32-byte stores
-HB_D void st_row32_as_u64(uint64_t* dst, const uint32_t* v) {
+// Forward results of a warp (32 rows x 32 uint32 words = 1024 consecutive
+// outputs) leave through the warp's 4 KiB slice of the dead working buffer:
+// rows go in with the tail pattern, come out with the lanes along consecutive
+// words, are widened to uint64 and written as 32-byte stores -- 1 KiB contiguous
+// per warp instruction instead of 32-byte pieces at a 256-byte lane stride.
+template <class C32>
+HB_D void store_rows32_coalesced(uint32_t* S, uint64_t* dst, uint32_t row, const uint32_t* v) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* slice = S + (threadIdx.x >> 5) * 1024;
+    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "l"((uint64_t)v[4 * c]),
-                     "l"((uint64_t)v[4 * c + 1]), "l"((uint64_t)v[4 * c + 2]), "l"((uint64_t)v[4 * c + 3])
+    for (int c = 0; c < 8; ++c) st_chunk(slice + lane * 32 + (((uint32_t)c ^ (lane & 7u)) << 2), v + 4 * c);
+    __syncwarp();
+    uint64_t* out = dst + (size_t)(row - lane) * C32::ROW;     // first output word of the warp's 32 rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t r = i * 4 + (lane >> 3), ch = lane & 7u;
+        uint32_t w[4];
+        ld_chunk(slice + r * 32 + ((ch ^ (r & 7u)) << 2), w);
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(out + i * 128 + lane * 4), "l"((uint64_t)w[0]),
+                     "l"((uint64_t)w[1]), "l"((uint64_t)w[2]), "l"((uint64_t)w[3])
                      : "memory");
+    }
 }
 
 // forward, small modulus: base -> dst (bit-reversed order, [0,q)); false = deferred
@@ -509,7 +525,9 @@ HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     fwd_tail_compute<C32>(tid, v, t.ftw32, a);
 #pragma unroll
     for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
-        st_row32_as_u64(dst + (size_t)(tid + ri * C32::NT) * C32::ROW, v + ri * C32::ROW);
+        store_rows32_coalesced<C32>(S, dst, tid + ri * C32::NT, v + ri * C32::ROW);
+    // the next transform's first pass writes S: all staged rows must have been read back
+    __syncthreads();
     return true;
 }
 
