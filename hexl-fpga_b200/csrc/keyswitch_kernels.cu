@@ -23,7 +23,7 @@
 
 namespace hb {
 
-int g_ks_mac_items = 4;   // items served per key load in the MAC stage (4 or 8)
+int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys (slower: latency bound)
 
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
     return r < D ? r * (D - 1) + (j < r ? j : j - 1) : D * (D - 1) + j;
@@ -177,6 +177,45 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
             st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, reduce_small_multiple(a1[it][0], fm),
                 reduce_small_multiple(a1[it][1], fm));
         }
+    }
+}
+
+// Register-resident-key version: a thread owns ONE coefficient of one output
+// modulus, keeps its 2*D {key, Shoup factor} pairs in registers and walks over
+// a slice of the items, so the key set crosses L2 once per slice instead of
+// once per item group (the per-item-group version above is L2-bandwidth bound:
+// 29 MB of keys against 6 MB of operands).
+template <int DMAX>
+__global__ void __launch_bounds__(256, 2)
+k_ks_mac_regkeys(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
+                 uint64_t* __restrict__ ACC, uint32_t items, uint32_t items_per_slice) {
+    const uint32_t N = 1u << ks.logn;
+    const uint32_t l = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t r = blockIdx.y;
+    const uint32_t idx = (r == ks.D) ? ks.K - 1 : r;
+    const FastMod fm = ks.tabs[idx].fm;
+    TwPair k0[DMAX], k1[DMAX];
+#pragma unroll
+    for (int j = 0; j < DMAX; ++j)
+        if (j < (int)ks.D) {
+            k0[j] = ldpair(ks.keys_sh + (((size_t)j * 2 + 0) * ks.K + idx) * N + l);
+            k1[j] = ldpair(ks.keys_sh + (((size_t)j * 2 + 1) * ks.K + idx) * N + l);
+        }
+    const uint32_t b_begin = blockIdx.z * items_per_slice;
+    const uint32_t b_end = min(items, b_begin + items_per_slice);
+    for (uint32_t b = b_begin; b < b_end; ++b) {
+        uint64_t a0 = 0, a1 = 0;
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+            if (j < (int)ks.D) {
+                const uint64_t* op = ((uint32_t)j == r) ? t_target + ((size_t)b * ks.D + j) * N
+                                                        : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
+                const uint64_t x = __ldg(op + l);
+                a0 += mul_shoup_approx(x, k0[j].w, k0[j].wp, fm.nq);
+                a1 += mul_shoup_approx(x, k1[j].w, k1[j].wp, fm.nq);
+            }
+        ACC[(((size_t)b * 2 + 0) * ks.R + r) * N + l] = reduce_small_multiple(a0, fm);
+        ACC[(((size_t)b * 2 + 1) * ks.R + r) * N + l] = reduce_small_multiple(a1, fm);
     }
 }
 
@@ -346,7 +385,13 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         nl += 2;
     }
     dim3 g(C::N / 512, ks.R, (unsigned)items);
-    if (ks.fast_ok && ks.keys_sh) {
+    if (ks.fast_ok && ks.keys_sh && g_ks_mac_items == 1 && ks.D <= 8) {
+        // register-resident keys: ~8 item slices keep the grid several waves deep
+        const uint32_t slices = (uint32_t)(items < 8 ? items : 8);
+        const uint32_t per = (uint32_t)((items + slices - 1) / slices);
+        dim3 gk(C::N / 256, ks.R, (unsigned)((items + per - 1) / per));
+        k_ks_mac_regkeys<8><<<gk, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items, per);
+    } else if (ks.fast_ok && ks.keys_sh) {
         if (g_ks_mac_items == 8) {
             dim3 gf(C::N / 512, ks.R, (unsigned)((items + 7) / 8));
             k_ks_mac_fast<8><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
