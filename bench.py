@@ -66,46 +66,74 @@ def ncu_traffic(kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is
+    polled from a thread every ~2 ms (the timed region is tens of milliseconds,
+    far below nvidia-smi's loop granularity); nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.p = [], None
+        self.index, self.rows, self.stop_flag, self.nvml, self.h = index, [], False, None, None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.p = None
+            self.nvml = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for _, r in self.rows]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+    def _poll(self):
+        n = self.nvml
+        bits = [("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)]
+        while not self.stop_flag:
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                for nme, v in zip(names, f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
+                mhz = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), mhz, [nm for nm, b in bits if r & b]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(0.002)
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            f = [x.strip() for x in out.strip().split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return float(f[0]), float(f[1]), [nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")]
+        except Exception:
+            return None
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.nvml is None or not self.rows:
+            one = self._smi_once()
+            if one is None:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
+            return {"sm_mhz": one[0], "sm_max_mhz": one[1], "samples": 1, "reasons": one[2],
+                    "source": "nvidia-smi right after the timed region"}
+        self.t.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        reasons = sorted({x for r in rows for x in r[2]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max, "samples": len(rows),
+                "reasons": reasons, "source": "NVML polled every ~2 ms inside the timed region"}
 
 
 # --------------------------------------------------------------------------

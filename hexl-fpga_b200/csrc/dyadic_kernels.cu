@@ -32,6 +32,7 @@ k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
         s_dv = make_divisor(moduli[(moduli_per_item ? item * M : 0) + m]);
     __syncthreads();
     const Divisor dv = s_dv;
+    const bool lazy = (dv.q >> 63) == 0;   // CTA-uniform
 
     const uint64_t in_item = item * 2ull * M * n;
     const uint64_t out_item = item * 3ull * M * n;
@@ -58,17 +59,31 @@ k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
             x0[0] = x0p[i]; x1[0] = x1p[i]; y0[0] = y0p[i]; y1[0] = y1p[i];
             x0[1] = x1[1] = y0[1] = y1[1] = 0;
         }
+        if (lazy) {
+            // q < 2^63: the cross term is reduced once, from the 128-bit sum of
+            // its two products (x0*y1 + x1*y0 < 2q^2 <= q*2^64, so the high
+            // word of the normalised sum stays below the divisor)
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const uint64_t a0 = mod64(x0[k], dv), a1 = mod64(x1[k], dv);
-            const uint64_t b0 = mod64(y0[k], dv), b1 = mod64(y1[k], dv);
-            r0[k] = mulmod_reduced(a0, b0, dv);
-            const uint64_t c = mulmod_reduced(a0, b1, dv);
-            const uint64_t d = mulmod_reduced(a1, b0, dv);
-            uint64_t s = c + d;                      // c,d < q <= 2^64-1: detect wrap
-            if (s < c || s >= dv.q) s -= dv.q;
-            r1[k] = s;
-            r2[k] = mulmod_reduced(a1, b1, dv);
+            for (int k = 0; k < 2; ++k) {
+                const uint64_t a0 = mod64(x0[k], dv), a1 = mod64(x1[k], dv);
+                const uint64_t b0 = mod64(y0[k], dv), b1 = mod64(y1[k], dv);
+                r0[k] = mulmod_reduced(a0, b0, dv);
+                r1[k] = mul2add_mod_reduced(a0, b1, a1, b0, dv);
+                r2[k] = mulmod_reduced(a1, b1, dv);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint64_t a0 = mod64(x0[k], dv), a1 = mod64(x1[k], dv);
+                const uint64_t b0 = mod64(y0[k], dv), b1 = mod64(y1[k], dv);
+                r0[k] = mulmod_reduced(a0, b0, dv);
+                const uint64_t c = mulmod_reduced(a0, b1, dv);
+                const uint64_t d = mulmod_reduced(a1, b0, dv);
+                uint64_t s = c + d;                      // c,d < q <= 2^64-1: detect wrap
+                if (s < c || s >= dv.q) s -= dv.q;
+                r1[k] = s;
+                r2[k] = mulmod_reduced(a1, b1, dv);
+            }
         }
         if (i + 1 < end) {
             st2(r0p + i, r0[0], r0[1]);

@@ -281,4 +281,14 @@ HB_HD uint64_t mulmod_reduced(uint64_t a, uint64_t b, const Divisor& dv) {
     return rem_2by1(u1, u0, dv.d, dv.v) >> dv.s;
 }
 
+// (a*b + c*d) mod q with a,b,c,d < q < 2^63: one reduction of the 128-bit sum.
+HB_HD uint64_t mul2add_mod_reduced(uint64_t a, uint64_t b, uint64_t c, uint64_t d, const Divisor& dv) {
+    const uint64_t lo1 = a * b, lo2 = c * d;
+    const uint64_t lo = lo1 + lo2;
+    const uint64_t hi = mulhi64(a, b) + mulhi64(c, d) + ((lo < lo1) ? 1 : 0);
+    const uint64_t u1 = dv.s ? ((hi << dv.s) | (lo >> (64 - dv.s))) : hi;
+    const uint64_t u0 = lo << dv.s;
+    return rem_2by1(u1, u0, dv.d, dv.v) >> dv.s;
+}
+
 }  // namespace hb

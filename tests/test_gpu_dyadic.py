@@ -71,8 +71,10 @@ def test_random_primes_vs_oracle(hb, bits):
 def test_unreduced_and_extreme_moduli(hb):
     import torch
 
-    n, M, B = 1024, 5, 2
-    moduli = np.array([1, 2, 2**63 + 29, 2**64 - 59, 10], dtype=np.uint64)
+    n, M, B = 1024, 8, 2
+    # 2^63 is where the kernel switches from the lazily summed cross term to two
+    # separate reductions: cover both sides of it
+    moduli = np.array([1, 2, 2**63 + 29, 2**64 - 59, 10, 2**63 - 25, 2**63 - 1, 2**63], dtype=np.uint64)
     op1 = ob.splitmix(B * 2 * M * n, 5, 0)
     op2 = ob.splitmix(B * 2 * M * n, 6, 0)
     res = torch.zeros(B * 3 * M * n, dtype=torch.int64, device="cuda")

@@ -20,8 +20,8 @@ def gpu(a):
 op = sys.argv[1] if len(sys.argv) > 1 else "ntt"
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
-if op == "ntt":
-    N, q = 16384, 2251799814045697
+if op in ("ntt", "ntt28"):
+    N, q = 16384, (2251799814045697 if op == "ntt" else 136314881)
     t = ob.Tables(N, q)
     x = torch.randint(0, q, (batch, N), dtype=torch.int64, device="cuda")
     r, p, ir, ip = gpu(t.roots), gpu(t.precon), gpu(t.inv_roots), gpu(t.precon_inv)
