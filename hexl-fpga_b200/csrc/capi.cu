@@ -46,7 +46,9 @@ static int ilog2_exact(uint64_t n) {
 }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-static std::atomic<int> g_small_path{1};   // use the 32-bit kernels for q < 2^30 (option "small_path")
+// 32-bit kernels for q < 2^30 (option "small_path"): 0 off, 1 TMA landing buffer
+// (one CTA per SM), 2 direct global loads (two CTAs per SM)
+static std::atomic<int> g_small_path{1};
 
 hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
                        const hb::TwPair* itw, int logn, const hb::Tw32* ftw32, const hb::Tw32* itw32) {
@@ -66,7 +68,7 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.sm32 = hb::make_small32(q, t.sc);
     t.ftw32 = ftw32;
     t.itw32 = itw32;
-    t.small_ok = (hb::small_modulus_ok(q) && (ftw32 || itw32)) ? 1u : 0u;
+    t.small_ok = (hb::small_modulus_ok(q) && (ftw32 || itw32)) ? (uint32_t)g_small_path.load() : 0u;
     t.pad = 0;
     return t;
 }
@@ -149,7 +151,8 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "small_path")) {
-        g_small_path = value ? 1 : 0;
+        if (value < 0 || value > 2) return fail(HEXL_B200_EINVAL, "small_path must be 0, 1 or 2");
+        g_small_path = (int)value;
         return 0;
     }
     if (!strcmp(name, "ks_mac_items")) {

@@ -610,6 +610,172 @@ HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const Mo
     }
 }
 
+// ---------------------------------------------------------------------------
+// small-modulus path, second generation ("small2"): no landing buffer
+// ---------------------------------------------------------------------------
+// The first pass reads the uint64 polynomial straight from global memory into
+// registers (forward: columns, coalesced along the lanes; inverse: the 1024
+// consecutive words of a warp's 32 rows, dropped into the warp's own rows of
+// the working buffer), so a CTA needs only the 64 KiB uint32 working buffer
+// and 64 registers per thread: TWO CTAs per SM, whose barrier / load / store
+// phases overlap each other's butterflies.  The polynomial of the next
+// iteration is pulled towards L2 while the current one is transformed.
+template <class C32>
+struct Small2Plan {
+    static constexpr uint32_t FLAG_U32 = C32::N;     // two range-vote flags (iteration parity)
+    static constexpr size_t BYTES = (size_t)C32::N * 4 + 16;
+};
+
+HB_D uint64_t ldg_stream(const uint64_t* p) {
+    uint64_t x;
+    asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(x) : "l"(p));
+    return x;
+}
+HB_D void ldg_stream2(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    asm volatile("ld.global.cs.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+HB_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Range vote of the small2 kernels.  Flag (iter & 1) belongs to this iteration;
+// the other one (raised at most in the previous iteration, read by everybody
+// before this iteration's barrier) is cleared here, a full iteration ahead of
+// its next use.
+template <class C32>
+HB_D bool small2_vote(uint32_t* S, int bad, uint32_t iter) {
+    volatile uint32_t* flag = S + Small2Plan<C32>::FLAG_U32;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) flag[iter & 1u] = 1;
+    __syncthreads();
+    const bool deferred = flag[iter & 1u] != 0;
+    if (threadIdx.x == 0) flag[(iter & 1u) ^ 1u] = 0;
+    return deferred;
+}
+
+// forward first pass: word k of group g is poly[base(g) + (k << LS)]; the lanes
+// of a warp read consecutive words (256 contiguous bytes per instruction)
+template <class C, int R, int LS>
+HB_D void head_load_global_narrow(uint32_t tid, const uint64_t* poly, uint32_t* v, uint32_t& hi_or,
+                                  uint32_t& lo_max) {
+    using Gm = HeadGeom<C, R, LS>;
+    static_for<0, Gm::G>([&](auto gc) {
+        constexpr int gi = decltype(gc)::value;
+        const uint64_t* p = poly + Gm::base(tid + gi * C::NT);
+        static_for<0, (1 << R) / 8>([&](auto cc) {
+            constexpr int c0 = decltype(cc)::value * 8;
+            uint64_t t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = ldg_stream(p + ((uint32_t)(c0 + j) << LS));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hi_or |= (uint32_t)(t[j] >> 32);
+                lo_max = max(lo_max, (uint32_t)t[j]);
+                v[gi * (1 << R) + c0 + j] = (uint32_t)t[j];
+            }
+        });
+    });
+}
+
+template <class C32, int MODE>
+HB_D bool ntt_fwd_small2_cta(uint32_t* S, const ModTab& t, uint64_t* poly, uint32_t iter) {
+    using P0 = FwdPass<C32, 0>;
+    const uint32_t tid = threadIdx.x;
+    const SmallArith a = {t.sm32};
+    uint32_t v[C32::E];
+    uint32_t hi_or = 0, lo_max = 0;
+    head_load_global_narrow<C32, P0::R, P0::LS>(tid, poly, v, hi_or, lo_max);
+    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a);
+    head_store<C32, P0::R, P0::LS>(tid, S, v);
+    if constexpr (MODE == kFastVote) {
+        // forward contract: every word < 4q; global memory still holds the untouched input
+        if (small2_vote<C32>(S, (hi_or != 0) | (lo_max >= 2u * t.sm32.twoq), iter)) return false;
+    } else {
+        __syncthreads();
+    }
+    fwd_mid_passes32<C32, 1>(tid, S, t.ftw32, a);
+    tail_load<C32>(tid, S, v, XfSame32());
+    __syncthreads();                          // the staging slices below overwrite S
+    fwd_tail_compute<C32>(tid, v, t.ftw32, a);
+#pragma unroll
+    for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
+        store_rows32_coalesced<C32>(S, poly, tid + ri * C32::NT, v + ri * C32::ROW);
+    __syncthreads();                          // the next transform's first pass writes S
+    return true;
+}
+
+template <class C32, int MODE>
+HB_D bool ntt_inv_small2_cta(uint32_t* S, const ModTab& t, uint64_t* poly, uint32_t iter) {
+    using PL = InvPass<C32, C32::NP - 1>;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const SmallArith a = {t.sm32};
+    uint32_t v[C32::E];
+    uint32_t hi_or = 0, lo_max = 0;
+    // rows tid + ri*NT: the 32 rows of a warp are 1024 consecutive words of the
+    // polynomial -> coalesced 16-byte reads, narrowed into the warp's rows of S
+#pragma unroll
+    for (int ri = 0; ri < C32::E / C32::ROW; ++ri) {
+        const uint32_t row0 = (tid - lane) + ri * C32::NT;
+        const uint64_t* src = poly + (size_t)row0 * C32::ROW;
+#pragma unroll
+        for (int i0 = 0; i0 < 16; i0 += 4) {
+            uint64_t x[4], y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ldg_stream2(src + (i0 + j) * 64 + lane * 2, x[j], y[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hi_or |= (uint32_t)(x[j] >> 32) | (uint32_t)(y[j] >> 32);
+                lo_max = max(lo_max, max((uint32_t)x[j], (uint32_t)y[j]));
+                const uint32_t e = (i0 + j) * 64 + lane * 2;
+                const uint32_t r = row0 + (e >> 5), col = e & 31u;
+                uint32_t* d = S + r * C32::ROW + ((((col >> 2) ^ (r & 7u)) << 2) | (col & 3u));
+                *reinterpret_cast<uint2*>(d) = make_uint2((uint32_t)x[j], (uint32_t)y[j]);
+            }
+        }
+    }
+    __syncwarp();
+    tail_load<C32>(tid, S, v, XfSame32());
+    __syncwarp();                             // tail_store below rewrites the warp's rows
+    inv_tail_compute<C32>(tid, v, t.itw32, a);
+    tail_store<C32>(tid, S, v);
+    if constexpr (MODE == kFastVote) {
+        // inverse contract: every word < 2q
+        if (small2_vote<C32>(S, (hi_or != 0) | (lo_max >= t.sm32.twoq), iter)) return false;
+    } else {
+        __syncthreads();
+    }
+    inv_mid_passes32<C32, 0>(tid, S, t.itw32, a);
+    head_load<C32, PL::R, PL::LS>(tid, S, v, XfSame32());
+    __syncthreads();                          // S is free for the next transform's rows
+    inv_head_compute<C32, C32::NP - 1>(tid, v, t.itw32, a);
+#pragma unroll
+    for (int gi = 0; gi < (C32::E >> PL::R); ++gi)
+#pragma unroll
+        for (int k = 0; k < (1 << PL::R); ++k) poly[inv_last_index<C32>(tid, gi, k)] = v[gi * (1 << PL::R) + k];
+    return true;
+}
+
+template <class C32, bool FWD, int MODE>
+HB_D void ntt_persistent_small2(uint64_t* data, const ModTab& t, uint32_t n_items, uint32_t* list) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint32_t* S = reinterpret_cast<uint32_t*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    if (tid < 2) S[Small2Plan<C32>::FLAG_U32 + tid] = 0;
+    __syncthreads();
+    uint32_t iter = 0;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++iter) {
+        const uint32_t next = item + gridDim.x;
+        if (next < n_items) {
+            // 128 KiB = 1024 lines of 128 bytes: two per thread
+            const uint8_t* nx = reinterpret_cast<const uint8_t*>(data + (size_t)next * C32::N);
+#pragma unroll
+            for (uint32_t l = tid; l < C32::N * 8 / 128; l += C32::NT) prefetch_l2(nx + (size_t)l * 128);
+        }
+        uint64_t* poly = data + (size_t)item * C32::N;
+        bool done;
+        if constexpr (FWD) done = ntt_fwd_small2_cta<C32, MODE>(S, t, poly, iter);
+        else done = ntt_inv_small2_cta<C32, MODE>(S, t, poly, iter);
+        if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
+    }
+}
+
 template <class C>
 constexpr size_t ntt_smem_bytes() {
     return SmemPlan<C>::BYTES;

@@ -47,6 +47,13 @@ __global__ void __launch_bounds__(C32::NT, 1) k_ntt_small(const __grid_constant_
     ntt_persistent_small<C64, C32, FWD, MODE>(&tmap, data, tab, n_items, list);
 }
 
+// second generation: no landing buffer, two CTAs per SM (ntt_block.cuh)
+template <class C32, bool FWD, int MODE>
+__global__ void __launch_bounds__(C32::NT, 2) k_ntt_small2(uint64_t* data, const ModTab tab, uint32_t n_items,
+                                                          uint32_t* list) {
+    ntt_persistent_small2<C32, FWD, MODE>(data, tab, n_items, list);
+}
+
 // ---- packed twiddle builder -------------------------------------------------
 template <class C>
 __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
@@ -179,6 +186,25 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
         // 64-bit exact kernel through the deferred list)
         if (tab.small_ok) {
             using C32 = NttCfg<14, 5, 5>;
+            if (tab.small_ok == 2) {
+                const size_t smem2 = Small2Plan<C32>::BYTES;
+                if (trust) {
+                    auto kern = k_ntt_small2<C32, FWD, kFastTrust>;
+                    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)))
+                        return e;
+                    kern<<<persistent_grid((const void*)kern, C32::NT, smem2, batch), C32::NT, smem2, st>>>(
+                        data, tab, (uint32_t)batch, list);
+                    *launches += 1;
+                    return cudaGetLastError();
+                }
+                auto kern = k_ntt_small2<C32, FWD, kFastVote>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2))) return e;
+                kern<<<persistent_grid((const void*)kern, C32::NT, smem2, batch), C32::NT, smem2, st>>>(
+                    data, tab, (uint32_t)batch, list);
+                if ((e = cudaGetLastError())) return e;
+                *launches += 2;
+                return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+            }
             const size_t smem = SmallPlan<C32>::BYTES;
             if (trust) {
                 auto kern = k_ntt_small<C, C32, FWD, kFastTrust>;

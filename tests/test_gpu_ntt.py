@@ -158,18 +158,21 @@ def test_host_api_ntt_intt(acquired):
     assert np.array_equal(one, ob.fwd_ntt(data[0], t))
 
 
-@pytest.mark.parametrize("n,batch", [(16384, 1), (16384, 149), (16384, 300), (1024, 1000), (4096, 777)])
-def test_persistent_loop_remainders(hb, n, batch):
+@pytest.mark.parametrize("n,batch,bits", [(16384, 1, 51), (16384, 149, 51), (16384, 300, 51), (1024, 1000, 51),
+                                          (4096, 777, 51), (16384, 297, 27), (16384, 700, 27), (16384, 2, 27)])
+def test_persistent_loop_remainders(hb, n, batch, bits):
     """Batches that are not a multiple of the persistent grid (148 CTAs x occupancy),
     a mix of in-contract and garbage polynomials (deferred exact list), checked
     against the oracle on a sample of positions and by the inverse round trip."""
     import torch
 
-    q = ob.primes(1, 51, n)[0]
+    q = ob.primes(1, bits, n)[0]          # bits=27: the uint32 small-modulus kernels (two CTAs per SM)
     t = ob.Tables(n, q)
     g = torch.Generator(device="cuda").manual_seed(batch)
     x = torch.randint(0, q, (batch, n), dtype=torch.int64, device="cuda", generator=g)
-    garbage_rows = sorted({0, batch // 2, batch - 1})
+    # incl. pairs that land on the same persistent CTA in consecutive iterations (grid 148 or 296)
+    extra = [r for r in (batch // 2 + 1, batch // 2 + 148, batch // 2 + 296) if batch > 4 and r < batch]
+    garbage_rows = sorted({0, batch // 2, batch - 1, *extra})
     for r in garbage_rows[1:] if batch > 1 else []:
         x[r] = torch.from_numpy(ob.splitmix(n, r + 1, 0).view(np.int64)).cuda()
     x0 = x.clone()
@@ -219,7 +222,7 @@ def test_small_modulus_32bit_path(hb, q):
     polys.append(np.where(np.arange(N) % 2 == 0, 4 * q - 1, q - 1).astype(np.uint64))     # fwd contract edge
     polys.append(np.where(np.arange(N) % 2 == 0, 2 * q - 1, 0).astype(np.uint64))         # inv contract edge
     polys.append(np.full(N, 2**32 + 5, dtype=np.uint64))                                  # high word set
-    for small in (1, 0):
+    for small in (2, 1, 0):               # 1: TMA landing buffer (default); 2: direct loads, two CTAs per SM
         hb.set_option("small_path", small)
         try:
             got = run_fwd(hb, polys, t)
