@@ -46,6 +46,7 @@ static int ilog2_exact(uint64_t n) {
 }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+static std::atomic<int> g_inv_lazy{0};     // correction-free inverse butterflies for q < 2^52 (option "inv_lazy")
 // 32-bit kernels for q < 2^30 (option "small_path"): 0 off, 1 TMA landing buffer
 // (one CTA per SM), 2 direct global loads (two CTAs per SM)
 static std::atomic<int> g_small_path{1};
@@ -69,7 +70,7 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.ftw32 = ftw32;
     t.itw32 = itw32;
     t.small_ok = (hb::small_modulus_ok(q) && (ftw32 || itw32)) ? (uint32_t)g_small_path.load() : 0u;
-    t.pad = 0;
+    t.inv_lazy_ok = (g_inv_lazy.load() && hb::inv_lazy_modulus_ok(q)) ? 1u : 0u;
     return t;
 }
 
@@ -153,6 +154,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "small_path")) {
         if (value < 0 || value > 2) return fail(HEXL_B200_EINVAL, "small_path must be 0, 1 or 2");
         g_small_path = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "inv_lazy")) {
+        g_inv_lazy = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "ks_mac_items")) {
@@ -286,10 +291,16 @@ int hexl_b200_dyadic_multiply(uint64_t* d_results, const uint64_t* d_op1, const 
                     (unsigned long long)n_moduli);
     if (!aligned16(d_results) || !aligned16(d_op1) || !aligned16(d_op2))
         return fail(HEXL_B200_EINVAL, "dyadic_multiply: buffers must be 16-byte aligned");
-    cudaError_t e = hb::launch_dyadic(d_results, d_op1, d_op2, n, d_moduli, n_moduli, batch,
-                                      moduli_per_item, (cudaStream_t)stream);
+    if (batch == 0) return 0;
+    // per-stream scratch (shared with the NTT calls of the stream, which are ordered before / after us)
+    uint8_t* scratch = nullptr;
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, hb::dyadic_scratch_bytes(n_moduli, batch, moduli_per_item),
+                                  (void**)&scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "dyadic_multiply: scratch");
+    e = hb::launch_dyadic(d_results, d_op1, d_op2, n, d_moduli, n_moduli, batch, moduli_per_item, scratch,
+                          (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "dyadic_multiply launch");
-    g_launches += batch ? 1 : 0;
+    g_launches += 2;
     return 0;
 }
 

@@ -17,21 +17,34 @@ constexpr int kDyThreads = 256;
 constexpr int kDyCoeffPerThread = 2;   // one 16-byte access per array
 constexpr int kDySlab = 2048;          // coefficients per CTA
 
+// reciprocal / shift of every modulus of the call, once (the 128-by-64 division
+// inside make_divisor is a few hundred instructions: far too slow to repeat in
+// every CTA of the streaming kernel behind a block barrier)
+__global__ void k_dyadic_prep(const uint64_t* __restrict__ moduli, Divisor* __restrict__ divs, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) divs[i] = make_divisor(moduli[i]);
+}
+
 __global__ void __launch_bounds__(kDyThreads)
 k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
-         const uint64_t* __restrict__ op2, uint32_t n, const uint64_t* __restrict__ moduli,
+         const uint64_t* __restrict__ op2, uint32_t n, const Divisor* __restrict__ divs,
          uint32_t M, int moduli_per_item, uint32_t slabs_per_poly) {
-    __shared__ Divisor s_dv;
     // blockIdx.x = ((item * M) + m) * slabs_per_poly + slab
     const uint64_t bid = blockIdx.x;
     const uint32_t slab = (uint32_t)(bid % slabs_per_poly);
     const uint64_t im = bid / slabs_per_poly;
     const uint32_t m = (uint32_t)(im % M);
     const uint64_t item = im / M;
-    if (threadIdx.x == 0)
-        s_dv = make_divisor(moduli[(moduli_per_item ? item * M : 0) + m]);
-    __syncthreads();
-    const Divisor dv = s_dv;
+    Divisor dv;
+    {
+        const ulonglong2* dp = reinterpret_cast<const ulonglong2*>(divs + (moduli_per_item ? item * M : 0) + m);
+        const ulonglong2 a = __ldg(dp), b = __ldg(dp + 1);
+        dv.d = a.x;
+        dv.v = a.y;
+        dv.s = (uint32_t)b.x;
+        dv.pad = 0;
+        dv.q = b.y;
+    }
     const bool lazy = (dv.q >> 63) == 0;   // CTA-uniform
 
     const uint64_t in_item = item * 2ull * M * n;
@@ -95,10 +108,19 @@ k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
     }
 }
 
+size_t dyadic_scratch_bytes(uint64_t n_moduli, uint64_t batch, int moduli_per_item) {
+    return (size_t)(moduli_per_item ? batch * n_moduli : n_moduli) * sizeof(Divisor);
+}
+
 cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op2, uint64_t n,
                           const uint64_t* moduli, uint64_t n_moduli, uint64_t batch,
-                          int moduli_per_item, cudaStream_t st) {
+                          int moduli_per_item, void* scratch, cudaStream_t st) {
     if (batch == 0 || n == 0 || n_moduli == 0) return cudaSuccess;
+    static_assert(sizeof(Divisor) == 32 && alignof(Divisor) == 8, "k_dyadic reads a Divisor as two 16-byte words");
+    Divisor* divs = static_cast<Divisor*>(scratch);
+    const uint64_t n_div = moduli_per_item ? batch * n_moduli : n_moduli;
+    if (n_div >> 32) return cudaErrorInvalidValue;
+    k_dyadic_prep<<<(unsigned)((n_div + 127) / 128), 128, 0, st>>>(moduli, divs, (uint32_t)n_div);
     // 16-byte accesses need even n for every slab base to stay aligned.
     if (n & 1) return cudaErrorInvalidValue;
     const uint32_t slabs = (uint32_t)((n + kDySlab - 1) / kDySlab);
@@ -110,7 +132,7 @@ cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op
         k_dyadic<<<(unsigned)(cnt * per_item), kDyThreads, 0, st>>>(
             res + off * 3 * n_moduli * n, op1 + off * 2 * n_moduli * n,
             op2 + off * 2 * n_moduli * n, (uint32_t)n,
-            moduli + (moduli_per_item ? off * n_moduli : 0), (uint32_t)n_moduli,
+            divs + (moduli_per_item ? off * n_moduli : 0), (uint32_t)n_moduli,
             moduli_per_item, slabs);
     }
     return cudaGetLastError();

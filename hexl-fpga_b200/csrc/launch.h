@@ -57,9 +57,11 @@ cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uin
 cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
                            uint32_t* list, cudaStream_t st, int* launches);
 
+size_t dyadic_scratch_bytes(uint64_t n_moduli, uint64_t batch, int moduli_per_item);
+// `scratch`: dyadic_scratch_bytes() of device memory, 16-byte aligned (per-modulus reciprocals)
 cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op2, uint64_t n,
                           const uint64_t* moduli, uint64_t n_moduli, uint64_t batch, int moduli_per_item,
-                          cudaStream_t st);
+                          void* scratch, cudaStream_t st);
 
 // keyswitch stages over a chunk of `items` ciphertexts (scratch layouts in
 // keyswitch_kernels.cu); returns the number of kernel launches in *launches

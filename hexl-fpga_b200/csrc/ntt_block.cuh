@@ -25,7 +25,7 @@ struct ModTab {
     const Tw32* ftw32;
     const Tw32* itw32;
     uint32_t small_ok;
-    uint32_t pad;
+    uint32_t inv_lazy_ok;   // q < 2^52: the correction-free inverse butterflies may be used
 };
 
 // ---- load transforms (applied to each word as it enters the transform) ----
@@ -356,9 +356,10 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 //   const ModTab& mod(item)
 //   Xf xf(item), Of of(item, store_map)
 // `list`: the deferred list (written in kFastVote, read in kExactList mode).
-template <class C, bool FWD, int MODE, class Job>
+template <class C, bool FWD, int MODE, class Job, bool LAZY = false>
 HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
                          uint32_t* list) {
+    static_assert(!LAZY || (!FWD && (MODE == kFastVote || MODE == kFastTrust)), "LAZY is an inverse fast-path option");
     // The 128-byte TMA swizzle needs the buffer 1024-byte aligned; the dynamic
     // shared window of a kernel without static shared memory starts aligned.
     uint64_t* W = smem_poly<C>();
@@ -389,7 +390,10 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         parity ^= 1;
         const ModTab& t = job.mod(item);
         bool done;
-        if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+        if constexpr (LAZY) {
+            const LazyInvArith a = {t.fm, t.sc};
+            done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (MODE == kFastVote || MODE == kFastTrust) {
             const FastArith a = {t.fm, t.sc};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);

@@ -208,6 +208,9 @@ struct ExactArith {
     HB_HD void inv_last(uint64_t& X, uint64_t& Y) const {
         inv_last_bfly(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, q, twoq);
     }
+    static constexpr bool kLazyInv = false;
+    template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv(X, Y, t); }
+    template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last(X, Y); }
 };
 
 // any-correct-algorithm path for in-contract inputs (modarith.cuh)
@@ -222,6 +225,53 @@ struct FastArith {
     HB_HD void inv(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv_bfly_fast(X, Y, t.w, t.wp, m); }
     HB_HD void inv_last(uint64_t& X, uint64_t& Y) const {
         inv_last_bfly_fast(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, m);
+    }
+    static constexpr bool kLazyInv = false;
+    template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv(X, Y, t); }
+    template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last(X, Y); }
+};
+
+// inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
+// E = log2 of the bound (in units of q) of the words entering the stage
+struct LazyInvArith {
+    using elem = uint64_t;
+    using Tw = TwPair;
+    FastMod m;
+    InvScale sc;
+    static constexpr bool kLazyInv = true;
+    HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
+    template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
+        inv_bfly_lazy<E>(X, Y, t.w, t.wp, m);
+    }
+    template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const {
+        inv_last_bfly_lazy<E>(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, m);
+    }
+    HB_HD uint64_t reduce(uint64_t x) const { return reduce_mid(x, m); }
+};
+
+// Bound schedule of the lazy inverse: words enter the transform below 2q (E = 1),
+// every stage adds one to E, and a pass that ends with E >= 8 (and is not the
+// last) reduces its words to [0,q) before storing them.
+template <class C>
+struct InvLazy {
+    static constexpr int pass_stages(int p) { return p < 0 ? C::LOGROW : C::pass_r(p); }   // p = -1: tail
+    static constexpr bool reduce_after_e(int p, int e_out) { return p < C::NP - 1 && e_out >= 8; }
+    static constexpr int e_in(int p) {
+        int e = 1;
+        for (int i = -1; i < p; ++i) {
+            e += pass_stages(i);
+            if (reduce_after_e(i, e)) e = 1;
+        }
+        return e;
+    }
+    static constexpr int e_out(int p) { return e_in(p) + pass_stages(p); }
+    static constexpr bool reduce_after(int p) { return reduce_after_e(p, e_out(p)); }
+    static constexpr bool valid() {
+        for (int p = -1; p < C::NP; ++p) {
+            if (e_in(p) + pass_stages(p) - 1 > 11) return false;     // 2^(E+1) q < 2^64 at every stage
+            if (reduce_after(p) && e_out(p) > 10) return false;      // reduce_mid handles < 1024q
+        }
+        return true;
     }
 };
 
@@ -286,6 +336,9 @@ struct SmallArith {
         X = csub32(mul_lazy32(tx, m.inv_n, m.inv_n_p, m.nq), m.q);
         Y = csub32(mul_lazy32(ty, m.inv_n_w, m.inv_n_w_p, m.nq), m.q);
     }
+    static constexpr bool kLazyInv = false;
+    template <int E> HB_HD void inv_at(uint32_t& X, uint32_t& Y, const Tw32& t) const { inv(X, Y, t); }
+    template <int E> HB_HD void inv_last_at(uint32_t& X, uint32_t& Y) const { inv_last(X, Y); }
 };
 HB_HD bool small_modulus_ok(uint64_t q) { return q < ((uint64_t)1 << 30); }
 HB_HD Small32 make_small32(uint64_t q, const InvScale& sc) {
@@ -342,7 +395,7 @@ HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
 // pairs k with k + 2^d inside blocks of 2^(d+1); its twiddle
 // inv_roots[1 + N - (N >> u) + (idx >> (u+1))] (ntt.cpp:600-636) is packed at
 // slot 2^(R-1-d) + blk.  When LAST, the final stage is the inv_n-fused one.
-template <int R, bool LAST, int TS, class A>
+template <int R, bool LAST, int TS, int E0, class A>
 HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
     static_for<0, R>([&](auto dc) {
         constexpr int d = decltype(dc)::value;
@@ -352,13 +405,13 @@ HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
             if constexpr (LAST && d == R - 1) {
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    a.inv_last(v[blk * 2 * half + j], v[blk * 2 * half + j + half]);
+                    a.template inv_last_at<E0 + d>(v[blk * 2 * half + j], v[blk * 2 * half + j + half]);
                 });
             } else {
                 const typename A::Tw t = a.ld(g + ((1 << (R - 1 - d)) + blk) * TS);
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    a.inv(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
+                    a.template inv_at<E0 + d>(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
                 });
             }
         });
@@ -541,8 +594,13 @@ HB_HD void inv_tail_compute(uint32_t tid, typename A::elem* v, const typename A:
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tid + ri * C::NT;
-        inv_group<C::LOGROW, false, 32>(v + ri * C::ROW, tw + tail_tw_base<C>(row), a);
+        inv_group<C::LOGROW, false, 32, 1>(v + ri * C::ROW, tw + tail_tw_base<C>(row), a);
     });
+    if constexpr (A::kLazyInv) {
+        static_assert(InvLazy<C>::valid(), "lazy inverse bound schedule broken for this shape");
+        if constexpr (InvLazy<C>::reduce_after(-1))
+            static_for<0, C::E>([&](auto ec) { v[decltype(ec)::value] = a.reduce(v[decltype(ec)::value]); });
+    }
 }
 
 template <class C, int P, class A>
@@ -552,8 +610,13 @@ HB_HD void inv_head_compute(uint32_t tid, typename A::elem* v, const typename A:
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t hi = Gm::hi(tid + gi * C::NT);
-        inv_group<Ps::R, Ps::LAST, 1>(v + gi * (1 << Ps::R), tw + C::inv_off(P) + (hi << Ps::R), a);
+        inv_group<Ps::R, Ps::LAST, 1, (A::kLazyInv ? InvLazy<C>::e_in(P) : 1)>(
+            v + gi * (1 << Ps::R), tw + C::inv_off(P) + (hi << Ps::R), a);
     });
+    if constexpr (A::kLazyInv) {
+        if constexpr (InvLazy<C>::reduce_after(P))
+            static_for<0, C::E>([&](auto ec) { v[decltype(ec)::value] = a.reduce(v[decltype(ec)::value]); });
+    }
 }
 
 // in-place inverse head pass (not the last one)

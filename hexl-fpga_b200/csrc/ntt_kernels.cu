@@ -34,10 +34,10 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_fwd(const __grid_con
                                                    uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
 }
-template <class C, int MODE>
+template <class C, int MODE, bool LAZY = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
                                                    uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, false, MODE>(&tmap, nullptr, job, n_items, list);
+    ntt_persistent<C, false, MODE, JobInv<C>, LAZY>(&tmap, nullptr, job, n_items, list);
 }
 
 // small-modulus kernels (q < 2^30): uint32 arithmetic, see ntt_block.cuh
@@ -154,11 +154,20 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, smap, job, (uint32_t)cnt,
                                                                                        list);
     } else {
-        auto kern = k_ntt_inv<C, MODE>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
         JobInv<C> job;
         job.data = base;
         job.tab = tab;
+        if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+            if (tab.inv_lazy_ok) {   // q < 2^52: butterflies without per-stage corrections
+                auto kern = k_ntt_inv<C, MODE, true>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+                kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt,
+                                                                                               list);
+                return cudaGetLastError();
+            }
+        }
+        auto kern = k_ntt_inv<C, MODE>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
         kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt, list);
     }
     return cudaGetLastError();

@@ -128,17 +128,19 @@ int run(uint64_t q, int garbage) {
     if (garbage == 2) for (auto& x : a) x = ~(uint64_t)0;
     if (garbage == 3) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 4 * q - 1 - (i % 5) : q - 1;  // edge of fwd contract
     if (garbage == 4) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? 2 * q - 1 - (i % 3) : q - 1;  // edge of inv contract
+    if (garbage == 5) for (uint64_t i = 0; i < n; ++i) a[i] = 2 * q - 1;   // worst growth of the lazy inverse sums
     uint64_t inv_n = ho_inv_mod(n % q, q), inv_n_w = ho_mul_mod(inv_n, ir[n - 1], q);
     InvScale sc = {inv_n, ho_mult_factor64(inv_n, q), inv_n_w, ho_mult_factor64(inv_n_w, q)};
     ExactArith ex = {q, 2 * q, sc};
     FastArith fa = {make_fastmod(q), sc};
-    int bad = 0, badi = 0, badf = -1, badfi = -1;
+    LazyInvArith la = {make_fastmod(q), sc};
+    int bad = 0, badi = 0, badf = -1, badfi = -1, badli = -1;
     // exact path: always matches the oracle word for word
     ref = a;
     ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
     emul_fwd<C, C>(a, out, ftw.data(), ex);
     for (uint64_t i = 0; i < n; ++i) bad += out[i] != ref[i];
-    const bool fwd_in_contract = (garbage == 0 || garbage == 3 || garbage == 4) && fwd_fast_modulus_ok(q, LOGN);
+    const bool fwd_in_contract = (garbage == 0 || garbage >= 3) && fwd_fast_modulus_ok(q, LOGN);
     if (fwd_in_contract) {
         emul_fwd<C, C>(a, out, ftw.data(), fa);
         badf = 0;
@@ -148,15 +150,21 @@ int run(uint64_t q, int garbage) {
     ho_inv_ntt(ref.data(), n, q, ir.data(), ip.data(), inv_n, inv_n_w);
     emul_inv<C, C>(a, out, itw.data(), ex);
     for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
-    const bool inv_in_contract = (garbage == 0 || garbage == 4) && inv_fast_modulus_ok(q);
+    const bool inv_in_contract = (garbage == 0 || garbage >= 4) && inv_fast_modulus_ok(q);
     if (inv_in_contract) {
         emul_inv<C, C>(a, out, itw.data(), fa);
         badfi = 0;
         for (uint64_t i = 0; i < n; ++i) badfi += out[i] != ref[i];
+        if (inv_lazy_modulus_ok(q)) {      // correction-free butterflies + mid-transform reduction
+            emul_inv<C, C>(a, out, itw.data(), la);
+            badli = 0;
+            for (uint64_t i = 0; i < n; ++i) badli += out[i] != ref[i];
+        }
     }
-    printf("LOGN=%d LOGE=%d q=%llu in=%d exact fwd/inv mismatch=%d/%d fast fwd/inv mismatch=%d/%d pack_cover_err=%d\n",
-           LOGN, LOGE, (unsigned long long)q, garbage, bad, badi, badf, badfi, cover);
-    return bad + badi + (badf > 0 ? badf : 0) + (badfi > 0 ? badfi : 0) + cover;
+    printf("LOGN=%d LOGE=%d q=%llu in=%d exact fwd/inv mismatch=%d/%d fast fwd/inv mismatch=%d/%d lazy inv mismatch=%d "
+           "pack_cover_err=%d\n",
+           LOGN, LOGE, (unsigned long long)q, garbage, bad, badi, badf, badfi, badli, cover);
+    return bad + badi + (badf > 0 ? badf : 0) + (badfi > 0 ? badfi : 0) + (badli > 0 ? badli : 0) + cover;
 }
 
 // small-modulus (uint32) path: configuration with 32-word rows
@@ -227,7 +235,7 @@ int run_all() {
     for (size_t b : bits) {
         if (((size_t)1 << b) < ((size_t)2 << LOGN)) continue;
         if (ho_generate_primes(p, 1, b, (size_t)1 << LOGN) != 1) continue;
-        for (int g = 0; g < 5; ++g) rc += run<LOGN, LOGE>(p[0], g);
+        for (int g = 0; g < 6; ++g) rc += run<LOGN, LOGE>(p[0], g);
     }
     return rc;
 }
@@ -258,6 +266,10 @@ int main() {
                 if (t >= 4 * q || t % q != ho_mul_mod(w, y % q, q)) ++fbad;
                 uint64_t v = (q < (1ULL << 58)) ? r[2] % (60 * q) : r[2] % q;
                 if (reduce_small_multiple(v, m) != v % q) ++fbad;
+                if (inv_lazy_modulus_ok(q)) {
+                    const uint64_t v2 = (it % 3 == 0) ? 1024 * q - 1 - (r[2] % 1000) : r[2] % (1024 * q);
+                    if (reduce_mid(v2, m) != v2 % q) ++fbad;
+                }
             }
         }
         printf("fast arithmetic property failures=%d\n", fbad);

@@ -232,3 +232,24 @@ def test_small_modulus_32bit_path(hb, q):
         for i in range(len(polys)):
             assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t)), (small, i)
             assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t)), (small, i)
+
+
+@pytest.mark.parametrize("n,bits", [(16384, 51), (16384, 40), (8192, 51), (4096, 51), (2048, 45), (1024, 51)])
+def test_inverse_lazy_and_corrected_butterflies_agree(hb, n, bits):
+    """q < 2^52 takes the correction-free inverse butterflies (one reduction half way);
+    option inv_lazy=0 keeps the per-stage corrected ones.  Both must give the oracle's
+    words, including on the inputs that make the lazy sums grow fastest (all 2q-1)."""
+    q = ob.primes(1, bits, n)[0]
+    t = ob.Tables(n, q)
+    polys = [stimulus(k, n, q, 300 + i) for i, k in enumerate(STIMULI)]
+    polys.append(np.full(n, 2 * q - 1, dtype=np.uint64))
+    polys.append(np.where(np.arange(n) % 2 == 0, 2 * q - 1, 0).astype(np.uint64))
+    want = [ob.inv_ntt(p, t) for p in polys]
+    for lazy in (1, 0):
+        hb.set_option("inv_lazy", lazy)
+        try:
+            got = run_inv(hb, polys, t)
+        finally:
+            hb.set_option("inv_lazy", 0)
+        for i in range(len(polys)):
+            assert np.array_equal(got[i], want[i]), (lazy, i)
