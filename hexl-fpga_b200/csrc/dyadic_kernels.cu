@@ -46,6 +46,7 @@ k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
         dv.q = b.y;
     }
     const bool lazy = (dv.q >> 63) == 0;   // CTA-uniform
+    const uint32_t qh = (uint32_t)(dv.q >> 32);
 
     const uint64_t in_item = item * 2ull * M * n;
     const uint64_t out_item = item * 3ull * M * n;
@@ -72,30 +73,28 @@ k_dyadic(uint64_t* __restrict__ res, const uint64_t* __restrict__ op1,
             x0[0] = x0p[i]; x1[0] = x1p[i]; y0[0] = y0p[i]; y1[0] = y1p[i];
             x0[1] = x1[1] = y0[1] = y1[1] = 0;
         }
-        if (lazy) {
-            // q < 2^63: the cross term is reduced once, from the 128-bit sum of
-            // its two products (x0*y1 + x1*y0 < 2q^2 <= q*2^64, so the high
-            // word of the normalised sum stays below the divisor)
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint64_t a0 = mod64(x0[k], dv), a1 = mod64(x1[k], dv);
-                const uint64_t b0 = mod64(y0[k], dv), b1 = mod64(y1[k], dv);
-                r0[k] = mulmod_reduced(a0, b0, dv);
-                r1[k] = mul2add_mod_reduced(a0, b1, a1, b0, dv);
-                r2[k] = mulmod_reduced(a1, b1, dv);
+        for (int k = 0; k < 2; ++k) {
+            uint64_t a0 = x0[k], a1 = x1[k], b0 = y0[k], b1 = y1[k];
+            // operands are normally reduced already: one test on the high words
+            // (sufficient, not necessary) skips the four 64-bit compares
+            const uint32_t mh = max(max((uint32_t)(a0 >> 32), (uint32_t)(a1 >> 32)),
+                                    max((uint32_t)(b0 >> 32), (uint32_t)(b1 >> 32)));
+            if (mh >= qh) {   // rare (always for q < 2^32): exact per-operand reduction
+                a0 = mod64(a0, dv); a1 = mod64(a1, dv); b0 = mod64(b0, dv); b1 = mod64(b1, dv);
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint64_t a0 = mod64(x0[k], dv), a1 = mod64(x1[k], dv);
-                const uint64_t b0 = mod64(y0[k], dv), b1 = mod64(y1[k], dv);
-                r0[k] = mulmod_reduced(a0, b0, dv);
-                const uint64_t c = mulmod_reduced(a0, b1, dv);
-                const uint64_t d = mulmod_reduced(a1, b0, dv);
+            const uint64_t as0 = a0 << dv.s, as1 = a1 << dv.s;
+            r0[k] = mulmod_preshifted(as0, b0, dv);
+            r2[k] = mulmod_preshifted(as1, b1, dv);
+            if (lazy) {
+                // q < 2^63: the cross term is reduced once, from the 128-bit sum of its two products
+                r1[k] = mul2add_mod_preshifted(as0, b1, as1, b0, dv);
+            } else {
+                const uint64_t c = mulmod_preshifted(as0, b1, dv);
+                const uint64_t d = mulmod_preshifted(as1, b0, dv);
                 uint64_t s = c + d;                      // c,d < q <= 2^64-1: detect wrap
                 if (s < c || s >= dv.q) s -= dv.q;
                 r1[k] = s;
-                r2[k] = mulmod_reduced(a1, b1, dv);
             }
         }
         if (i + 1 < end) {

@@ -332,6 +332,36 @@ HB_HD uint64_t mulmod_reduced(uint64_t a, uint64_t b, const Divisor& dv) {
     return rem_2by1(u1, u0, dv.d, dv.v) >> dv.s;
 }
 
+// full 64x64 -> 128 product from four 32x32 partial products (4 IMAD.WIDE)
+HB_HD void mul_full(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo) {
+    const uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32);
+    const uint64_t p00 = (uint64_t)a0 * b0, p01 = (uint64_t)a0 * b1, p10 = (uint64_t)a1 * b0, p11 = (uint64_t)a1 * b1;
+    const uint64_t mid = p01 + (p00 >> 32);              // < 2^64: (2^32-1)^2 + 2^32 - 1
+    const uint64_t mid2 = p10 + (uint32_t)mid;
+    hi = p11 + (mid >> 32) + (mid2 >> 32);
+    lo = (mid2 << 32) | (uint32_t)p00;
+}
+
+// Products with the normalisation shift applied to ONE OPERAND instead of the
+// 128-bit product: for a, b < q,  (a << s) * b = (a*b) << s  has its high word
+// below d = q << s, which is what rem_2by1 needs; the remainder comes back
+// shifted by s.  as_ = a << s.
+HB_HD uint64_t mulmod_preshifted(uint64_t as_, uint64_t b, const Divisor& dv) {
+    uint64_t u1, u0;
+    mul_full(as_, b, u1, u0);
+    return rem_2by1(u1, u0, dv.d, dv.v) >> dv.s;
+}
+// (a*b + c*e) mod q for a,b,c,e < q < 2^63 from pre-shifted a, c: the sum of
+// the two shifted products stays below d * 2^64 (2*q^2*2^s <= q*2^s*2^64).
+HB_HD uint64_t mul2add_mod_preshifted(uint64_t as_, uint64_t b, uint64_t cs_, uint64_t e, const Divisor& dv) {
+    uint64_t h1, l1, h2, l2;
+    mul_full(as_, b, h1, l1);
+    mul_full(cs_, e, h2, l2);
+    const uint64_t u0 = l1 + l2;
+    const uint64_t u1 = h1 + h2 + ((u0 < l1) ? 1 : 0);
+    return rem_2by1(u1, u0, dv.d, dv.v) >> dv.s;
+}
+
 // (a*b + c*d) mod q with a,b,c,d < q < 2^63: one reduction of the 128-bit sum.
 HB_HD uint64_t mul2add_mod_reduced(uint64_t a, uint64_t b, uint64_t c, uint64_t d, const Divisor& dv) {
     const uint64_t lo1 = a * b, lo2 = c * d;

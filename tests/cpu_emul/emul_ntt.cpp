@@ -289,6 +289,17 @@ int main() {
             if (am != a % q || bm != b % q) ++dbad;
             uint64_t m = mulmod_reduced(am, bm, dv);
             if (m != (uint64_t)(((unsigned __int128)am * bm) % q)) ++dbad;
+            // the dyadic kernel's forms: normalisation shift on one operand, lazily summed cross term
+            if (mulmod_preshifted(am << dv.s, bm, dv) != m) ++dbad;
+            uint64_t hi, lo;
+            mul_full(a, b, hi, lo);
+            if ((((unsigned __int128)hi << 64) | lo) != (unsigned __int128)a * b) ++dbad;
+            if ((q >> 63) == 0) {
+                const uint64_t cm = mod64(r[0] ^ r[1], dv), em = (it % 7 == 0) ? q - 1 : mod64(r[1] * 3 + it, dv);
+                const uint64_t want = (uint64_t)((((unsigned __int128)am * bm) % q + ((unsigned __int128)cm * em) % q) % q);
+                if (mul2add_mod_preshifted(am << dv.s, bm, cm << dv.s, em, dv) != want) ++dbad;
+                if (mul2add_mod_reduced(am, bm, cm, em, dv) != want) ++dbad;
+            }
         }
     }
     printf("divisor mismatches=%d\n", dbad);
