@@ -112,8 +112,14 @@ int hexl_b200_keyswitch(hexl_b200_ks_plan* plan, uint64_t* d_result, const uint6
 int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, uint64_t* inv_n,
                                uint64_t* inv_n_w);
 
-/* Kernel selection knobs for benchmarking (0 = default).  Not part of the
- * reference surface. */
+/* Kernel selection knobs for benchmarking.  Not part of the reference surface.
+ *   "ntt_variant"      bit 0: 32 words per thread at n = 16384 (default 1);
+ *                      bit 1: skip the input-range vote (caller guarantees the contract)
+ *   "small_path"       q < 2^30 kernels: 0 off, 1 uint32 kernels behind a TMA landing
+ *                      buffer (default), 2 uint32 kernels with direct loads, two CTAs / SM
+ *   "inv_lazy"         1: correction-free inverse butterflies for q < 2^52 (default 0)
+ *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16)
+ *   "ks_mac_items"     items sharing one key load in the keyswitch MAC (1, 4, 8) */
 int hexl_b200_set_option(const char* name, int64_t value);
 
 /* ------------------------------------------------------------------------- */
