@@ -278,6 +278,58 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
     return 0;
 }
 
+int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint64_t* d_b,
+                            const uint64_t* d_roots, const uint64_t* d_precon, const uint64_t* d_inv_roots,
+                            const uint64_t* d_precon_inv, uint64_t q, uint64_t inv_n, uint64_t inv_n_w,
+                            uint64_t n, uint64_t batch, void* stream) {
+    const int logn = ilog2_exact(n);
+    if (logn < 0 || !hb::ntt_shape_supported((uint32_t)logn))
+        return fail(HEXL_B200_EINVAL, "poly_multiply: n=%llu unsupported (power of two in [1024,16384])",
+                    (unsigned long long)n);
+    if (!d_result || !d_a || !d_b || !d_roots || !d_precon || !d_inv_roots || !d_precon_inv)
+        return fail(HEXL_B200_EINVAL, "poly_multiply: NULL pointer");
+    if (!aligned16(d_result) || !aligned16(d_a) || !aligned16(d_b))
+        return fail(HEXL_B200_EINVAL, "poly_multiply: buffers must be 16-byte aligned");
+    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "poly_multiply: modulus must be in [2, 2^62)");
+    if (inv_n >= q || inv_n_w >= q)
+        return fail(HEXL_B200_EINVAL, "poly_multiply: inv_n / inv_n_w must be reduced mod q");
+    if (batch == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int variant = g_ntt_variant.load() & 1;     // the range vote always runs on caller data
+    // per-stream scratch: packed forward / inverse twiddles, one deferred list, and NTT(b) of a chunk
+    const uint64_t chunk_max = 2048;
+    const uint64_t chunk = batch < chunk_max ? batch : chunk_max;
+    const size_t list_bytes = ((chunk + 1) * 4 + 255) & ~(size_t)255;
+    const size_t tb_off = (size_t)(1u << 20) + list_bytes;
+    uint8_t* scratch = nullptr;
+    cudaError_t e = g_scratch.get(st, tb_off + (size_t)chunk * n * 8, (void**)&scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: scratch");
+    hb::TwPair* pf = reinterpret_cast<hb::TwPair*>(scratch);
+    hb::TwPair* pi = reinterpret_cast<hb::TwPair*>(scratch + (1u << 19));
+    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (1u << 20));
+    uint64_t* tb = reinterpret_cast<uint64_t*>(scratch + tb_off);
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, pf, d_inv_roots, d_precon_inv, pi, list, st);
+    if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: pack twiddles");
+    const hb::ModTab t = make_modtab(q, inv_n, inv_n_w, pf, pi, logn, nullptr, nullptr);
+    int launches = 1;
+    for (uint64_t off = 0; off < batch; off += chunk) {
+        const uint64_t cnt = batch - off < chunk ? batch - off : chunk;
+        uint64_t* res = d_result + off * n;
+        // NTT(a) -> result, NTT(b) -> scratch; out-of-contract words take the exact kernel (deferred list)
+        if (off && (e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
+        e = hb::launch_ntt_fwd(res, t, (uint32_t)logn, cnt, variant, list, st, &launches, d_a + off * n);
+        if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: forward a");
+        if ((e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
+        e = hb::launch_ntt_fwd(tb, t, (uint32_t)logn, cnt, variant, list, st, &launches, d_b + off * n);
+        if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: forward b");
+        e = hb::launch_ntt_inv_mul(res, tb, t, (uint32_t)logn, cnt, variant, st);
+        if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: inverse");
+        ++launches;
+    }
+    g_launches += launches;
+    return 0;
+}
+
 int hexl_b200_dyadic_multiply(uint64_t* d_results, const uint64_t* d_op1, const uint64_t* d_op2,
                               uint64_t n, const uint64_t* d_moduli, uint64_t n_moduli,
                               uint64_t batch, int moduli_per_item, void* stream) {

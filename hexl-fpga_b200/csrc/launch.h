@@ -52,8 +52,13 @@ cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, u
 // variant bit 0: 32 words / thread at N = 16384 (else 16); bit 1: trust the
 // caller about the input range (no vote).  `list`: 1 + batch words of device
 // scratch, word 0 zero on entry (the deferred list of out-of-contract items).
+// `src` (forward only): read the polynomials from there and write the transforms to `data`
 cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
-                           uint32_t* list, cudaStream_t st, int* launches);
+                           uint32_t* list, cudaStream_t st, int* launches, const uint64_t* src = nullptr);
+// data[b] <- INTT(data[b] (.) other[b]): inverse transform whose first pass multiplies
+// by the second NTT-form operand on the fly (fused polynomial multiply)
+cudaError_t launch_ntt_inv_mul(uint64_t* data, const uint64_t* other, const ModTab& tab, uint32_t logn,
+                               uint64_t batch, int variant, cudaStream_t st);
 cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
                            uint32_t* list, cudaStream_t st, int* launches);
 

@@ -30,11 +30,13 @@ struct ModTab {
 
 // ---- load transforms (applied to each word as it enters the transform) ----
 struct XfIdent {
+    static constexpr bool kPost = false;
     HB_D uint64_t operator()(uint64_t x) const { return x; }
 };
 // base conversion of a coefficient-form word to this modulus
 // (device/keyswitch/intt1_redu.hpp:36-38)
 struct XfReduce {
+    static constexpr bool kPost = false;
     uint64_t q, mu;
     HB_D uint64_t operator()(uint64_t x) const { return barrett_reduce64(x, q, mu); }
 };
@@ -43,12 +45,48 @@ struct XfReduce {
 // out = (v mod qi + fix_i) mod qi.  When qk < 2*qi (same-size primes, the common
 // case) "v mod qi" is one conditional subtraction instead of a Barrett product.
 struct XfKsConvert {
+    static constexpr bool kPost = false;
     uint64_t q, mu, fix;
     uint32_t small;   // qk < 2*q
     HB_D uint64_t operator()(uint64_t v) const {
         uint64_t r = small ? (v - ((v >= q) ? q : 0)) : barrett_reduce64(v, q, mu);
         r += fix;
         return r - ((r >= q) ? q : 0);
+    }
+};
+
+// Fused polynomial multiply: the polynomial in shared memory is NTT(a); as the
+// first inverse pass pulls its rows into registers every word is multiplied by
+// the matching word of NTT(b), read straight from global memory (a row is 128
+// contiguous bytes), so the dyadic product never makes an HBM round trip.
+// Both factors are variable, so this is the generic 2-by-1 division of the
+// dyadic kernel (any modulus, unreduced words tolerated); the products are
+// canonical, inside the inverse transform's contract.
+struct XfMulGlobal {
+    static constexpr bool kPost = true;
+    const uint64_t* other;   // NTT(b) of this item, same (bit-reversed) order
+    Divisor dv;
+    HB_D uint64_t operator()(uint64_t x) const { return x; }
+    HB_D uint64_t mul(uint64_t x, uint64_t y) const {
+        if (((x | y) >> 32) >= (dv.q >> 32)) {   // rarely: operands not obviously below q
+            x = mod64(x, dv);
+            y = mod64(y, dv);
+        }
+        return mulmod_preshifted(x << dv.s, y, dv);
+    }
+    template <class C>
+    HB_D void post(uint32_t tid, uint64_t* v) const {
+        static_assert(C::ROW == 16, "64-bit rows");
+#pragma unroll
+        for (int ri = 0; ri < C::E / 16; ++ri) {
+            const uint64_t* p = other + (size_t)(tid + ri * C::NT) * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2*>(p + 2 * c));
+                v[ri * 16 + 2 * c] = mul(v[ri * 16 + 2 * c], y.x);
+                v[ri * 16 + 2 * c + 1] = mul(v[ri * 16 + 2 * c + 1], y.y);
+            }
+        }
     }
 };
 
@@ -321,6 +359,7 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     const uint32_t tid = threadIdx.x;
     uint64_t v[C::E];
     tail_load<C>(tid, W, v, xf);
+    if constexpr (Xf::kPost) xf.template post<C>(tid, v);
     int bad = 0;
     if constexpr (MODE == kFastVote) {
         // inverse contract: every word < 2q (ntt.cpp:600-606)

@@ -40,6 +40,20 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_con
     ntt_persistent<C, false, MODE, JobInv<C>, LAZY>(&tmap, nullptr, job, n_items, list);
 }
 
+// inverse transform of NTT(a) (.) NTT(b): the fused tail of a polynomial multiply
+template <class C>
+struct JobInvMul : JobPlain<C> {
+    const uint64_t* other;
+    Divisor dv;
+    HB_D XfMulGlobal xf(uint32_t item) const { return XfMulGlobal{other + (size_t)item * C::N, dv}; }
+    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
+};
+template <class C, int MODE>
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv_mul(const __grid_constant__ CUtensorMap tmap,
+                                                                   const JobInvMul<C> job, uint32_t n_items) {
+    ntt_persistent<C, false, MODE>(&tmap, nullptr, job, n_items, nullptr);
+}
+
 // small-modulus kernels (q < 2^30): uint32 arithmetic, see ntt_block.cuh
 template <class C64, class C32, bool FWD, int MODE>
 __global__ void __launch_bounds__(C32::NT, 1) k_ntt_small(const __grid_constant__ CUtensorMap tmap, uint64_t* data,
@@ -175,15 +189,16 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
 
 // `list`: device scratch of 1 + batch words whose first word is zero on entry
 // (launch_pack_twiddles resets it); `trust` skips the input-range vote.
+// `src`: where the polynomials are read from (nullptr: in place, from `data`)
 template <class C, bool FWD>
 static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch, bool trust, uint32_t* list,
-                              cudaStream_t st, int* launches) {
+                              cudaStream_t st, int* launches, const uint64_t* src = nullptr) {
     CUtensorMap tmap, smap;
     cudaError_t e;
     // the tensor map's row coordinate is 32 bits
     const uint64_t kMaxPolys = ((1ull << 32) - 1) / (C::N / 16);
     if (batch > kMaxPolys) return cudaErrorInvalidValue;
-    if ((e = make_poly_tmap(&tmap, data, batch, C::LOGN)) != cudaSuccess) return e;
+    if ((e = make_poly_tmap(&tmap, src ? src : data, batch, C::LOGN)) != cudaSuccess) return e;
     if ((e = make_poly_tmap(&smap, data, batch, C::LOGN, 32)) != cudaSuccess) return e;
     const bool fast = FWD ? tab.fwd_fast_ok : tab.inv_fast_ok;
     if (!fast) {
@@ -300,10 +315,44 @@ cudaError_t launch_pack_twiddles32(const uint64_t* roots, const uint64_t* precon
 }
 
 cudaError_t launch_ntt_fwd(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
-                           uint32_t* list, cudaStream_t st, int* launches) {
+                           uint32_t* list, cudaStream_t st, int* launches, const uint64_t* src) {
     if (batch == 0) return cudaSuccess;
     const bool trust = (variant & 2) != 0;
-    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true>(data, tab, batch, trust, list, st, launches)));
+    HB_DISPATCH_CFG(logn, variant, return (launch_one<C, true>(data, tab, batch, trust, list, st, launches, src)));
+    return cudaErrorInvalidValue;
+}
+
+template <class C>
+static cudaError_t launch_inv_mul_one(uint64_t* data, const uint64_t* other, const ModTab& tab, uint64_t batch,
+                                      cudaStream_t st) {
+    static_assert(SmemPlan<C>::kStagedStore || true, "");
+    CUtensorMap tmap;
+    cudaError_t e;
+    const uint64_t kMaxPolys = ((1ull << 32) - 1) / (C::N / 16);
+    if (batch > kMaxPolys) return cudaErrorInvalidValue;
+    if ((e = make_poly_tmap(&tmap, data, batch, C::LOGN)) != cudaSuccess) return e;
+    const size_t smem = ntt_smem_bytes<C>();
+    JobInvMul<C> job;
+    job.data = data;
+    job.tab = tab;
+    job.other = other;
+    job.dv = make_divisor(tab.q);
+    if (tab.inv_fast_ok) {
+        auto kern = k_ntt_inv_mul<C, kFastTrust>;   // the products are canonical: no range vote needed
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        kern<<<persistent_grid((const void*)kern, C::NT, smem, batch), C::NT, smem, st>>>(tmap, job, (uint32_t)batch);
+    } else {
+        auto kern = k_ntt_inv_mul<C, kExactAll>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        kern<<<persistent_grid((const void*)kern, C::NT, smem, batch), C::NT, smem, st>>>(tmap, job, (uint32_t)batch);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_inv_mul(uint64_t* data, const uint64_t* other, const ModTab& tab, uint32_t logn,
+                               uint64_t batch, int variant, cudaStream_t st) {
+    if (batch == 0) return cudaSuccess;
+    HB_DISPATCH_CFG(logn, variant, return (launch_inv_mul_one<C>(data, other, tab, batch, st)));
     return cudaErrorInvalidValue;
 }
 cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "hexl_b200_ntt_fwd": ([vp, vp, vp, u64, u64, u64, vp], C.c_int),
     "hexl_b200_ntt_inv": ([vp, vp, vp, u64, u64, u64, u64, u64, vp], C.c_int),
     "hexl_b200_dyadic_multiply": ([vp, vp, vp, u64, vp, u64, u64, C.c_int, vp], C.c_int),
+    "hexl_b200_poly_multiply": ([vp, vp, vp, vp, vp, vp, vp, u64, u64, u64, u64, u64, vp], C.c_int),
     "hexl_b200_ks_plan_create": ([C.POINTER(vp), u64, u64, u64, u64, u64, vp, vp, vp, vp], C.c_int),
     "hexl_b200_ks_plan_destroy": ([vp], C.c_int),
     "hexl_b200_keyswitch": ([vp, vp, vp, u64, vp], C.c_int),
@@ -154,6 +155,14 @@ def ntt_inv(operand, inv_roots, precon_inv, q, inv_n, inv_n_w, n):
     batch = operand.numel() // n
     _check(lib().hexl_b200_ntt_inv(_dptr(operand), _dptr(inv_roots), _dptr(precon_inv), q, inv_n, inv_n_w,
                                    n, batch, _stream()), "ntt_inv")
+
+
+def poly_multiply(result, a, b, roots, precon, inv_roots, precon_inv, q, inv_n, inv_n_w, n):
+    """result = a * b mod (x^n + 1, q) for every polynomial of the [batch, n] GPU tensors."""
+    batch = a.numel() // n
+    _check(lib().hexl_b200_poly_multiply(_dptr(result), _dptr(a), _dptr(b), _dptr(roots), _dptr(precon),
+                                         _dptr(inv_roots), _dptr(precon_inv), q, inv_n, inv_n_w, n, batch,
+                                         _stream()), "poly_multiply")
 
 
 def dyadic_multiply(results, op1, op2, n, moduli, n_moduli, batch, moduli_per_item=False):

@@ -67,6 +67,20 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_root_of_unity_p
                       const uint64_t* d_precon_inv_root_of_unity_powers, uint64_t coeff_modulus,
                       uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch, void* stream);
 
+/* Batched negacyclic polynomial multiply  result = a * b  mod (x^n + 1, q):
+ * INTT(NTT(a) (.) NTT(b)) with the dyadic product fused into the first pass
+ * of the inverse transform (no HBM round trip of the product).  The step on
+ * either side of the standalone primitives that the reference motivates
+ * (README.md:47) but does not ship as one call; SURVEY section 8(f) row 4.
+ * a, b, result: batch*n words, coefficient form, natural order; result may
+ * alias a (not b).  Tables and scalars as for hexl_b200_ntt_fwd / _ntt_inv. */
+int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint64_t* d_b,
+                            const uint64_t* d_root_of_unity_powers,
+                            const uint64_t* d_precon_root_of_unity_powers,
+                            const uint64_t* d_inv_root_of_unity_powers,
+                            const uint64_t* d_precon_inv_root_of_unity_powers, uint64_t coeff_modulus,
+                            uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch, void* stream);
+
 /* Batched dyadic ciphertext multiply.  Replaces input_fifo_usm + dyadic_multiply
  * + output_nb_fifo_usm (device/dyadic_multiply.cpp:61-376).  Per item:
  * op1/op2 [2][n_moduli][n], results [3][n_moduli][n] (host/inc/hexl-fpga.h:
