@@ -166,9 +166,13 @@ def cpu_ntt_rate(polys, threads, reps=1):
 
 
 def host_threads():
-    import oracle_binding as ob
-
-    return max(1, min(ob.oracle().ho_max_threads(), os.cpu_count() or 1))
+    """Host cores this process may use.  Deliberately NOT omp_get_max_threads(): torchrun
+    exports OMP_NUM_THREADS=1, and the CPU arms pass their thread count explicitly
+    (num_threads clause), so the baseline keeps all cores under torchrun too."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def run_reference(args, rank):
@@ -229,9 +233,20 @@ def event_pair():
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
+def _claim_stdout():
+    """Route everything that prints to fd 1 (NCCL's version banner, library chatter) to
+    stderr and return a file object on the real stdout for the one JSON line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+
+    json_out = _claim_stdout()
 
     import hexl_b200 as hb
     import oracle_binding as ob
@@ -335,7 +350,8 @@ def run_ours(args, rank, world, local_rank):
                    "api": "hexl_b200_host_{set_worksize_,}ntt/intt(+completed) on pinned host buffers",
                    "batch_per_gpu": e2e["batch"], "steps": e2e["steps"]}
     if rank == 0:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -446,16 +462,17 @@ def extras(args, hb, ob, dev, hbm_peak, world):
     out["keyswitch"]["e2e"] = {"value": eb / ks_e2e_s, "unit": "KeySwitch/s", "batch": eb,
                                "h2d_bytes_per_step": st["h2d_bytes"] // 2, "d2h_bytes_per_step": st["d2h_bytes"] // 2,
                                "api": "hexl_b200_host_keyswitch (+set_worksize/completed), pinned host buffers"}
-    # CPU baseline for keyswitch: the oracle port (intel-hexl's KeySwitch is unvendored)
-    threads = host_threads()
-    cb = max(2, threads)
-    c_res = np.ascontiguousarray(np.resize(p.result, (cb, 2 * KS_D * N)))
-    c_t = np.ascontiguousarray(np.resize(p.t_target, (cb, KS_D * N)))
-    t0 = time.perf_counter()
-    ob.keyswitch(c_res.reshape(-1), c_t.reshape(-1), N, KS_D, KS_K, p.moduli, p.keys, p.msf, cb, threads=threads)
-    ks_cpu_s = time.perf_counter() - t0
-    out["keyswitch"]["cpu_baseline"] = {"value": cb / ks_cpu_s, "unit": "KeySwitch/s", "cores": threads, "kind": "port",
-                                        "sample": f"{cb} items, oracle restatement (scalar), tables rebuilt per call"}
+    if world == 1:      # CPU baselines are an N=1 item
+        # CPU baseline for keyswitch: the oracle port (intel-hexl's KeySwitch is unvendored)
+        threads = host_threads()
+        cb = max(2, threads)
+        c_res = np.ascontiguousarray(np.resize(p.result, (cb, 2 * KS_D * N)))
+        c_t = np.ascontiguousarray(np.resize(p.t_target, (cb, KS_D * N)))
+        t0 = time.perf_counter()
+        ob.keyswitch(c_res.reshape(-1), c_t.reshape(-1), N, KS_D, KS_K, p.moduli, p.keys, p.msf, cb, threads=threads)
+        ks_cpu_s = time.perf_counter() - t0
+        out["keyswitch"]["cpu_baseline"] = {"value": cb / ks_cpu_s, "unit": "KeySwitch/s", "cores": threads, "kind": "port",
+                                            "sample": f"{cb} items, oracle restatement (scalar), tables rebuilt per call"}
     # -- the reference's own NTT benchmark modulus (benchmark/bench_fwd_ntt.cpp:29-30: q = 136314881,
     #    28 bits): q < 2^30 takes the uint32 kernels --
     q28 = 136314881
@@ -501,14 +518,39 @@ def extras(args, hb, ob, dev, hbm_peak, world):
                                         "peak": hbm_peak, "unit": "GB/s",
                                         "frac": DY_BATCH * DY_BYTES / dy_s / 1e9 / hbm_peak}}
     del op1, op2, rs
-    # -- CPU baseline (bounded sample of the headline workload) --
-    threads = host_threads()
-    polys = 128 * threads
-    rate, kind = cpu_ntt_rate(polys, threads)
-    out["cpu_baseline"] = {"value": rate, "unit": "NTT/s", "cores": threads, "kind": kind,
-                           "sample": f"{polys} polynomials fwd+inv, N=16384, 52-bit prime, {threads} threads; "
-                                     "reference tests/test_utils/ntt.cpp scalar Harvey NTT "
-                                     "(intel-hexl AVX-512 is unvendored)"}
+    # -- fused polynomial multiply: a*b mod (x^N+1, q), N=16384, 52-bit prime --
+    pb = 2048
+    t52 = ob.Tables(N, Q52)
+    pa = torch.randint(0, Q52, (pb, N), dtype=torch.int64, device=dev)
+    pbb = torch.randint(0, Q52, (pb, N), dtype=torch.int64, device=dev)
+    pr = torch.empty_like(pa)
+    tw = [gpu_tensor(x, dev) for x in (t52.roots, t52.precon, t52.inv_roots, t52.precon_inv)]
+    hb.poly_multiply(pr, pa, pbb, *tw, Q52, t52.inv_n, t52.inv_n_w, N)
+    e0, e1 = event_pair()
+    e0.record()
+    for _ in range(3):
+        hb.poly_multiply(pr, pa, pbb, *tw, Q52, t52.inv_n, t52.inv_n_w, N)
+    e1.record()
+    e1.synchronize()
+    pm_s = e0.elapsed_time(e1) * 1e-3 / 3
+    out["poly_multiply"] = {
+        "metric": "negacyclic polynomial multiplies/s (N=16384, 52-bit prime)", "value": pb / pm_s,
+        "unit": "multiplies/s", "batch": pb,
+        "note": "2 forward NTTs + inverse NTT with the dyadic product fused into its first pass (3 transforms per "
+                "multiply, compute-bound like the NTT itself)",
+        "roofline": {"bound": "hbm", "achieved": pb * 3 * N * 8 / pm_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": pb * 3 * N * 8 / pm_s / 1e9 / hbm_peak,
+                     "algorithmic_bytes_per_multiply": 3 * N * 8}}
+    del pa, pbb, pr
+    if world == 1:
+        # -- CPU baseline (bounded sample of the headline workload) --
+        threads = host_threads()
+        polys = 128 * threads
+        rate, kind = cpu_ntt_rate(polys, threads)
+        out["cpu_baseline"] = {"value": rate, "unit": "NTT/s", "cores": threads, "kind": kind,
+                               "sample": f"{polys} polynomials fwd+inv, N=16384, 52-bit prime, {threads} threads; "
+                                         "reference tests/test_utils/ntt.cpp scalar Harvey NTT "
+                                         "(intel-hexl AVX-512 is unvendored)"}
     return out
 
 
