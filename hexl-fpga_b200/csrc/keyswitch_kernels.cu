@@ -290,18 +290,26 @@ struct OfKsFinal {
             // touched with coalesced 8-byte accesses (lanes along the words)
             const uint32_t lane = threadIdx.x & 31u;
             uint64_t* slice = smem_poly<C>() + C::N + (threadIdx.x >> 5) * 512;
+            const uint32_t base = (rw - lane) * 16;   // first word of the warp's 32 rows
+            // all 32 global loads of the round are issued before anything waits on them
+            // (one exposed L2 latency per round instead of one per word)
+            uint64_t a[16], r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                a[i] = __ldg(acc + base + lane + 32u * i);
+                r[i] = result[base + lane + 32u * i];
+            }
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 8; ++c)
                 st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
             __syncwarp();
-            const uint32_t base = (rw - lane) * 16;   // first word of the warp's 32 rows
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const uint32_t w = lane + 32u * i;
                 const uint32_t row = w >> 4, ch = (w >> 1) & 7u;
                 const uint64_t x = slice[row * 16 + ((ch ^ (row & 7u)) << 1) + (w & 1u)];
-                result[base + w] = finish(acc[base + w], x, result[base + w]);
+                result[base + w] = finish(a[i], x, r[i]);
             }
         } else {
             const uint32_t off = rw * 16;
