@@ -161,7 +161,8 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "ks_mac_items")) {
-        if (value != 1 && value != 4 && value != 8) return fail(HEXL_B200_EINVAL, "ks_mac_items must be 1, 4 or 8");
+        if (value != 1 && value != 2 && value != 4 && value != 8)
+            return fail(HEXL_B200_EINVAL, "ks_mac_items must be 1, 2, 4 or 8");
         hb::g_ks_mac_items = (int)value;
         return 0;
     }

@@ -23,7 +23,7 @@
 
 namespace hb {
 
-int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys (slower: latency bound)
+int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys, 2 = 128-bit accumulators (both slower: latency bound)
 
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
     return r < D ? r * (D - 1) + (j < r ? j : j - 1) : D * (D - 1) + j;
@@ -180,6 +180,97 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
     }
 }
 
+// Wide-accumulator version (all moduli < 2^58, D <= 16): no per-term reduction at
+// all.  Every term is a plain 64x64 product of a reduced operand and a reduced
+// key, accumulated as three partial sums by weight (2^0 as 96 bits, 2^32 and
+// 2^64 as 64 bits -- operand and key high words are below 2^26, so 2*D cross
+// products of < 2^58 and D high products of < 2^52 cannot overflow), assembled
+// into 128 bits and reduced once with the 2-by-1 division of the dyadic kernel.
+// 16 multiplier cycles per term instead of the Shoup product's 28, and the keys
+// are read as plain words (8 bytes, not a {key, factor} pair).  MEASURED SLOWER
+// than k_ks_mac_fast<4> (58.5k vs 68.9k KeySwitch/s): 28 accumulator registers per
+// output leave 116 registers per thread and half the resident warps, and stage S3
+// is latency bound (51 % multiplier, 52 % HBM), not multiplier bound.  Kept as
+// option ks_mac_items=2.
+struct WideAcc {
+    uint64_t a0, a1, a2;
+    uint32_t c0;
+};
+HB_D void wide_mac(WideAcc& a, uint64_t x, uint64_t k) {
+    const uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), k0 = (uint32_t)k, k1 = (uint32_t)(k >> 32);
+    const uint64_t p00 = (uint64_t)x0 * k0;
+    a.a0 += p00;
+    a.c0 += (a.a0 < p00) ? 1u : 0u;
+    a.a1 += (uint64_t)x0 * k1;
+    a.a1 += (uint64_t)x1 * k0;
+    a.a2 += (uint64_t)x1 * k1;
+}
+HB_D uint64_t wide_reduce(const WideAcc& a, const Divisor& dv) {
+    const uint64_t lo = a.a0 + (a.a1 << 32);
+    const uint64_t hi = (uint64_t)a.c0 + (a.a1 >> 32) + a.a2 + ((lo < a.a0) ? 1 : 0);
+    // dv.s >= 6 here (q < 2^58); the sum is below D*q^2, so its shifted high word stays below d
+    const uint64_t u1 = (hi << dv.s) | (lo >> (64 - dv.s));
+    const uint64_t u0 = lo << dv.s;
+    return rem_2by1(u1, u0, dv.d, dv.v) >> dv.s;
+}
+HB_D void ld_keys2_plain(const uint64_t* p, uint64_t& a, uint64_t& b) {
+    // (the L2::evict_last policy of ld_keys2 exists for 256-bit loads only)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+}
+
+template <int kMacItems>
+__global__ void __launch_bounds__(256, 2)
+k_ks_mac_wide(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
+              uint64_t* __restrict__ ACC, uint32_t items) {
+    const uint32_t N = 1u << ks.logn;
+    const uint32_t l = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const uint32_t r = blockIdx.y, b0 = blockIdx.z * kMacItems;
+    const uint32_t idx = (r == ks.D) ? ks.K - 1 : r;
+    const Divisor dv = ks.divs[idx];
+    WideAcc acc[kMacItems][2][2];   // [item][component][coefficient]
+#pragma unroll
+    for (int it = 0; it < kMacItems; ++it)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) acc[it][c][e] = WideAcc{0, 0, 0, 0};
+    for (uint32_t j = 0; j < ks.D; ++j) {
+        // ks.keys holds the keys reduced mod q_i (k_ks_prepare_keys rewrites the device copy)
+        uint64_t u[2], w[2];
+        ld_keys2_plain(ks.keys + (((size_t)j * 2 + 0) * ks.K + idx) * N + l, u[0], u[1]);
+        ld_keys2_plain(ks.keys + (((size_t)j * 2 + 1) * ks.K + idx) * N + l, w[0], w[1]);
+#pragma unroll
+        for (int it = 0; it < kMacItems; ++it) {
+            const uint32_t b = b0 + it;
+            if (b < items) {
+                uint64_t x[2];
+                if (j == r) {   // the digit's own modulus: caller data, reduce defensively
+                    ld2(t_target + ((size_t)b * ks.D + j) * N + l, x[0], x[1]);
+                    x[0] = mod64(x[0], dv);
+                    x[1] = mod64(x[1], dv);
+                } else {
+                    ld2(V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N + l, x[0], x[1]);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    wide_mac(acc[it][0][e], x[e], u[e]);
+                    wide_mac(acc[it][1][e], x[e], w[e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < kMacItems; ++it) {
+        const uint32_t b = b0 + it;
+        if (b < items) {
+            st2(ACC + (((size_t)b * 2 + 0) * ks.R + r) * N + l, wide_reduce(acc[it][0][0], dv),
+                wide_reduce(acc[it][0][1], dv));
+            st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, wide_reduce(acc[it][1][0], dv),
+                wide_reduce(acc[it][1][1], dv));
+        }
+    }
+}
+
 // Register-resident-key version: a thread owns ONE coefficient of one output
 // modulus, keeps its 2*D {key, Shoup factor} pairs in registers and walks over
 // a slice of the items, so the key set crosses L2 once per slice instead of
@@ -231,6 +322,7 @@ __global__ void k_ks_prepare_keys(KsDev ks, TwPair* __restrict__ out) {
         t.w = k;
         t.wp = (uint64_t)((((unsigned __int128)k) << 64) / q);
         out[e] = t;
+        const_cast<uint64_t*>(ks.keys)[e] = k;   // the plan's own device copy: keep it reduced (k_ks_mac_wide)
     }
 }
 
@@ -399,6 +491,9 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         const uint32_t per = (uint32_t)((items + slices - 1) / slices);
         dim3 gk(C::N / 256, ks.R, (unsigned)((items + per - 1) / per));
         k_ks_mac_regkeys<8><<<gk, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items, per);
+    } else if (ks.fast_ok && ks.keys_sh && g_ks_mac_items == 2 && ks.D <= 16) {
+        dim3 gw(C::N / 512, ks.R, (unsigned)((items + 1) / 2));
+        k_ks_mac_wide<2><<<gw, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
     } else if (ks.fast_ok && ks.keys_sh) {
         if (g_ks_mac_items == 8) {
             dim3 gf(C::N / 512, ks.R, (unsigned)((items + 7) / 8));

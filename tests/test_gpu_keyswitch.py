@@ -111,3 +111,22 @@ def test_full_size_property(hb):
     plan.keyswitch(res, tt, batch)
     exp = gpu(p.expected())
     assert torch.equal(res, exp.expand(batch, -1))
+
+
+@pytest.mark.parametrize("mac_items", [1, 2, 8])
+@pytest.mark.parametrize("n,D,K,batch,bits", [(16384, 7, 8, 3, 51), (4096, 3, 4, 5, 45), (16384, 2, 8, 2, 57)])
+def test_mac_variants_agree_with_oracle(hb, n, D, K, batch, bits, mac_items):
+    """Stage S3 has several kernels (option ks_mac_items: 4 = Shoup products, four items per key
+    load (default); 2 = 128-bit accumulators, one reduction per output; 8; 1 = register-resident
+    keys): all must give the oracle's words, odd batch sizes included."""
+    p = KsProblem(n, D, K, batch, bits)
+    hb.set_option("ks_mac_items", mac_items)
+    try:
+        plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+        res = gpu(p.result)
+        plan.keyswitch(res, gpu(p.t_target), batch)
+        got = res.cpu().numpy().view(np.uint64)
+        plan.close()
+    finally:
+        hb.set_option("ks_mac_items", 4)
+    assert np.array_equal(got, p.expected())

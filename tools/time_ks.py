@@ -10,7 +10,7 @@ p = KsProblem(n, D, K, 1, 51)
 plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
 res = gpu(p.result).repeat(B, 1).contiguous(); tt = gpu(p.t_target).repeat(B, 1).contiguous()
 exp = gpu(p.expected())
-for mi in (1, 4):
+for mi in (4, 2, 8):
     for ws in (1024, 4096):
         hb.set_option("ks_mac_items", mi); hb.set_option("ks_workspace_mb", ws)
         r2 = gpu(p.result).repeat(B, 1).contiguous()
