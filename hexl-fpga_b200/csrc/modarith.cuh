@@ -110,6 +110,10 @@ struct FastMod {
     uint32_t shift2; // max(bitlen(q) - 21, 0): (v >> shift2) < 2^31 for v < 1024q
     uint32_t kb2;    // 52, or bitlen(q)+31 for tiny q
     uint32_t pad2;
+    // Always 0.  Added as a third operand to two-operand 64-bit sums in the butterflies: ptxas
+    // turns the high half of a plain a + b into IMAD.X (a*1 + b + carry) on the FMA-heavy pipe,
+    // which is the pipe the transform is bound by; a three-operand sum stays an IADD3.X on the ALU.
+    uint64_t zero64;
 };
 
 HB_HD FastMod make_fastmod(uint64_t q) {
@@ -129,6 +133,7 @@ HB_HD FastMod make_fastmod(uint64_t q) {
     unsigned __int128 k2 = (((unsigned __int128)1) << (m.shift2 + m.kb2)) / q;
     m.kmul2 = k2 > 0xffffffffu ? 0xffffffffu : (uint32_t)k2;
     m.pad2 = 0;
+    m.zero64 = 0;
     return m;
 }
 
@@ -185,7 +190,7 @@ HB_HD uint64_t csub(uint64_t x, uint64_t m) {
 HB_HD void fwd_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wp, const FastMod& m) {
     const uint64_t T = mul_shoup_approx(Y, w, wp, m.nq);
     const uint64_t x = X;
-    X = x + T;
+    X = x + T + m.zero64;
     Y = x + m.q4 - T;
 }
 
@@ -201,7 +206,7 @@ HB_HD uint64_t reduce_small_multiple(uint64_t v, const FastMod& m) {
 
 // inverse, values in [0,4q):  X' = (X+Y) csub 4q,  Y' = T''(X + 4q - Y)
 HB_HD void inv_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wp, const FastMod& m) {
-    const uint64_t tx = X + Y;
+    const uint64_t tx = X + Y + m.zero64;
     const uint64_t ty = X + m.q4 - Y;
     X = csub(tx, m.q4);
     Y = mul_shoup_approx(ty, w, wp, m.nq);
