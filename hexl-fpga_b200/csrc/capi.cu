@@ -156,6 +156,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         g_small_path = (int)value;
         return 0;
     }
+    if (!strcmp(name, "small_tma_store")) {
+        hb::g_small_tma_store = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "inv_lazy")) {
         g_inv_lazy = value ? 1 : 0;
         return 0;

@@ -174,6 +174,14 @@ HB_D void tma_store_rows(const CUtensorMap* map, const void* smem_src, uint32_t 
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// 3-D variant for the small-modulus forward epilogue: the map views the output as
+// [row of 32 words][half j][16 words]; one box = half j of 32 consecutive rows
+HB_D void tma_store_rows3(const CUtensorMap* map, const void* smem_src, uint32_t half, uint32_t row) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map),
+                 "r"(smem_u32(smem_src)), "r"(0), "r"(half), "r"(row)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // all earlier bulk stores of this thread have finished READING shared memory
 HB_D void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -543,9 +551,32 @@ HB_D void store_rows32_coalesced(uint32_t* S, uint64_t* dst, uint32_t row, const
     }
 }
 
+// Asynchronous version: the rows are widened to uint64 into the warp's 4 KiB slice
+// of the dead working buffer (128-byte tensor rows, TMA swizzle) and handed to the
+// TMA store engine, 16 words of 32 rows per box, so the 128 KiB of results drain
+// in the background instead of as one burst of register stores that every warp
+// waits on.  `row` = first of the warp's 32 consecutive rows in the store map.
+template <class C32>
+HB_D void store_rows32_tma(uint64_t* slice, const CUtensorMap* smap32, uint32_t row, const uint32_t* v) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        if (lane == 0) tma_store_wait_read();     // the previous box of this slice has left
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), (uint64_t)v[j * 16 + 2 * c],
+                (uint64_t)v[j * 16 + 2 * c + 1]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_rows3(smap32, slice, (uint32_t)j, row);
+    }
+}
+
 // forward, small modulus: base -> dst (bit-reversed order, [0,q)); false = deferred
 template <class C64, class C32, int MODE>
-HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf) {
+HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf,
+                            const CUtensorMap* smap32, uint32_t item) {
     using P0 = FwdPass<C32, 0>;
     const uint32_t tid = threadIdx.x;
     uint32_t* S = reinterpret_cast<uint32_t*>(base + SmallPlan<C32>::S_WORD);
@@ -566,9 +597,18 @@ HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     tail_load<C32>(tid, S, v, XfSame32());
     __syncthreads();                          // S may be overwritten by the next polynomial's first pass
     fwd_tail_compute<C32>(tid, v, t.ftw32, a);
+    if (smap32) {
+        uint64_t* slice = base + SmallPlan<C32>::S_WORD + (tid >> 5) * 512;
 #pragma unroll
-    for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
-        store_rows32_coalesced<C32>(S, dst, tid + ri * C32::NT, v + ri * C32::ROW);
+        for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
+            store_rows32_tma<C32>(slice, smap32, item * (C32::N / C32::ROW) + (tid & ~31u) + ri * C32::NT,
+                                  v + ri * C32::ROW);
+        if ((tid & 31u) == 0) tma_store_wait_read();
+    } else {
+#pragma unroll
+        for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
+            store_rows32_coalesced<C32>(S, dst, tid + ri * C32::NT, v + ri * C32::ROW);
+    }
     // the next transform's first pass writes S: all staged rows must have been read back
     __syncthreads();
     return true;
@@ -621,7 +661,7 @@ HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
 // persistent skeleton of the small-modulus kernels (plain in-place batches)
 template <class C64, class C32, bool FWD, int MODE>
 HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const ModTab& t, uint32_t n_items,
-                               uint32_t* list) {
+                               uint32_t* list, const CUtensorMap* smap32) {
     uint64_t* base = smem_poly<C64>();
     uint64_t* bar = base + SmallPlan<C32>::BAR_WORD;
     const uint32_t tid = threadIdx.x;
@@ -645,7 +685,7 @@ HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const Mo
         parity ^= 1;
         uint64_t* dst = data + (size_t)item * C64::N;
         bool done;
-        if constexpr (FWD) done = ntt_fwd_small_cta<C64, C32, MODE>(base, t, dst, pf);
+        if constexpr (FWD) done = ntt_fwd_small_cta<C64, C32, MODE>(base, t, dst, pf, smap32, item);
         else done = ntt_inv_small_cta<C64, C32, MODE>(base, t, dst, pf);
         if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
         // the next transform's first pass writes S: everyone must have left this one

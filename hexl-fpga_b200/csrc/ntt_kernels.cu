@@ -8,6 +8,8 @@
 
 namespace hb {
 
+int g_small_tma_store = 0;   // small-modulus forward epilogue through TMA stores (option "small_tma_store"): measured 5% slower than the coalesced register stores (slice reuse waits on the store engine), off by default
+
 // ---- plain batched transform, in place ------------------------------------
 template <class C>
 struct JobPlain {
@@ -55,10 +57,14 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv_mul(const __grid
 }
 
 // small-modulus kernels (q < 2^30): uint32 arithmetic, see ntt_block.cuh
+// smap32: 3-D store map of the forward epilogue (use_tma_store = 0: plain coalesced stores)
 template <class C64, class C32, bool FWD, int MODE>
-__global__ void __launch_bounds__(C32::NT, 1) k_ntt_small(const __grid_constant__ CUtensorMap tmap, uint64_t* data,
-                                                         const ModTab tab, uint32_t n_items, uint32_t* list) {
-    ntt_persistent_small<C64, C32, FWD, MODE>(&tmap, data, tab, n_items, list);
+__global__ void __launch_bounds__(C32::NT, 1) k_ntt_small(const __grid_constant__ CUtensorMap tmap,
+                                                         const __grid_constant__ CUtensorMap smap32, uint64_t* data,
+                                                         const ModTab tab, uint32_t n_items, uint32_t* list,
+                                                         int use_tma_store) {
+    ntt_persistent_small<C64, C32, FWD, MODE>(&tmap, data, tab, n_items, list,
+                                              (FWD && use_tma_store) ? &smap32 : nullptr);
 }
 
 // second generation: no landing buffer, two CTAs per SM (ntt_block.cuh)
@@ -125,6 +131,23 @@ static EncodeTiledFn encode_fn() {
             fn = reinterpret_cast<EncodeTiledFn>(p);
     });
     return fn;
+}
+
+// store map of the small-modulus forward epilogue: [polys * N/32 rows][2 halves][16 words],
+// box = 16 words x 1 half x 32 rows (4 KiB, 128-byte swizzle)
+static cudaError_t make_rows32_store_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    const uint64_t rows = polys * ((1ull << logn) / 32);
+    if (rows == 0 || rows >> 32) return cudaErrorInvalidValue;
+    const cuuint64_t gdim[3] = {16, 2, rows};
+    const cuuint64_t gstride[2] = {128, 256};
+    const cuuint32_t box[3] = {16, 1, 32};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 cudaError_t make_poly_tmap(CUtensorMap* out, const void* base, uint64_t polys, uint32_t logn, uint32_t box_rows) {
@@ -230,18 +253,21 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
                 return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
             }
             const size_t smem = SmallPlan<C32>::BYTES;
+            CUtensorMap smap32;
+            const int tma_store = FWD && g_small_tma_store;
+            if ((e = make_rows32_store_tmap(&smap32, data, batch, C::LOGN)) != cudaSuccess) return e;
             if (trust) {
                 auto kern = k_ntt_small<C, C32, FWD, kFastTrust>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
                 kern<<<persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st>>>(
-                    tmap, data, tab, (uint32_t)batch, list);
+                    tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
                 *launches += 1;
                 return cudaGetLastError();
             }
             auto kern = k_ntt_small<C, C32, FWD, kFastVote>;
             if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
             kern<<<persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st>>>(
-                tmap, data, tab, (uint32_t)batch, list);
+                tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
             if ((e = cudaGetLastError())) return e;
             *launches += 2;
             return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);

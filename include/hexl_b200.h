@@ -131,6 +131,7 @@ int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, ui
  *                      bit 1: skip the input-range vote (caller guarantees the contract)
  *   "small_path"       q < 2^30 kernels: 0 off, 1 uint32 kernels behind a TMA landing
  *                      buffer (default), 2 uint32 kernels with direct loads, two CTAs / SM
+ *   "small_tma_store"  1: small-modulus forward results leave through TMA stores (default 0)
  *   "inv_lazy"         1: correction-free inverse butterflies for q < 2^52 (default 0)
  *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16)
  *   "ks_mac_items"     items sharing one key load in the keyswitch MAC (1, 4, 8) */

@@ -222,13 +222,17 @@ def test_small_modulus_32bit_path(hb, q):
     polys.append(np.where(np.arange(N) % 2 == 0, 4 * q - 1, q - 1).astype(np.uint64))     # fwd contract edge
     polys.append(np.where(np.arange(N) % 2 == 0, 2 * q - 1, 0).astype(np.uint64))         # inv contract edge
     polys.append(np.full(N, 2**32 + 5, dtype=np.uint64))                                  # high word set
-    for small in (2, 1, 0):               # 1: TMA landing buffer (default); 2: direct loads, two CTAs per SM
-        hb.set_option("small_path", small)
+    # small_path 1: TMA landing buffer (default); 2: direct loads, two CTAs per SM; "1t": path 1 with the
+    # forward epilogue through TMA stores (option small_tma_store)
+    for small in (2, 1, "1t", 0):
+        hb.set_option("small_path", 1 if small == "1t" else small)
+        hb.set_option("small_tma_store", 1 if small == "1t" else 0)
         try:
             got = run_fwd(hb, polys, t)
             goti = run_inv(hb, polys, t)
         finally:
             hb.set_option("small_path", 1)
+            hb.set_option("small_tma_store", 0)
         for i in range(len(polys)):
             assert np.array_equal(got[i], ob.fwd_ntt(polys[i], t)), (small, i)
             assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t)), (small, i)
