@@ -343,9 +343,8 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     tail_load<C>(tid, W, v, XfIdent());
     __syncthreads();        // every word of W is in registers now
     pf.template issue<C>(); // ... so the buffer can take the next polynomial
-    fwd_tail_compute<C>(tid, v, t.ftw, a);
-#pragma unroll
-    for (int ri = 0; ri < C::E / 16; ++ri) of.template store<C>(tid + ri * C::NT, v + ri * 16);
+    // each row leaves as soon as it is final: its staged TMA store drains while the next row is computed
+    fwd_tail_compute<C>(tid, v, t.ftw, a, [&](int ri) { of.template store<C>(tid + ri * C::NT, v + ri * 16); });
     return true;
 }
 
@@ -596,18 +595,18 @@ HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     fwd_mid_passes32<C32, 1>(tid, S, t.ftw32, a);
     tail_load<C32>(tid, S, v, XfSame32());
     __syncthreads();                          // S may be overwritten by the next polynomial's first pass
-    fwd_tail_compute<C32>(tid, v, t.ftw32, a);
+    // each row leaves as soon as it is final, so its stores drain while the next row is computed
     if (smap32) {
         uint64_t* slice = base + SmallPlan<C32>::S_WORD + (tid >> 5) * 512;
-#pragma unroll
-        for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
+        fwd_tail_compute<C32>(tid, v, t.ftw32, a, [&](int ri) {
             store_rows32_tma<C32>(slice, smap32, item * (C32::N / C32::ROW) + (tid & ~31u) + ri * C32::NT,
                                   v + ri * C32::ROW);
+        });
         if ((tid & 31u) == 0) tma_store_wait_read();
     } else {
-#pragma unroll
-        for (int ri = 0; ri < C32::E / C32::ROW; ++ri)
+        fwd_tail_compute<C32>(tid, v, t.ftw32, a, [&](int ri) {
             store_rows32_coalesced<C32>(S, dst, tid + ri * C32::NT, v + ri * C32::ROW);
+        });
     }
     // the next transform's first pass writes S: all staged rows must have been read back
     __syncthreads();

@@ -565,8 +565,11 @@ HB_HD void fwd_head_pass(uint32_t tid, typename A::elem* sm, const typename A::T
 }
 
 // tail: last LOGROW stages + final reduction on registers v[E] (from tail_load)
-template <class C, class A>
-HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
+// after_row(ri) runs as soon as row ri is final: the kernels start that row's
+// (asynchronous) stores there, so they drain while the next row is computed
+template <class C, class A, class F>
+HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a,
+                            const F& after_row) {
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tid + ri * C::NT;
@@ -575,7 +578,12 @@ HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A:
             constexpr int k = decltype(kc)::value;
             v[ri * C::ROW + k] = a.fwd_final(v[ri * C::ROW + k]);
         });
+        after_row(ri);
     });
+}
+template <class C, class A>
+HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
+    fwd_tail_compute<C>(tid, v, tw, a, [](int) {});
 }
 
 // ---------------------------------------------------------------------------
