@@ -102,14 +102,14 @@ struct FastMod {
     uint32_t kmul;   // floor(2^(shift+kb) / q), in (2^31, 2^32)
     uint32_t shift;  // max(bitlen(q) - 25, 0): (v >> shift) < 2^31 for v < 64q
     uint32_t kb;     // 56, or bitlen(q)+31 for tiny q
-    uint32_t pad;
+    uint32_t kmul3;  // table reduction (reduce_by_table): floor(2^(shift3+16) / q), at most 2^16
     // lazy inverse transform (q < 2^52): offsets 2^e * q and the constants of the
     // mid-transform reduction of values < 1024q
     uint64_t qsh[12];
     uint32_t kmul2;  // floor(2^(shift2+kb2) / q)
     uint32_t shift2; // max(bitlen(q) - 21, 0): (v >> shift2) < 2^31 for v < 1024q
     uint32_t kb2;    // 52, or bitlen(q)+31 for tiny q
-    uint32_t pad2;
+    uint32_t shift3; // max(bitlen(q) - 6, 0): (v >> shift3) < 2^12 for v < 64q
     // Always 0.  Added as a third operand to two-operand 64-bit sums in the butterflies: ptxas
     // turns the high half of a plain a + b into IMAD.X (a*1 + b + carry) on the FMA-heavy pipe,
     // which is the pipe the transform is bound by; a three-operand sum stays an IADD3.X on the ALU.
@@ -126,13 +126,13 @@ HB_HD FastMod make_fastmod(uint64_t q) {
     m.kb = bl >= 25 ? 56u : (uint32_t)(bl + 31);
     unsigned __int128 k = (((unsigned __int128)1) << (m.shift + m.kb)) / q;
     m.kmul = k > 0xffffffffu ? 0xffffffffu : (uint32_t)k;
-    m.pad = 0;
+    m.shift3 = bl > 6 ? (uint32_t)(bl - 6) : 0u;
+    m.kmul3 = (uint32_t)((((unsigned __int128)1) << (m.shift3 + 16)) / q);
     for (int e = 0; e < 12; ++e) m.qsh[e] = q << e;   // meaningful when q < 2^52 (lazy inverse only)
     m.shift2 = bl > 21 ? (uint32_t)(bl - 21) : 0u;
     m.kb2 = bl >= 21 ? 52u : (uint32_t)(bl + 31);
     unsigned __int128 k2 = (((unsigned __int128)1) << (m.shift2 + m.kb2)) / q;
     m.kmul2 = k2 > 0xffffffffu ? 0xffffffffu : (uint32_t)k2;
-    m.pad2 = 0;
     m.zero64 = 0;
     return m;
 }
@@ -202,6 +202,18 @@ HB_HD uint64_t reduce_small_multiple(uint64_t v, const FastMod& m) {
     const uint32_t k = (uint32_t)(((uint64_t)vh * m.kmul) >> m.kb);
     const uint64_t r = v - (uint64_t)k * m.q;
     return csub(r, m.q);
+}
+
+// Same reduction with the multiple of q looked up instead of multiplied: kq[k] = k*q
+// for k < 64 (a 512-byte table in shared memory).  The estimate needs one 32-bit
+// IMAD (12-bit by 17-bit product) instead of two IMAD.WIDE and an IMAD, i.e. 2
+// instead of 10 cycles of the multiplier pipe the forward transform is bound by:
+// k = floor((v >> shift3) * kmul3 / 2^16) is floor(v/q) or one less (the two
+// truncations cost less than 0.1 of a unit), so r = v - kq[k] lies in [0, 2q).
+HB_HD uint64_t reduce_by_table(uint64_t v, const FastMod& m, const uint64_t* kq) {
+    const uint32_t vh = (uint32_t)(v >> m.shift3);
+    const uint32_t k = (vh * m.kmul3) >> 16;
+    return csub(v - kq[k], m.q);
 }
 
 // inverse, values in [0,4q):  X' = (X+Y) csub 4q,  Y' = T''(X + 4q - Y)

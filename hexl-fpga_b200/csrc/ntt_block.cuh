@@ -102,7 +102,8 @@ struct SmemPlan {
     static constexpr uint32_t STAGE_WORDS = kStagedStore ? (C::NT / 32) * 512 : 0;
     static constexpr uint32_t BAR_WORD = C::N + STAGE_WORDS;
     static constexpr uint32_t FLAG_WORD = BAR_WORD + 1;   // range-vote flag (fast-vote kernels)
-    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2) * 8;
+    static constexpr uint32_t KQ_WORD = BAR_WORD + 2;     // two tables of k*q, k < 64 (iteration parity)
+    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2 + 128) * 8;
 };
 
 // forward output: the 16 contiguous words of one row per thread
@@ -440,9 +441,21 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
             const LazyInvArith a = {t.fm, t.sc};
             done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (MODE == kFastVote || MODE == kFastTrust) {
-            const FastArith a = {t.fm, t.sc};
-            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
-            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            if constexpr (FWD) {
+                // multiples of this item's modulus for the final reduction; the table of the
+                // previous item may still be read by slower warps, hence two of them.  Written
+                // before the first barrier of the transform, read after its last one.
+                uint64_t* kq = W + SmemPlan<C>::KQ_WORD + (parity ? 0 : 64);
+                if (tid < 64) kq[tid] = (uint64_t)tid * t.fm.q;
+                FastArithTab a;
+                a.m = t.fm;
+                a.sc = t.sc;
+                a.kq = kq;
+                done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            } else {
+                const FastArith a = {t.fm, t.sc};
+                done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            }
         } else {
             const ExactArith a = {t.q, t.twoq, t.sc};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);

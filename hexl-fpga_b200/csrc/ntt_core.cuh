@@ -231,6 +231,13 @@ struct FastArith {
     template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last(X, Y); }
 };
 
+// FastArith whose final forward reduction looks the multiple of q up in a 64-entry
+// shared-memory table (kernels only; the table is built per item by the CTA)
+struct FastArithTab : FastArith {
+    const uint64_t* kq;
+    HB_HD uint64_t fwd_final(uint64_t x) const { return reduce_by_table(x, m, kq); }
+};
+
 // inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
 // E = log2 of the bound (in units of q) of the words entering the stage
 struct LazyInvArith {

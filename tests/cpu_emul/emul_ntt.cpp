@@ -266,6 +266,12 @@ int main() {
                 if (t >= 4 * q || t % q != ho_mul_mod(w, y % q, q)) ++fbad;
                 uint64_t v = (q < (1ULL << 58)) ? r[2] % (60 * q) : r[2] % q;
                 if (reduce_small_multiple(v, m) != v % q) ++fbad;
+                if (q < (1ULL << 58)) {          // table form used by the forward kernels
+                    uint64_t kq[64];
+                    for (uint64_t k = 0; k < 64; ++k) kq[k] = k * q;
+                    const uint64_t v3 = (it % 5 == 0) ? 64 * q - 1 - (r[2] % 64) : v;
+                    if (reduce_by_table(v3, m, kq) != v3 % q) ++fbad;
+                }
                 if (inv_lazy_modulus_ok(q)) {
                     const uint64_t v2 = (it % 3 == 0) ? 1024 * q - 1 - (r[2] % 1000) : r[2] % (1024 * q);
                     if (reduce_mid(v2, m) != v2 % q) ++fbad;
