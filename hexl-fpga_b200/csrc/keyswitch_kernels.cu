@@ -136,7 +136,7 @@ HB_D void ld_keys2(const TwPair* p, TwPair& a, TwPair& b) {
 }
 
 template <int kMacItems>
-__global__ void __launch_bounds__(256, kMacItems > 4 ? 2 : 4)
+__global__ void __launch_bounds__(256, kMacItems > 4 ? 2 : 3)
 k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
               uint64_t* __restrict__ ACC, uint32_t items) {
     const uint32_t N = 1u << ks.logn;
@@ -150,22 +150,26 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
     for (uint32_t j = 0; j < ks.D; ++j) {
         const TwPair* k0 = ks.keys_sh + (((size_t)j * 2 + 0) * ks.K + idx) * N + l;
         const TwPair* k1 = ks.keys_sh + (((size_t)j * 2 + 1) * ks.K + idx) * N + l;
+        // every load of the digit is issued before the first product waits on one: the items past
+        // the end of the batch re-read the last item (their sums are never stored), which keeps the
+        // loads unconditional so that they can all be in flight together
+        uint64_t x0[kMacItems], x1[kMacItems];
+#pragma unroll
+        for (int it = 0; it < kMacItems; ++it) {
+            const uint32_t b = min(b0 + it, items - 1);
+            const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
+                                          : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
+            ld2(op + l, x0[it], x1[it]);
+        }
         TwPair u0, u1, w0, w1;
         ld_keys2(k0, u0, u1);
         ld_keys2(k1, w0, w1);
 #pragma unroll
         for (int it = 0; it < kMacItems; ++it) {
-            const uint32_t b = b0 + it;
-            if (b < items) {
-                const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
-                                              : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
-                uint64_t x0, x1;
-                ld2(op + l, x0, x1);
-                a0[it][0] += mul_shoup_approx(x0, u0.w, u0.wp, fm.nq);
-                a0[it][1] += mul_shoup_approx(x1, u1.w, u1.wp, fm.nq);
-                a1[it][0] += mul_shoup_approx(x0, w0.w, w0.wp, fm.nq);
-                a1[it][1] += mul_shoup_approx(x1, w1.w, w1.wp, fm.nq);
-            }
+            a0[it][0] += mul_shoup_approx(x0[it], u0.w, u0.wp, fm.nq);
+            a0[it][1] += mul_shoup_approx(x1[it], u1.w, u1.wp, fm.nq);
+            a1[it][0] += mul_shoup_approx(x0[it], w0.w, w0.wp, fm.nq);
+            a1[it][1] += mul_shoup_approx(x1[it], w1.w, w1.wp, fm.nq);
         }
     }
 #pragma unroll
