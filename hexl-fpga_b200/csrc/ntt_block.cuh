@@ -373,9 +373,9 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         // inverse contract: every word < 2q (ntt.cpp:600-606)
         bad = out_of_range<C::E>(v, t.twoq);
     }
-    if constexpr (MODE == kFastVote) vote_raise<C>(bad);
     inv_tail_compute<C>(tid, v, t.itw, a);
     tail_store<C>(tid, W, v);
+    if constexpr (MODE == kFastVote) vote_raise<C>(bad);   // right before the barrier it rides on
     __syncthreads();
     if constexpr (MODE == kFastVote) {
         if (vote_read<C>()) {
