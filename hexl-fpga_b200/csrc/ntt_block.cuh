@@ -387,11 +387,12 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
     __syncthreads();
     pf.template issue<C>();
-    inv_head_compute<C, C::NP - 1>(tid, v, t.itw, a);
-#pragma unroll
-    for (int gi = 0; gi < (C::E >> PL::R); ++gi)
-#pragma unroll
-        for (int k = 0; k < (1 << PL::R); ++k) of.word(inv_last_index<C>(tid, gi, k), v[gi * (1 << PL::R) + k]);
+    // every pair is stored as soon as its last butterfly has made it final: the stores (32 B/clk
+    // per SM at most) drain under the remaining butterflies instead of as one burst at the end
+    inv_head_compute<C, C::NP - 1>(tid, v, t.itw, a, [&](int gi, int k0, int k1) {
+        of.word(inv_last_index<C>(tid, gi, k0), v[gi * (1 << PL::R) + k0]);
+        of.word(inv_last_index<C>(tid, gi, k1), v[gi * (1 << PL::R) + k1]);
+    });
     return true;
 }
 
@@ -662,11 +663,10 @@ HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     inv_mid_passes32<C32, 0>(tid, S, t.itw32, a);
     head_load<C32, PL::R, PL::LS>(tid, S, v, XfSame32());
     __syncthreads();
-    inv_head_compute<C32, C32::NP - 1>(tid, v, t.itw32, a);
-#pragma unroll
-    for (int gi = 0; gi < (C32::E >> PL::R); ++gi)
-#pragma unroll
-        for (int k = 0; k < (1 << PL::R); ++k) dst[inv_last_index<C32>(tid, gi, k)] = v[gi * (1 << PL::R) + k];
+    inv_head_compute<C32, C32::NP - 1>(tid, v, t.itw32, a, [&](int gi, int k0, int k1) {
+        dst[inv_last_index<C32>(tid, gi, k0)] = v[gi * (1 << PL::R) + k0];
+        dst[inv_last_index<C32>(tid, gi, k1)] = v[gi * (1 << PL::R) + k1];
+    });
     return true;
 }
 

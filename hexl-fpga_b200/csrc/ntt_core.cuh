@@ -402,8 +402,14 @@ HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
 // pairs k with k + 2^d inside blocks of 2^(d+1); its twiddle
 // inv_roots[1 + N - (N >> u) + (idx >> (u+1))] (ntt.cpp:600-636) is packed at
 // slot 2^(R-1-d) + blk.  When LAST, the final stage is the inv_n-fused one.
-template <int R, bool LAST, int TS, int E0, class A>
-HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
+// fin(k0, k1): called right after the LAST stage's butterfly on registers k0, k1 has made
+// them final, so that the kernels can store the pair while the next pairs are computed
+struct NoFin {
+    HB_HD void operator()(int, int) const {}
+    HB_HD void operator()(int, int, int) const {}
+};
+template <int R, bool LAST, int TS, int E0, class A, class Fin = NoFin>
+HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a, const Fin& fin = Fin()) {
     static_for<0, R>([&](auto dc) {
         constexpr int d = decltype(dc)::value;
         constexpr int half = 1 << d;
@@ -413,6 +419,7 @@ HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     a.template inv_last_at<E0 + d>(v[blk * 2 * half + j], v[blk * 2 * half + j + half]);
+                    fin(blk * 2 * half + j, blk * 2 * half + j + half);
                 });
             } else {
                 const typename A::Tw t = a.ld(g + ((1 << (R - 1 - d)) + blk) * TS);
@@ -618,15 +625,17 @@ HB_HD void inv_tail_compute(uint32_t tid, typename A::elem* v, const typename A:
     }
 }
 
-template <class C, int P, class A>
-HB_HD void inv_head_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
+template <class C, int P, class A, class Fin = NoFin>
+HB_HD void inv_head_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a,
+                            const Fin& fin = Fin()) {
     using Ps = InvPass<C, P>;
     using Gm = HeadGeom<C, Ps::R, Ps::LS>;
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t hi = Gm::hi(tid + gi * C::NT);
         inv_group<Ps::R, Ps::LAST, 1, (A::kLazyInv ? InvLazy<C>::e_in(P) : 1)>(
-            v + gi * (1 << Ps::R), tw + C::inv_off(P) + (hi << Ps::R), a);
+            v + gi * (1 << Ps::R), tw + C::inv_off(P) + (hi << Ps::R), a,
+            [&](int k0, int k1) { fin(gi, k0, k1); });
     });
     if constexpr (A::kLazyInv) {
         if constexpr (InvLazy<C>::reduce_after(P))
