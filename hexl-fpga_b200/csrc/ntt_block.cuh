@@ -331,8 +331,10 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         bad = out_of_range<C::E>(v, t.fm.q4);
     }
     if constexpr (MODE == kFastVote) vote_raise<C>(bad);
-    fwd_head_compute<C, 0>(tid, v, t.ftw, a);
-    head_store<C, P0::R, P0::LS>(tid, W, v);
+    fwd_head_compute<C, 0>(tid, v, t.ftw, a, [&](int gi, int k0, int k1) {
+        head_store_word<C, P0::R, P0::LS>(tid, W, gi, k0, v[gi * (1 << P0::R) + k0]);
+        head_store_word<C, P0::R, P0::LS>(tid, W, gi, k1, v[gi * (1 << P0::R) + k1]);
+    });
     __syncthreads();
     if constexpr (MODE == kFastVote) {
         if (vote_read<C>()) {          // global memory still holds the untouched input
@@ -599,8 +601,10 @@ HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     head_load<C32, P0::R, P0::LS>(tid, base, v, XfNarrowVote{&hi_or, &lo_max});
     if constexpr (MODE == kFastVote)   // forward contract: every word < 4q
         small_vote_raise<C32>((hi_or != 0) | (lo_max >= 2u * t.sm32.twoq), base);
-    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a);
-    head_store<C32, P0::R, P0::LS>(tid, S, v);
+    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a, [&](int gi, int k0, int k1) {
+        head_store_word<C32, P0::R, P0::LS>(tid, S, gi, k0, v[gi * (1 << P0::R) + k0]);
+        head_store_word<C32, P0::R, P0::LS>(tid, S, gi, k1, v[gi * (1 << P0::R) + k1]);
+    });
     __syncthreads();
     pf.template issue<C64, C32>(base);       // the landing buffer is free from here on
     if constexpr (MODE == kFastVote) {
@@ -777,8 +781,10 @@ HB_D bool ntt_fwd_small2_cta(uint32_t* S, const ModTab& t, uint64_t* poly, uint3
     uint32_t v[C32::E];
     uint32_t hi_or = 0, lo_max = 0;
     head_load_global_narrow<C32, P0::R, P0::LS>(tid, poly, v, hi_or, lo_max);
-    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a);
-    head_store<C32, P0::R, P0::LS>(tid, S, v);
+    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a, [&](int gi, int k0, int k1) {
+        head_store_word<C32, P0::R, P0::LS>(tid, S, gi, k0, v[gi * (1 << P0::R) + k0]);
+        head_store_word<C32, P0::R, P0::LS>(tid, S, gi, k1, v[gi * (1 << P0::R) + k1]);
+    });
     if constexpr (MODE == kFastVote) {
         // forward contract: every word < 4q; global memory still holds the untouched input
         if (small2_vote<C32>(S, (hi_or != 0) | (lo_max >= 2u * t.sm32.twoq), iter)) return false;

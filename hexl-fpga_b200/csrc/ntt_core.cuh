@@ -382,8 +382,15 @@ HB_HD uint32_t tail_tw_base(uint32_t row) {
 // R forward stages on 2^R registers.  Stage d (global stage s = S0+d) pairs
 // k with k + 2^(R-1-d) inside blocks of 2^(R-d); its twiddle
 // roots[2^s + (idx >> (LOGN-s))] (ntt.cpp:494-500) is packed at slot 2^d + blk.
-template <int R, int TS, class A>
-HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
+// fin(k0, k1): called right after the group's LAST stage has made registers k0, k1 final,
+// so that a pass can put the pair back (or send it out) while the next pairs are computed
+// instead of in one burst of stores at the end
+struct NoFin {
+    HB_HD void operator()(int, int) const {}
+    HB_HD void operator()(int, int, int) const {}
+};
+template <int R, int TS, class A, class Fin = NoFin>
+HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a, const Fin& fin = Fin()) {
     static_for<0, R>([&](auto dc) {
         constexpr int d = decltype(dc)::value;
         constexpr int half = 1 << (R - 1 - d);
@@ -393,6 +400,7 @@ HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
             static_for<0, half>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 a.fwd(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
+                if constexpr (d == R - 1) fin(blk * 2 * half + j, blk * 2 * half + j + half);
             });
         });
     });
@@ -402,12 +410,6 @@ HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a) {
 // pairs k with k + 2^d inside blocks of 2^(d+1); its twiddle
 // inv_roots[1 + N - (N >> u) + (idx >> (u+1))] (ntt.cpp:600-636) is packed at
 // slot 2^(R-1-d) + blk.  When LAST, the final stage is the inv_n-fused one.
-// fin(k0, k1): called right after the LAST stage's butterfly on registers k0, k1 has made
-// them final, so that the kernels can store the pair while the next pairs are computed
-struct NoFin {
-    HB_HD void operator()(int, int) const {}
-    HB_HD void operator()(int, int, int) const {}
-};
 template <int R, bool LAST, int TS, int E0, class A, class Fin = NoFin>
 HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a, const Fin& fin = Fin()) {
     static_for<0, R>([&](auto dc) {
@@ -426,6 +428,7 @@ HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a, c
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     a.template inv_at<E0 + d>(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
+                    if constexpr (d == R - 1) fin(blk * 2 * half + j, blk * 2 * half + j + half);
                 });
             }
         });
@@ -514,6 +517,13 @@ HB_HD void head_store(uint32_t tid, T* sm, const T* v) {
     });
 }
 
+// one word of a head pass back to its place (gi, k as in head_store)
+template <class C, int R, int LS, class T>
+HB_HD void head_store_word(uint32_t tid, T* sm, int gi, int k, T x) {
+    using Gm = HeadGeom<C, R, LS>;
+    sm[swz_t<T>(Gm::base(tid + (uint32_t)gi * C::NT) + ((uint32_t)k << LS))] = x;
+}
+
 // tail rows: thread tid owns rows tid + ri*NT of ROW contiguous words (128 bytes)
 template <class C, class Xf>
 HB_HD void tail_load(uint32_t tid, const typename C::elem* sm, typename C::elem* v, const Xf& xf) {
@@ -555,14 +565,16 @@ struct FwdPass {
 };
 
 // butterflies of head pass P on registers v[E] (loaded by head_load)
-template <class C, int P, class A>
-HB_HD void fwd_head_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
+template <class C, int P, class A, class Fin = NoFin>
+HB_HD void fwd_head_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a,
+                            const Fin& fin = Fin()) {
     using Ps = FwdPass<C, P>;
     using Gm = HeadGeom<C, Ps::R, Ps::LS>;
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t hi = Gm::hi(tid + gi * C::NT);
-        fwd_group<Ps::R, 1>(v + gi * (1 << Ps::R), tw + C::fwd_off(P) + (hi << Ps::R), a);
+        fwd_group<Ps::R, 1>(v + gi * (1 << Ps::R), tw + C::fwd_off(P) + (hi << Ps::R), a,
+                            [&](int k0, int k1) { fin(gi, k0, k1); });
     });
 }
 
@@ -574,8 +586,11 @@ HB_HD void fwd_head_pass(uint32_t tid, typename A::elem* sm, const typename A::T
     T v[C::E];
     auto ident = [](T x) { return x; };
     head_load<C, Ps::R, Ps::LS>(tid, sm, v, ident);
-    fwd_head_compute<C, P>(tid, v, tw, a);
-    head_store<C, Ps::R, Ps::LS>(tid, sm, v);
+    // in place within the group: each pair goes back as soon as its last butterfly is done
+    fwd_head_compute<C, P>(tid, v, tw, a, [&](int gi, int k0, int k1) {
+        head_store_word<C, Ps::R, Ps::LS>(tid, sm, gi, k0, v[gi * (1 << Ps::R) + k0]);
+        head_store_word<C, Ps::R, Ps::LS>(tid, sm, gi, k1, v[gi * (1 << Ps::R) + k1]);
+    });
 }
 
 // tail: last LOGROW stages + final reduction on registers v[E] (from tail_load)
@@ -652,8 +667,15 @@ HB_HD void inv_head_pass(uint32_t tid, typename A::elem* sm, const typename A::T
     T v[C::E];
     auto ident = [](T x) { return x; };
     head_load<C, Ps::R, Ps::LS>(tid, sm, v, ident);
-    inv_head_compute<C, P>(tid, v, tw, a);
-    head_store<C, Ps::R, Ps::LS>(tid, sm, v);
+    if constexpr (A::kLazyInv) {      // the words may still need the mid-transform reduction
+        inv_head_compute<C, P>(tid, v, tw, a);
+        head_store<C, Ps::R, Ps::LS>(tid, sm, v);
+    } else {
+        inv_head_compute<C, P>(tid, v, tw, a, [&](int gi, int k0, int k1) {
+            head_store_word<C, Ps::R, Ps::LS>(tid, sm, gi, k0, v[gi * (1 << Ps::R) + k0]);
+            head_store_word<C, Ps::R, Ps::LS>(tid, sm, gi, k1, v[gi * (1 << Ps::R) + k1]);
+        });
+    }
 }
 
 // natural-order global index of register slot (gi,k) in the last inverse pass
