@@ -50,6 +50,8 @@ static std::atomic<int> g_inv_lazy{0};     // correction-free inverse butterflie
 // 32-bit kernels for q < 2^30 (option "small_path"): 0 off, 1 TMA landing buffer
 // (one CTA per SM), 2 direct global loads (two CTAs per SM)
 static std::atomic<int> g_small_path{1};
+// butterflies on the FP64 pipe for 2^36 <= q <= 2^53/3 in the plain NTT entry points (option "fp64_path")
+static std::atomic<int> g_fp64_path{1};
 
 hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
                        const hb::TwPair* itw, int logn, const hb::Tw32* ftw32, const hb::Tw32* itw32) {
@@ -71,6 +73,10 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.itw32 = itw32;
     t.small_ok = (hb::small_modulus_ok(q) && (ftw32 || itw32)) ? (uint32_t)g_small_path.load() : 0u;
     t.inv_lazy_ok = (g_inv_lazy.load() && hb::inv_lazy_modulus_ok(q)) ? 1u : 0u;
+    t.fd = hb::make_fp64mod(q, inv_n < q ? inv_n : 0, inv_n_w < q ? inv_n_w : 0);
+    t.ftwd = nullptr;
+    t.itwd = nullptr;
+    t.fp64_ok = 0;          // set by the callers that build the FP64 tables
     return t;
 }
 
@@ -152,12 +158,16 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "small_path")) {
-        if (value < 0 || value > 2) return fail(HEXL_B200_EINVAL, "small_path must be 0, 1 or 2");
+        if (value < 0 || value > 3) return fail(HEXL_B200_EINVAL, "small_path must be 0, 1, 2 or 3");
         g_small_path = (int)value;
         return 0;
     }
     if (!strcmp(name, "small_tma_store")) {
         hb::g_small_tma_store = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "fp64_path")) {
+        g_fp64_path = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "inv_lazy")) {
@@ -217,13 +227,14 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
     if (batch == 0) return 0;
     const int variant = g_ntt_variant.load();
     // per-stream scratch: [0,512K) packed forward twiddles, [512K,1M) packed
-    // inverse twiddles, then two deferred lists of 1 + batch words
+    // inverse twiddles, [1M,1.5M) / [1.5M,2M) the same for the FP64 path, then
+    // two deferred lists of 1 + batch words
     uint8_t* scratch = nullptr;
     const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
-    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20) + 2 * list_bytes, (void**)&scratch);
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(2u << 20) + 2 * list_bytes, (void**)&scratch);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: scratch");
     hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch);
-    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (1u << 20));
+    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (2u << 20));
     e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr, list,
                                  (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack twiddles");
@@ -236,6 +247,15 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
         ++launches;
     }
     hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn, packed32, nullptr);
+    if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
+        hb::TwPair* packed_d = reinterpret_cast<hb::TwPair*>(scratch + (1u << 20));
+        e = hb::launch_pack_twiddles_fp64((uint32_t)logn, variant, d_roots, packed_d, nullptr, nullptr, q,
+                                          (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack FP64 twiddles");
+        ++launches;
+        t.ftwd = packed_d;
+        t.fp64_ok = 1;
+    }
     e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd launch");
     g_launches += launches;
@@ -259,11 +279,11 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
     const int variant = g_ntt_variant.load();
     uint8_t* scratch = nullptr;
     const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
-    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(1u << 20) + 2 * list_bytes, (void**)&scratch);
+    cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(2u << 20) + 2 * list_bytes, (void**)&scratch);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: scratch");
     // second halves, so a forward and an inverse call may be queued back to back
     hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch + (1u << 19));
-    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (1u << 20) + list_bytes);
+    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (2u << 20) + list_bytes);
     e = hb::launch_pack_twiddles((uint32_t)logn, variant, nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed,
                                  list, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack twiddles");
@@ -277,6 +297,15 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
         ++launches;
     }
     hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn, nullptr, packed32);
+    if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
+        hb::TwPair* packed_d = reinterpret_cast<hb::TwPair*>(scratch + (3u << 19));
+        e = hb::launch_pack_twiddles_fp64((uint32_t)logn, variant, nullptr, nullptr, d_inv_roots, packed_d, q,
+                                          (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack FP64 twiddles");
+        ++launches;
+        t.itwd = packed_d;
+        t.fp64_ok = 1;
+    }
     e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv launch");
     g_launches += launches;

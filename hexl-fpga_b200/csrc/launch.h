@@ -35,6 +35,10 @@ cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roo
                                  TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
                                  TwPair* inv_out, uint32_t* zero_count, cudaStream_t st);
 
+// FP64-pipe tables (modarith.cuh): same packed geometry, entries {centred root, root / q} as doubles
+cudaError_t launch_pack_twiddles_fp64(uint32_t logn, int variant, const uint64_t* roots, TwPair* fwd_out,
+                                      const uint64_t* inv_roots, TwPair* inv_out, uint64_t q, cudaStream_t st);
+
 // small-modulus (q < 2^30) 32-bit kernels: available for N = 16384 with the 32-word configuration
 bool small_path_available(uint32_t logn, int variant);
 size_t packed32_fwd_entries();

@@ -10,6 +10,8 @@
 // a product fallback: the product entry points in capi.cu only launch kernels).
 #pragma once
 #include <stdint.h>
+#include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define HB_HD __host__ __device__ __forceinline__
@@ -273,6 +275,169 @@ HB_HD void inv_last_bfly_fast(uint64_t& X, uint64_t& Y, uint64_t inv_n, uint64_t
     y = csub(y, m.q << 1);
     X = csub(x, m.q);
     Y = csub(y, m.q);
+}
+
+// ---------------------------------------------------------------------------
+// FP64-pipe arithmetic for 2^36 <= q <= 2^53 / 3  (the 50..52-bit primes of the
+// HE parameter sets), in-contract inputs only.
+//
+// The 64-bit integer butterfly is bound by the integer multiplier (28 FMA-heavy
+// pipe cycles per warp, modarith.cuh above); the B200's FP64 pipe issues a
+// DFMA/DADD/DMUL every ~2.1 cycles per warp and is otherwise idle.  Here the
+// words of a transform are integer-valued doubles in a centred, slightly
+// redundant range and a modular product is six FP64 instructions:
+//     c = rint(y * (w/q))        fma(y, wi, M) - M,  M = 1.5 * 2^52
+//     h + l = y * w  exactly     h = y*w,  l = fma(y, w, -h)
+//     r = (h - c*q) + l          fma(-c, q, h) is exact: an integer below 2^53
+// With |w| <= q/2 (centred twiddle), wi = fl(w/q) and |y| <= 2^52:
+//     |c - y*w/q| <= 1/2 + |y| * 2^-54   =>   |r| <= q * (1/2 + |y| * 2^-54).
+// A forward butterfly keeps every word in |v| <= 1.25 q: x is first brought to
+// |x| <= q/2 (1 + 2^-20) by one conditional -+q (the comparison and the selection
+// of the correction run on the ALU pipe, on the high word of the double), then
+// X' = x + r, Y' = x - r with |r| <= q (1/2 + 1.25 q 2^-54) <= 0.735 q.  An
+// inverse butterfly keeps |v| <= 0.75 q: s = x + y (<= 1.5 q) gets the same
+// conditional correction, u = x - y (<= 1.5 q <= 2^52) goes through the product,
+// |r| <= q (1/2 + 1.5 q 2^-54) <= 0.75 q.  Every sum is an integer below 2^53, so
+// all of this is exact and the canonical residue comes out bit-identical to the
+// integer paths: 9 FP64 + ~4 ALU instructions per butterfly.
+// ---------------------------------------------------------------------------
+HB_HD double u2d(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+HB_HD uint64_t d2u(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+// explicitly rounded operations: never contracted or re-associated by the compiler
+HB_HD double fp_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+HB_HD double fp_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+HB_HD double fp_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
+constexpr uint64_t kFpMagicBits = 0x4338000000000000ull;   // 1.5 * 2^52
+constexpr uint64_t kFpTwo52Bits = 0x4330000000000000ull;   // 2^52
+
+struct Fp64Mod {
+    double q, nq;          // the modulus and its negative
+    uint32_t half_hi;      // high word of (double)(q/2): the threshold of the conditional correction
+    uint32_t q_hi, q_lo;   // bit pattern of (double)q
+    uint32_t pad;
+    uint64_t qi;           // the modulus as an integer
+    uint64_t vote;         // in-contract inputs are below q + q/4
+    // n^-1 and n^-1 * w of the last inverse stage: centred residues and their quotients by q
+    double inv_n, inv_n_q, inv_n_w, inv_n_w_q;
+};
+HB_HD bool fp64_modulus_ok(uint64_t q) {
+    return q >= ((uint64_t)1 << 36) && q <= (((uint64_t)1 << 53) / 3) && (q & 1);
+}
+// centred representative of a residue as a double, and its correctly rounded quotient by q
+HB_HD double fp_centred(uint64_t w, uint64_t q) {
+    return (w > (q >> 1)) ? -(double)(int64_t)(q - w) : (double)(int64_t)w;
+}
+HB_HD double fp_quot(double ws, uint64_t q) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(ws, (double)(int64_t)q);
+#else
+    return ws / (double)(int64_t)q;
+#endif
+}
+HB_HD Fp64Mod make_fp64mod(uint64_t q, uint64_t inv_n, uint64_t inv_n_w) {
+    Fp64Mod m;
+    m.q = (double)(int64_t)q;
+    m.nq = -m.q;
+    m.half_hi = (uint32_t)(d2u(m.q * 0.5) >> 32);
+    m.q_hi = (uint32_t)(d2u(m.q) >> 32);
+    m.q_lo = (uint32_t)d2u(m.q);
+    m.pad = 0;
+    m.qi = q;
+    m.vote = q + (q >> 2);
+    m.inv_n = fp_centred(inv_n, q);
+    m.inv_n_q = fp_quot(m.inv_n, q);
+    m.inv_n_w = fp_centred(inv_n_w, q);
+    m.inv_n_w_q = fp_quot(m.inv_n_w, q);
+    return m;
+}
+
+// |x| <= 1.5 q  ->  |x'| <= max(q/2 (1 + 2^-20), |x| - q),  x' = x (mod q)
+HB_HD double fp_cred(double x, const Fp64Mod& m) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t hi = (uint32_t)__double2hiint(x);
+    const bool big = (hi & 0x7fffffffu) > m.half_hi;
+    const uint32_t chi = big ? (m.q_hi | (hi & 0x80000000u)) : 0u;
+    const uint32_t clo = big ? m.q_lo : 0u;
+    return __dadd_rn(x, -__hiloint2double((int)chi, (int)clo));
+#else
+    const uint32_t hi = (uint32_t)(d2u(x) >> 32);
+    const bool big = (hi & 0x7fffffffu) > m.half_hi;
+    const uint32_t chi = big ? (m.q_hi | (hi & 0x80000000u)) : 0u;
+    const uint32_t clo = big ? m.q_lo : 0u;
+    return fp_add(x, -u2d(((uint64_t)chi << 32) | clo));
+#endif
+}
+// y * w (mod q) for |y| <= 2^52, in |r| <= q (1/2 + |y| 2^-54)
+HB_HD double fp_mulmod(double y, double w, double wi, const Fp64Mod& m) {
+    const double magic = u2d(kFpMagicBits);
+    const double c = fp_add(fp_fma(y, wi, magic), -magic);
+    const double h = fp_mul(y, w);
+    const double l = fp_fma(y, w, -h);
+    const double d = fp_fma(c, m.nq, h);
+    return fp_add(d, l);
+}
+// integer word below 2^52 -> double
+HB_HD double fp_from_int(uint64_t x) { return fp_add(u2d(x | kFpTwo52Bits), -u2d(kFpTwo52Bits)); }
+// |v| <= 1.5 q  ->  canonical residue in [0, q) as an integer
+HB_HD uint64_t fp_to_canonical(double v, const Fp64Mod& m) {
+    v = fp_cred(v, m);                                             // |v| < 2^51
+    const int64_t s = (int64_t)(d2u(fp_add(v, u2d(kFpMagicBits))) - kFpMagicBits);
+    return (uint64_t)(s + ((s >> 63) & (int64_t)m.qi));
+}
+HB_HD void fwd_bfly_fp64(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, const Fp64Mod& m) {
+    const double x = fp_cred(u2d(X), m);
+    const double r = fp_mulmod(u2d(Y), u2d(w), u2d(wi), m);
+    X = d2u(fp_add(x, r));
+    Y = d2u(fp_add(x, -r));
+}
+HB_HD void inv_bfly_fp64(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, const Fp64Mod& m) {
+    const double x = u2d(X), y = u2d(Y);
+    const double s = fp_add(x, y), u = fp_add(x, -y);
+    X = d2u(fp_cred(s, m));
+    Y = d2u(fp_mulmod(u, u2d(w), u2d(wi), m));
+}
+HB_HD void inv_last_bfly_fp64(uint64_t& X, uint64_t& Y, const Fp64Mod& m) {
+    const double x = u2d(X), y = u2d(Y);
+    const double s = fp_add(x, y), u = fp_add(x, -y);
+    X = fp_to_canonical(fp_mulmod(s, m.inv_n, m.inv_n_q, m), m);
+    Y = fp_to_canonical(fp_mulmod(u, m.inv_n_w, m.inv_n_w_q, m), m);
 }
 
 // x mod q for any x < 2^64 with mu = floor(2^64/q)   (q < 2^63).

@@ -26,6 +26,11 @@ struct ModTab {
     const Tw32* itw32;
     uint32_t small_ok;
     uint32_t inv_lazy_ok;   // q < 2^52: the correction-free inverse butterflies may be used
+    // FP64-pipe path (modarith.cuh): constants and the {centred root, root / q} tables
+    Fp64Mod fd;
+    const TwPair* ftwd;
+    const TwPair* itwd;
+    uint32_t fp64_ok;       // 2^36 <= q <= 2^53 / 3 and the tables above are there
 };
 
 // ---- load transforms (applied to each word as it enters the transform) ----
@@ -327,11 +332,17 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     of.template prefetch<C>(tid);     // epilogue operands (keyswitch) towards L2 early
     int bad = 0;
     if constexpr (MODE == kFastVote) {
-        // forward contract: every word < 4q (tests/test_utils/ntt.cpp:483-486)
-        bad = out_of_range<C::E>(v, t.fm.q4);
+        // forward contract: every word < 4q (tests/test_utils/ntt.cpp:483-486); the FP64
+        // arithmetic takes words below 1.25 q, the rest goes to the exact kernel
+        bad = out_of_range<C::E>(v, A::kFp64 ? t.fd.vote : t.fm.q4);
     }
     if constexpr (MODE == kFastVote) vote_raise<C>(bad);
-    fwd_head_compute<C, 0>(tid, v, t.ftw, a, [&](int gi, int k0, int k1) {
+    const TwPair* ftw = A::kFp64 ? t.ftwd : t.ftw;
+    if constexpr (A::kFp64) {
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) v[e] = a.enter_fwd(v[e]);
+    }
+    fwd_head_compute<C, 0>(tid, v, ftw, a, [&](int gi, int k0, int k1) {
         head_store_word<C, P0::R, P0::LS>(tid, W, gi, k0, v[gi * (1 << P0::R) + k0]);
         head_store_word<C, P0::R, P0::LS>(tid, W, gi, k1, v[gi * (1 << P0::R) + k1]);
     });
@@ -342,12 +353,12 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
             return false;
         }
     }
-    fwd_mid_passes<C, 1>(tid, W, t.ftw, a);
+    fwd_mid_passes<C, 1>(tid, W, ftw, a);
     tail_load<C>(tid, W, v, XfIdent());
     __syncthreads();        // every word of W is in registers now
     pf.template issue<C>(); // ... so the buffer can take the next polynomial
     // each row leaves as soon as it is final: its staged TMA store drains while the next row is computed
-    fwd_tail_compute<C>(tid, v, t.ftw, a, [&](int ri) { of.template store<C>(tid + ri * C::NT, v + ri * 16); });
+    fwd_tail_compute<C>(tid, v, ftw, a, [&](int ri) { of.template store<C>(tid + ri * C::NT, v + ri * 16); });
     return true;
 }
 
@@ -372,10 +383,15 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     if constexpr (Xf::kPost) xf.template post<C>(tid, v);
     int bad = 0;
     if constexpr (MODE == kFastVote) {
-        // inverse contract: every word < 2q (ntt.cpp:600-606)
-        bad = out_of_range<C::E>(v, t.twoq);
+        // inverse contract: every word < 2q (ntt.cpp:600-606); FP64 arithmetic: below 1.25 q
+        bad = out_of_range<C::E>(v, A::kFp64 ? t.fd.vote : t.twoq);
     }
-    inv_tail_compute<C>(tid, v, t.itw, a);
+    const TwPair* itw = A::kFp64 ? t.itwd : t.itw;
+    if constexpr (A::kFp64) {
+#pragma unroll
+        for (int e = 0; e < C::E; ++e) v[e] = a.enter_inv(v[e]);
+    }
+    inv_tail_compute<C>(tid, v, itw, a);
     tail_store<C>(tid, W, v);
     if constexpr (MODE == kFastVote) vote_raise<C>(bad);   // right before the barrier it rides on
     __syncthreads();
@@ -385,13 +401,13 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
             return false;
         }
     }
-    inv_mid_passes<C, 0>(tid, W, t.itw, a);
+    inv_mid_passes<C, 0>(tid, W, itw, a);
     head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
     __syncthreads();
     pf.template issue<C>();
     // every pair is stored as soon as its last butterfly has made it final: the stores (32 B/clk
     // per SM at most) drain under the remaining butterflies instead of as one burst at the end
-    inv_head_compute<C, C::NP - 1>(tid, v, t.itw, a, [&](int gi, int k0, int k1) {
+    inv_head_compute<C, C::NP - 1>(tid, v, itw, a, [&](int gi, int k0, int k1) {
         of.word(inv_last_index<C>(tid, gi, k0), v[gi * (1 << PL::R) + k0]);
         of.word(inv_last_index<C>(tid, gi, k1), v[gi * (1 << PL::R) + k1]);
     });
@@ -406,10 +422,11 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 //   const ModTab& mod(item)
 //   Xf xf(item), Of of(item, store_map)
 // `list`: the deferred list (written in kFastVote, read in kExactList mode).
-template <class C, bool FWD, int MODE, class Job, bool LAZY = false>
+template <class C, bool FWD, int MODE, class Job, bool LAZY = false, bool FP64 = false>
 HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
                          uint32_t* list) {
     static_assert(!LAZY || (!FWD && (MODE == kFastVote || MODE == kFastTrust)), "LAZY is an inverse fast-path option");
+    static_assert(!FP64 || (!LAZY && (MODE == kFastVote || MODE == kFastTrust)), "FP64 is a fast-path option");
     // The 128-byte TMA swizzle needs the buffer 1024-byte aligned; the dynamic
     // shared window of a kernel without static shared memory starts aligned.
     uint64_t* W = smem_poly<C>();
@@ -440,7 +457,11 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         parity ^= 1;
         const ModTab& t = job.mod(item);
         bool done;
-        if constexpr (LAZY) {
+        if constexpr (FP64) {
+            const Fp64Arith a = {t.fd};
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (LAZY) {
             const LazyInvArith a = {t.fm, t.sc};
             done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (MODE == kFastVote || MODE == kFastTrust) {
@@ -874,6 +895,205 @@ HB_D void ntt_persistent_small2(uint64_t* data, const ModTab& t, uint32_t n_item
         if constexpr (FWD) done = ntt_fwd_small2_cta<C32, MODE>(S, t, poly, iter);
         else done = ntt_inv_small2_cta<C32, MODE>(S, t, poly, iter);
         if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// small-modulus path, third generation ("small3"): two transforms per SM
+// ---------------------------------------------------------------------------
+// One CTA of 1024 threads = two groups of 512, each running its own stream of polynomials
+// with its own named barrier, so that the store burst, the barrier bubbles and the shared-
+// memory phases of one transform hide under the butterflies of the other.  Shared memory:
+// three 64 KiB regions.  Group A lands a polynomial (uint64, 128 KiB) in R0 (lower half) +
+// R1 (upper half), narrows it IN PLACE into R0 during the first pass and works there;
+// group B uses R2 + R1 the same way.  R1 is needed only between a group's TMA issue and the
+// end of its first-pass loads, so the groups take turns on it: releases are arrivals on one
+// mbarrier (phase k = k-th release), A acquires on even turns, B on odd ones.
+template <class C32>
+struct Small3Plan {
+    static constexpr uint32_t REGION = C32::N / 2;          // uint64 words per 64 KiB region
+    static constexpr uint32_t BAR_WORD = 3 * REGION;        // full[A], full[B], R1 token
+    static constexpr uint32_t FLAG_WORD = BAR_WORD + 3;     // four uint32 flags: [group][iteration parity]
+    static constexpr size_t BYTES = (size_t)(FLAG_WORD + 2) * 8;
+};
+
+HB_D void group_sync(uint32_t g) { asm volatile("bar.sync %0, 512;" ::"r"(g + 1u) : "memory"); }
+HB_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// range vote of a group: flag (iter & 1) belongs to this iteration, the other one is cleared
+// a full iteration ahead of its next use (cf. small2_vote); includes the group barrier
+HB_D bool small3_vote(volatile uint32_t* flags, int bad, uint32_t iter, uint32_t g, uint32_t gtid, bool vote) {
+    if (vote && __any_sync(0xffffffffu, bad) && (gtid & 31u) == 0) flags[iter & 1u] = 1;
+    group_sync(g);
+    if (!vote) return false;
+    const bool deferred = flags[iter & 1u] != 0;
+    if (gtid == 0) flags[(iter & 1u) ^ 1u] = 0;
+    return deferred;
+}
+
+// 32 consecutive result words of one row, widened, straight from registers (8 x 32 bytes)
+HB_D void store_row32_direct(uint64_t* dst, const uint32_t* v) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * c), "l"((uint64_t)v[4 * c]),
+                     "l"((uint64_t)v[4 * c + 1]), "l"((uint64_t)v[4 * c + 2]), "l"((uint64_t)v[4 * c + 3])
+                     : "memory");
+}
+
+template <class C32, int P>
+HB_D void fwd_mid_passes3(uint32_t gtid, uint32_t g, uint32_t* S, const Tw32* tw, const SmallArith& a) {
+    if constexpr (P < C32::NP) {
+        fwd_head_pass<C32, P>(gtid, S, tw, a);
+        group_sync(g);
+        fwd_mid_passes3<C32, P + 1>(gtid, g, S, tw, a);
+    }
+}
+template <class C32, int P>
+HB_D void inv_mid_passes3(uint32_t gtid, uint32_t g, uint32_t* S, const Tw32* tw, const SmallArith& a) {
+    if constexpr (P < C32::NP - 1) {
+        inv_head_pass<C32, P>(gtid, S, tw, a);
+        group_sync(g);
+        inv_mid_passes3<C32, P + 1>(gtid, g, S, tw, a);
+    }
+}
+
+// forward: landing (low | up) -> poly (bit-reversed order, [0,q)); false = deferred
+template <class C32, int MODE>
+HB_D bool ntt_fwd_small3(const uint64_t* low, const uint64_t* up, uint32_t* S, uint64_t* token,
+                         volatile uint32_t* flags, const ModTab& t, uint64_t* poly, uint32_t iter, uint32_t g,
+                         uint32_t gtid) {
+    using P0 = FwdPass<C32, 0>;
+    static_assert(P0::LS == C32::LOGN - P0::R && (C32::E >> P0::R) == 1, "one column per thread in the first pass");
+    const SmallArith a = {t.sm32};
+    uint32_t v[C32::E];
+    uint32_t hi_or = 0, lo_max = 0;
+    // column gtid: word k sits at k * 2^LS + gtid; k below E/2 in the lower landing half
+#pragma unroll
+    for (int c0 = 0; c0 < C32::E; c0 += 8) {
+        uint64_t tt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = c0 + j;
+            const uint64_t* src = (k < C32::E / 2) ? low : up;
+            tt[j] = src[swz(((uint32_t)(k & (C32::E / 2 - 1)) << P0::LS) + gtid)];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            hi_or |= (uint32_t)(tt[j] >> 32);
+            lo_max = max(lo_max, (uint32_t)tt[j]);
+            v[c0 + j] = (uint32_t)tt[j];
+        }
+    }
+    // everybody has read the landing halves: R1 goes to the other group, the lower half becomes S
+    const bool deferred =
+        small3_vote(flags, (hi_or != 0) | (lo_max >= 2u * t.sm32.twoq), iter, g, gtid, MODE == kFastVote);
+    if (gtid == 0) mbar_arrive(token);
+    if (deferred) return false;
+    fwd_head_compute<C32, 0>(gtid, v, t.ftw32, a, [&](int gi, int k0, int k1) {
+        head_store_word<C32, P0::R, P0::LS>(gtid, S, gi, k0, v[gi * (1 << P0::R) + k0]);
+        head_store_word<C32, P0::R, P0::LS>(gtid, S, gi, k1, v[gi * (1 << P0::R) + k1]);
+    });
+    group_sync(g);
+    fwd_mid_passes3<C32, 1>(gtid, g, S, t.ftw32, a);
+    tail_load<C32>(gtid, S, v, XfSame32());
+    group_sync(g);                            // S (the lower region) is free for the next landing
+    fwd_tail_compute<C32>(gtid, v, t.ftw32, a, [&](int ri) {
+        store_row32_direct(poly + (size_t)(gtid + ri * C32::NT) * C32::ROW, v + ri * C32::ROW);
+    });
+    return true;
+}
+
+// inverse: landing (bit-reversed order) -> poly (natural order, [0,q))
+template <class C32, int MODE>
+HB_D bool ntt_inv_small3(const uint64_t* low, const uint64_t* up, uint32_t* S, uint64_t* token,
+                         volatile uint32_t* flags, const ModTab& t, uint64_t* poly, uint32_t iter, uint32_t g,
+                         uint32_t gtid) {
+    using PL = InvPass<C32, C32::NP - 1>;
+    static_assert(C32::E == C32::ROW, "one row per thread");
+    const SmallArith a = {t.sm32};
+    uint32_t v[C32::E];
+    uint32_t hi_or = 0, lo_max = 0;
+    // row gtid = uint64 landing rows 2*gtid, 2*gtid + 1; rows below N/64 live in the lower half
+    const uint32_t row64 = gtid * 2;
+    const uint64_t* src = (gtid < C32::NT / 2) ? low : up - Small3Plan<C32>::REGION;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint64_t x, y;
+            ld2(src + (row64 + h) * 16 + (((uint32_t)c ^ ((row64 + h) & 7u)) << 1), x, y);
+            hi_or |= (uint32_t)(x >> 32) | (uint32_t)(y >> 32);
+            lo_max = max(lo_max, max((uint32_t)x, (uint32_t)y));
+            v[h * 16 + 2 * c] = (uint32_t)x;
+            v[h * 16 + 2 * c + 1] = (uint32_t)y;
+        }
+    const bool deferred = small3_vote(flags, (hi_or != 0) | (lo_max >= t.sm32.twoq), iter, g, gtid, MODE == kFastVote);
+    if (gtid == 0) mbar_arrive(token);
+    if (deferred) return false;
+    inv_tail_compute<C32>(gtid, v, t.itw32, a);
+    tail_store<C32>(gtid, S, v);
+    group_sync(g);
+    inv_mid_passes3<C32, 0>(gtid, g, S, t.itw32, a);
+    head_load<C32, PL::R, PL::LS>(gtid, S, v, XfSame32());
+    group_sync(g);                            // S is free for the next landing
+    inv_head_compute<C32, C32::NP - 1>(gtid, v, t.itw32, a, [&](int gi, int k0, int k1) {
+        poly[inv_last_index<C32>(gtid, gi, k0)] = v[gi * (1 << PL::R) + k0];
+        poly[inv_last_index<C32>(gtid, gi, k1)] = v[gi * (1 << PL::R) + k1];
+    });
+    return true;
+}
+
+template <class C32, bool FWD, int MODE>
+HB_D void ntt_persistent_small3(const CUtensorMap* tmap, uint64_t* data, const ModTab& t, uint32_t n_items,
+                                uint32_t* list) {
+    using P3 = Small3Plan<C32>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint64_t* base = reinterpret_cast<uint64_t*>(smem_raw);
+    const uint32_t g = threadIdx.x >> 9, gtid = threadIdx.x & 511u;
+    uint64_t* low = base + (g ? 2 * P3::REGION : 0);           // R0 for group A, R2 for group B
+    uint64_t* up = base + P3::REGION;                          // R1, shared in turns
+    uint32_t* S = reinterpret_cast<uint32_t*>(low);
+    uint64_t* full = base + P3::BAR_WORD + g;
+    uint64_t* token = base + P3::BAR_WORD + 2;
+    volatile uint32_t* flags = reinterpret_cast<volatile uint32_t*>(base + P3::FLAG_WORD) + 2 * g;
+    constexpr uint32_t ROWS = C32::N / 16;                     // uint64 tensor-map rows per polynomial
+    if (threadIdx.x == 0) {
+        if (smem_u32(base) & 1023u) __trap();
+        mbar_init(base + P3::BAR_WORD, 1);
+        mbar_init(base + P3::BAR_WORD + 1, 1);
+        mbar_init(token, 1);
+        uint32_t* f = reinterpret_cast<uint32_t*>(base + P3::FLAG_WORD);
+        f[0] = f[1] = f[2] = f[3] = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+    // the CTA's items are blockIdx.x + s * gridDim.x; group g takes the positions s = g, g + 2, ...
+    auto item_at = [&](uint32_t j) { return blockIdx.x + (2 * j + g) * gridDim.x; };
+    // leader: take R1 (turn 2j + g waits for release 2j + g - 1) and start the landing of item j
+    auto land = [&](uint32_t j) {
+        if (2 * j + g > 0) mbar_wait(token, (g + 1u) & 1u);    // A waits odd phases, B even ones
+        fence_proxy_async();
+        const uint32_t row0 = item_at(j) * ROWS;
+        mbar_expect_tx(full, C32::N * 8);
+        tma_load_rows(low, tmap, full, row0);
+        tma_load_rows(low + 4096, tmap, full, row0 + 256);
+        tma_load_rows(up, tmap, full, row0 + 512);
+        tma_load_rows(up + 4096, tmap, full, row0 + 768);
+    };
+    if (item_at(0) >= n_items) return;                         // nothing for this group
+    if (gtid == 0) land(0);
+    for (uint32_t j = 0; item_at(j) < n_items; ++j) {
+        const uint32_t item = item_at(j);
+        mbar_wait(full, j & 1u);
+        uint64_t* poly = data + (size_t)item * C32::N;
+        bool done;
+        if constexpr (FWD) done = ntt_fwd_small3<C32, MODE>(low, up, S, token, flags, t, poly, j, g, gtid);
+        else done = ntt_inv_small3<C32, MODE>(low, up, S, token, flags, t, poly, j, g, gtid);
+        if (MODE == kFastVote && !done && gtid == 0) defer_item(list, item);
+        if (!done) group_sync(g);                              // nobody reads the landing any more
+        if (gtid == 0 && item_at(j + 1) < n_items) land(j + 1);
     }
 }
 

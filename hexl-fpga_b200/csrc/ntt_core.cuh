@@ -195,6 +195,7 @@ struct InvScale {
 struct ExactArith {
     using elem = uint64_t;
     using Tw = TwPair;
+    static constexpr bool kFp64 = false;
     uint64_t q, twoq;
     InvScale sc;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
@@ -217,6 +218,7 @@ struct ExactArith {
 struct FastArith {
     using elem = uint64_t;
     using Tw = TwPair;
+    static constexpr bool kFp64 = false;
     FastMod m;
     InvScale sc;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
@@ -238,11 +240,33 @@ struct FastArithTab : FastArith {
     HB_HD uint64_t fwd_final(uint64_t x) const { return reduce_by_table(x, m, kq); }
 };
 
+// FP64-pipe arithmetic (modarith.cuh): the registers and the shared buffer hold the bit
+// patterns of integer-valued doubles, the packed twiddles are {centred root, root / q} as
+// doubles (k_pack_twiddles_fp64); words are converted right after the range vote and come
+// back as canonical integers from fwd_final / inv_last.
+struct Fp64Arith {
+    using elem = uint64_t;
+    using Tw = TwPair;
+    static constexpr bool kFp64 = true;
+    static constexpr bool kLazyInv = false;
+    Fp64Mod m;
+    HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
+    HB_HD uint64_t enter_fwd(uint64_t x) const { return d2u(fp_from_int(x)); }               // [0, 1.25q)
+    HB_HD uint64_t enter_inv(uint64_t x) const { return d2u(fp_cred(fp_from_int(x), m)); }   // |v| <= q/2
+    HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly_fp64(X, Y, t.w, t.wp, m); }
+    HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical(u2d(x), m); }
+    template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
+        inv_bfly_fp64(X, Y, t.w, t.wp, m);
+    }
+    template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last_bfly_fp64(X, Y, m); }
+};
+
 // inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
 // E = log2 of the bound (in units of q) of the words entering the stage
 struct LazyInvArith {
     using elem = uint64_t;
     using Tw = TwPair;
+    static constexpr bool kFp64 = false;
     FastMod m;
     InvScale sc;
     static constexpr bool kLazyInv = true;

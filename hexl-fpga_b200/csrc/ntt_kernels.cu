@@ -30,16 +30,16 @@ struct JobInv : JobPlain<C> {
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
 };
 
-template <class C, int MODE>
+template <class C, int MODE, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap,
                                                    const __grid_constant__ CUtensorMap smap, const JobFwd<C> job,
                                                    uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
+    ntt_persistent<C, true, MODE, JobFwd<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
-template <class C, int MODE, bool LAZY = false>
+template <class C, int MODE, bool LAZY = false, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
                                                    uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, false, MODE, JobInv<C>, LAZY>(&tmap, nullptr, job, n_items, list);
+    ntt_persistent<C, false, MODE, JobInv<C>, LAZY, FP64>(&tmap, nullptr, job, n_items, list);
 }
 
 // inverse transform of NTT(a) (.) NTT(b): the fused tail of a polynomial multiply
@@ -74,6 +74,13 @@ __global__ void __launch_bounds__(C32::NT, 2) k_ntt_small2(uint64_t* data, const
     ntt_persistent_small2<C32, FWD, MODE>(data, tab, n_items, list);
 }
 
+// third generation: two transforms per SM sharing three 64 KiB regions (ntt_block.cuh)
+template <class C32, bool FWD, int MODE>
+__global__ void __launch_bounds__(1024, 1) k_ntt_small3(const __grid_constant__ CUtensorMap tmap, uint64_t* data,
+                                                       const ModTab tab, uint32_t n_items, uint32_t* list) {
+    ntt_persistent_small3<C32, FWD, MODE>(&tmap, data, tab, n_items, list);
+}
+
 // ---- packed twiddle builder -------------------------------------------------
 template <class C>
 __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
@@ -93,6 +100,26 @@ __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64
         TwPair t = {0, 0};
         if (s >= 0) t = TwPair{inv_roots[s], precon_inv[s]};
         inv_out[e] = t;
+    }
+}
+
+// FP64-pipe tables: {centred root as a double, its correctly rounded quotient by q}
+template <class C>
+__global__ void k_pack_twiddles_fp64(const uint64_t* __restrict__ roots, TwPair* __restrict__ fwd_out,
+                                     const uint64_t* __restrict__ inv_roots, TwPair* __restrict__ inv_out,
+                                     uint64_t q) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    auto entry = [&](uint64_t r) {
+        const double ws = fp_centred(r < q ? r : r % q, q);
+        return TwPair{d2u(ws), d2u(fp_quot(ws, q))};
+    };
+    if (fwd_out && e < (uint32_t)C::FWD_ENTRIES) {
+        const int s = fwd_pack_src<C>(e);
+        fwd_out[e] = s >= 0 ? entry(roots[s]) : TwPair{0, 0};
+    }
+    if (inv_out && e < (uint32_t)C::INV_ENTRIES) {
+        const int s = inv_pack_src<C>(e);
+        inv_out[e] = s >= 0 ? entry(inv_roots[s]) : TwPair{0, 0};
     }
 }
 
@@ -183,11 +210,20 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
     const size_t smem = ntt_smem_bytes<C>();
     cudaError_t e;
     if constexpr (FWD) {
-        auto kern = k_ntt_fwd<C, MODE>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
         JobFwd<C> job;
         job.data = base;
         job.tab = tab;
+        if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+            if (tab.fp64_ok) {       // 36..51-bit modulus: butterflies on the FP64 pipe
+                auto kern = k_ntt_fwd<C, MODE, true>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+                kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, smap, job,
+                                                                                               (uint32_t)cnt, list);
+                return cudaGetLastError();
+            }
+        }
+        auto kern = k_ntt_fwd<C, MODE>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
         kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, smap, job, (uint32_t)cnt,
                                                                                        list);
     } else {
@@ -195,6 +231,13 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         job.data = base;
         job.tab = tab;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+            if (tab.fp64_ok) {
+                auto kern = k_ntt_inv<C, MODE, false, true>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+                kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt,
+                                                                                               list);
+                return cudaGetLastError();
+            }
             if (tab.inv_lazy_ok) {   // q < 2^52: butterflies without per-stage corrections
                 auto kern = k_ntt_inv<C, MODE, true>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
@@ -233,6 +276,27 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
         // 64-bit exact kernel through the deferred list)
         if (tab.small_ok) {
             using C32 = NttCfg<14, 5, 5>;
+            if (tab.small_ok == 3) {
+                const size_t smem3 = Small3Plan<C32>::BYTES;
+                int sms = 0, dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const unsigned grid3 = (unsigned)(batch < (uint64_t)sms ? batch : (uint64_t)sms);
+                if (trust) {
+                    auto kern = k_ntt_small3<C32, FWD, kFastTrust>;
+                    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)))
+                        return e;
+                    kern<<<grid3, 1024, smem3, st>>>(tmap, data, tab, (uint32_t)batch, list);
+                    *launches += 1;
+                    return cudaGetLastError();
+                }
+                auto kern = k_ntt_small3<C32, FWD, kFastVote>;
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3))) return e;
+                kern<<<grid3, 1024, smem3, st>>>(tmap, data, tab, (uint32_t)batch, list);
+                if ((e = cudaGetLastError())) return e;
+                *launches += 2;
+                return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+            }
             if (tab.small_ok == 2) {
                 const size_t smem2 = Small2Plan<C32>::BYTES;
                 if (trust) {
@@ -325,6 +389,19 @@ cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roo
                                  TwPair* inv_out, uint32_t* zero_count, cudaStream_t st) {
     HB_DISPATCH_CFG(logn, variant,
                     return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, zero_count, st));
+    return cudaErrorInvalidValue;
+}
+
+template <class C>
+static cudaError_t pack_fp64_one(const uint64_t* roots, TwPair* fwd_out, const uint64_t* inv_roots, TwPair* inv_out,
+                                 uint64_t q, cudaStream_t st) {
+    const int total = C::FWD_ENTRIES > C::INV_ENTRIES ? C::FWD_ENTRIES : C::INV_ENTRIES;
+    k_pack_twiddles_fp64<C><<<(total + 255) / 256, 256, 0, st>>>(roots, fwd_out, inv_roots, inv_out, q);
+    return cudaGetLastError();
+}
+cudaError_t launch_pack_twiddles_fp64(uint32_t logn, int variant, const uint64_t* roots, TwPair* fwd_out,
+                                      const uint64_t* inv_roots, TwPair* inv_out, uint64_t q, cudaStream_t st) {
+    HB_DISPATCH_CFG(logn, variant, return pack_fp64_one<C>(roots, fwd_out, inv_roots, inv_out, q, st));
     return cudaErrorInvalidValue;
 }
 

@@ -130,9 +130,12 @@ int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, ui
  *   "ntt_variant"      bit 0: 32 words per thread at n = 16384 (default 1);
  *                      bit 1: skip the input-range vote (caller guarantees the contract)
  *   "small_path"       q < 2^30 kernels: 0 off, 1 uint32 kernels behind a TMA landing
- *                      buffer (default), 2 uint32 kernels with direct loads, two CTAs / SM
+ *                      buffer (default), 2 uint32 kernels with direct loads, two CTAs / SM,
+ *                      3 two transforms per SM sharing three 64 KiB regions (both measured slower)
  *   "small_tma_store"  1: small-modulus forward results leave through TMA stores (default 0)
  *   "inv_lazy"         1: correction-free inverse butterflies for q < 2^52 (default 0)
+ *   "fp64_path"        1 (default): hexl_b200_ntt_fwd / _inv run their butterflies on the FP64
+ *                      pipe when 2^36 <= q <= 2^53 / 3 (bit-identical results); 0: integer kernels
  *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16)
  *   "ks_mac_items"     items sharing one key load in the keyswitch MAC (1, 4, 8) */
 int hexl_b200_set_option(const char* name, int64_t value);

@@ -5,6 +5,7 @@
 // layout, the exact arithmetic on garbage inputs and the fast arithmetic
 // (approximate Shoup quotient, lazy forward, small-multiple reduction) on
 // in-range inputs, without a GPU.  Built and run by tests/test_cpu_emul.py.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -227,6 +228,73 @@ int run_small_all() {
     return rc;
 }
 
+// FP64-pipe arithmetic (modarith.cuh): words converted on entry as the kernels do after the vote
+template <int LOGN, int LOGE>
+int run_fp64(uint64_t q, int kind) {
+    using C = NttCfg<LOGN, LOGE>;
+    const uint64_t n = C::N;
+    if (!fp64_modulus_ok(q)) return 0;
+    uint64_t w = ho_min_primitive_root(2 * n, q);
+    std::vector<uint64_t> roots(n), precon(n), ir(n), ip(n), a(n), ad(n), ref(n), out(n);
+    ho_compute_roots(n, q, w, roots.data(), precon.data(), ir.data(), ip.data());
+    std::vector<TwPair> ftw(C::FWD_ENTRIES), itw(C::INV_ENTRIES);
+    auto entry = [&](uint64_t r) {
+        const double ws = fp_centred(r, q);
+        return TwPair{d2u(ws), d2u(fp_quot(ws, q))};
+    };
+    for (uint32_t e = 0; e < (uint32_t)C::FWD_ENTRIES; ++e) {
+        int s = fwd_pack_src<C>(e);
+        ftw[e] = s < 0 ? TwPair{0, 0} : entry(roots[s]);
+    }
+    for (uint32_t e = 0; e < (uint32_t)C::INV_ENTRIES; ++e) {
+        int s = inv_pack_src<C>(e);
+        itw[e] = s < 0 ? TwPair{0, 0} : entry(ir[s]);
+    }
+    ho_splitmix_fill(a.data(), n, 77 + LOGN + kind, q);
+    const uint64_t top = q + (q >> 2) - 1;     // largest in-contract word
+    if (kind == 1) for (auto& x : a) x = q - 1;
+    if (kind == 2) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? q - 1 : 0;
+    if (kind == 3) for (uint64_t i = 0; i < n; ++i) a[i] = (i & 1) ? top - (i % 7) : (q >> 1) + (i % 3);
+    if (kind == 4) for (uint64_t i = 0; i < n; ++i) a[i] = ((i >> (i % 14)) & 1) ? top : (q >> 1) + 1;
+    if (kind == 5) for (auto& x : a) x = top;
+    uint64_t inv_n = ho_inv_mod(n % q, q), inv_n_w = ho_mul_mod(inv_n, ir[n - 1], q);
+    Fp64Arith fa = {make_fp64mod(q, inv_n, inv_n_w)};
+    int bad = 0, badi = 0;
+    ref = a;
+    for (auto& x : ref) x %= q;                 // the oracle's contract; the result is the canonical residue either way
+    ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
+    for (uint64_t i = 0; i < n; ++i) ad[i] = fa.enter_fwd(a[i]);
+    emul_fwd<C, C>(ad, out, ftw.data(), fa);
+    for (uint64_t i = 0; i < n; ++i) bad += out[i] != ref[i];
+    ref = a;
+    for (auto& x : ref) x %= q;
+    ho_inv_ntt(ref.data(), n, q, ir.data(), ip.data(), inv_n, inv_n_w);
+    for (uint64_t i = 0; i < n; ++i) ad[i] = fa.enter_inv(a[i]);
+    emul_inv<C, C>(ad, out, itw.data(), fa);
+    for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
+    printf("FP64 LOGN=%d LOGE=%d q=%llu in=%d fwd/inv mismatch=%d/%d\n", LOGN, LOGE, (unsigned long long)q, kind, bad,
+           badi);
+    return bad + badi;
+}
+
+template <int LOGN, int LOGE>
+int run_fp64_all() {
+    int rc = 0;
+    uint64_t p[1];
+    size_t bits[] = {36, 44, 50, 51};
+    for (size_t b : bits) {
+        if (ho_generate_primes(p, 1, b, (size_t)1 << LOGN) != 1) continue;
+        for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE>(p[0], k);
+    }
+    // the largest admissible modulus: the last NTT prime below 2^53 / 3
+    for (uint64_t c = (((uint64_t)1 << 53) / 3 / (2ull << LOGN)) * (2ull << LOGN) + 1;; c -= (2ull << LOGN))
+        if (c <= (((uint64_t)1 << 53) / 3) && ho_is_prime(c)) {
+            for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE>(c, k);
+            break;
+        }
+    return rc;
+}
+
 template <int LOGN, int LOGE>
 int run_all() {
     uint64_t p[2];
@@ -238,6 +306,50 @@ int run_all() {
         for (int g = 0; g < 6; ++g) rc += run<LOGN, LOGE>(p[0], g);
     }
     return rc;
+}
+
+// unit properties of the FP64 modular product and the conditional correction at the edges
+// of their stated ranges
+static int fp64_properties() {
+    int fbad = 0;
+    uint64_t qs[] = {(1ULL << 36) + 1, 2251799814045697ULL, ((1ULL << 53) / 3 - 1) | 1};
+    uint64_t s = 2024, r[3];
+    for (uint64_t q : qs) {
+        if (!fp64_modulus_ok(q)) { ++fbad; continue; }
+        const Fp64Mod m = make_fp64mod(q, 1, 1);
+        const uint64_t ymax = q + (q >> 1);            // 1.5 q: the largest multiplied word (inverse)
+        for (int it = 0; it < 400000; ++it) {
+            s = ho_splitmix_fill(r, 3, s, 0);
+            uint64_t w = r[0] % q;
+            if (it % 11 == 0) w = (q >> 1) + (it % 3);  // |centred w| at its maximum
+            uint64_t ya = (it % 7 == 0) ? ymax - (r[1] % 5) : r[1] % (ymax + 1);
+            const bool neg = r[2] & 1;
+            const double y = neg ? -(double)(int64_t)ya : (double)(int64_t)ya;
+            const double ws = fp_centred(w, q);
+            const double rr = fp_mulmod(y, ws, fp_quot(ws, q), m);
+            // exactness: rr is an integer congruent to y*w, within the stated bound
+            const unsigned __int128 prod = (unsigned __int128)(ya % q) * w % q;
+            uint64_t want = (uint64_t)prod;
+            if (neg && want) want = q - want;
+            const int64_t ri = (int64_t)rr;
+            if ((double)ri != rr) ++fbad;
+            const uint64_t got = (uint64_t)(((ri % (int64_t)q) + (int64_t)q) % (int64_t)q);
+            if (got != want) ++fbad;
+            const double bound = (double)q * (0.5 + (double)ya / 18014398509481984.0) + 1.0;
+            if (fabs(rr) > bound) ++fbad;
+            if (fp_to_canonical(rr, m) != want) ++fbad;
+            // conditional correction: |x| <= 1.5 q -> at most max(q/2 (1 + 2^-20), |x| - q)
+            const double x = neg ? -(double)(int64_t)ya : (double)(int64_t)ya;
+            const double xr = fp_cred(x, m);
+            const double lim = fmax((double)q * 0.5 * (1.0 + 1.0 / 1048576.0), fabs(x) - (double)q);
+            if (fabs(xr) > lim) ++fbad;
+            const int64_t xi = (int64_t)xr;
+            if ((uint64_t)(((xi % (int64_t)q) + (int64_t)q) % (int64_t)q) != (neg ? (q - ya % q) % q : ya % q)) ++fbad;
+            if (fp_from_int(ya) != (double)(int64_t)ya) ++fbad;
+        }
+    }
+    printf("fp64 arithmetic property failures=%d\n", fbad);
+    return fbad;
 }
 
 int main() {
@@ -252,6 +364,10 @@ int main() {
     rc += run_all<12, 5>();
     rc += run_small_all<14, 5>();
     rc += run_small_all<13, 5>();
+    rc += run_fp64_all<14, 5>();
+    rc += run_fp64_all<14, 4>();
+    rc += run_fp64_all<12, 4>();
+    rc += fp64_properties();
     // fast-arithmetic unit properties
     {
         uint64_t qs[] = {12289, 1073153, 2251799814045697ULL, (1ULL << 57) + 0x1234567ULL * 2 + 1, (1ULL << 60) - 93};

@@ -51,6 +51,7 @@ def oracle():
         o.ho_fnv1a.argtypes = [vp, C.c_size_t]; o.ho_fnv1a.restype = u64
         o.ho_splitmix_fill.argtypes = [vp, C.c_size_t, u64, u64]; o.ho_splitmix_fill.restype = u64
         o.ho_max_threads.restype = C.c_int
+        o.ho_is_prime.argtypes = [u64]; o.ho_is_prime.restype = C.c_int
         _o = o
     return _o
 
@@ -85,6 +86,10 @@ def primes(num, bits, n):
     got = oracle().ho_generate_primes(P(out), num, bits, n)
     assert got == num
     return [int(x) for x in out]
+
+
+def is_prime(n):
+    return bool(oracle().ho_is_prime(n))
 
 
 class Tables:

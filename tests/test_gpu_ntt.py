@@ -224,7 +224,7 @@ def test_small_modulus_32bit_path(hb, q):
     polys.append(np.full(N, 2**32 + 5, dtype=np.uint64))                                  # high word set
     # small_path 1: TMA landing buffer (default); 2: direct loads, two CTAs per SM; "1t": path 1 with the
     # forward epilogue through TMA stores (option small_tma_store)
-    for small in (2, 1, "1t", 0):
+    for small in (3, 2, 1, "1t", 0):      # 3: two transforms per SM sharing three 64 KiB regions
         hb.set_option("small_path", 1 if small == "1t" else small)
         hb.set_option("small_tma_store", 1 if small == "1t" else 0)
         try:
@@ -257,3 +257,103 @@ def test_inverse_lazy_and_corrected_butterflies_agree(hb, n, bits):
             hb.set_option("inv_lazy", 0)
         for i in range(len(polys)):
             assert np.array_equal(got[i], want[i]), (lazy, i)
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 147, 149, 297, 700])
+def test_small_path_two_transforms_per_sm(hb, batch):
+    """small_path=3: two 512-thread groups per CTA take turns on the shared landing half; odd and
+    even item counts per CTA, garbage polynomials (deferred to the exact kernel) on both groups."""
+    import torch
+
+    n, q = 16384, 136314881
+    t = ob.Tables(n, q)
+    g = torch.Generator(device="cuda").manual_seed(1000 + batch)
+    x = torch.randint(0, q, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    garbage = sorted({r for r in (batch // 2, batch // 2 + 148, batch - 1) if 0 < r < batch})
+    for r in garbage:
+        x[r] = torch.from_numpy(ob.splitmix(n, r + 1, 0).view(np.int64)).cuda()
+    x0 = x.clone()
+    hb.set_option("small_path", 3)
+    try:
+        hb.ntt_fwd(x, to_gpu(t.roots), to_gpu(t.precon), q, n)
+        fwd = x.clone()
+        hb.ntt_inv(x, to_gpu(t.inv_roots), to_gpu(t.precon_inv), q, t.inv_n, t.inv_n_w, n)
+    finally:
+        hb.set_option("small_path", 1)
+    for r in sorted(set(garbage + [0, batch // 3, batch - 1])):
+        assert np.array_equal(to_np(fwd[r]), ob.fwd_ntt(to_np(x0[r]), t)), r
+    clean = torch.tensor([r for r in range(batch) if r not in garbage], device="cuda")
+    assert torch.equal(x[clean], x0[clean])
+
+
+def _largest_fp64_prime(n):
+    """the last NTT-friendly prime not above 2^53 / 3 (the FP64-pipe path's upper limit)"""
+    lim = 2**53 // 3
+    c = (lim // (2 * n)) * (2 * n) + 1
+    while c > lim or not ob.is_prime(c):
+        c -= 2 * n
+    return c
+
+
+@pytest.mark.parametrize("n", [16384, 4096])
+@pytest.mark.parametrize("which", ["b36", "b44", "b50", "b51", "top", "above"])
+def test_fp64_pipe_path_matches_oracle_and_integer_path(hb, n, which):
+    """Butterflies on the FP64 pipe (option fp64_path, default on, 2^36 <= q <= 2^53/3): bit-exact
+    against the oracle and the integer kernels on random words, on the edges of the centred ranges
+    (all q-1, alternating 0 / q-1, words in [q, 1.25q)), and on out-of-contract polynomials, which
+    the range vote sends to the exact kernel."""
+    if which == "top":
+        q = _largest_fp64_prime(n)
+    elif which == "above":                      # first prime beyond the limit: integer kernels
+        q = 2**53 // 3 // (2 * n) * (2 * n) + 1
+        while q <= 2**53 // 3 or not ob.is_prime(q):
+            q += 2 * n
+    else:
+        q = ob.primes(1, int(which[1:]), n)[0]
+    t = ob.Tables(n, q)
+    top = q + q // 4 - 1
+    idx = np.arange(n, dtype=np.uint64)
+    polys = [
+        ob.splitmix(n, 5, q),
+        np.full(n, q - 1, dtype=np.uint64),
+        np.where(idx & np.uint64(1), np.uint64(q - 1), np.uint64(0)),
+        np.where(idx & np.uint64(1), np.uint64(top) - idx % np.uint64(7), np.uint64(q // 2) + idx % np.uint64(3)),
+        np.full(n, top, dtype=np.uint64),
+        np.full(n, q + q // 4 + 2**33, dtype=np.uint64),          # just out of the FP64 contract, inside the integer one
+        ob.splitmix(n, 6, 0),                                      # garbage
+        np.full(n, 2**64 - 1, dtype=np.uint64),
+        ob.splitmix(n, 7, q),
+    ]
+    polys[8][n // 3] = 2**63 + 12345                               # one bad word in an otherwise clean polynomial
+    want_f = [ob.fwd_ntt(p, t) for p in polys]
+    want_i = [ob.inv_ntt(p, t) for p in polys]
+    for fp64 in (1, 0):
+        for variant in ((1, 0) if n == 16384 else (1,)):
+            hb.set_option("fp64_path", fp64)
+            hb.set_option("ntt_variant", variant)
+            try:
+                got_f = run_fwd(hb, polys, t)
+                got_i = run_inv(hb, polys, t)
+            finally:
+                hb.set_option("fp64_path", 1)
+                hb.set_option("ntt_variant", 1)
+            for i in range(len(polys)):
+                assert np.array_equal(got_f[i], want_f[i]), (which, fp64, variant, "fwd", i)
+                assert np.array_equal(got_i[i], want_i[i]), (which, fp64, variant, "inv", i)
+
+
+def test_fp64_pipe_path_large_batch_round_trip(hb):
+    """4096 polynomials (BASELINE configs[1]) through the FP64-pipe kernels: forward spot-checked
+    against the oracle, inverse(forward(x)) == x for the whole batch."""
+    import torch
+
+    q = 2251799814045697
+    t = ob.Tables(N, q)
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    x = torch.randint(0, q, (4096, N), dtype=torch.int64, device="cuda", generator=g)
+    x0 = x.clone()
+    hb.ntt_fwd(x, to_gpu(t.roots), to_gpu(t.precon), q, N)
+    for r in (0, 147, 148, 2047, 4095):
+        assert np.array_equal(to_np(x[r]), ob.fwd_ntt(to_np(x0[r]), t)), r
+    hb.ntt_inv(x, to_gpu(t.inv_roots), to_gpu(t.precon_inv), q, t.inv_n, t.inv_n_w, N)
+    assert torch.equal(x, x0)

@@ -26,6 +26,8 @@ if op in ("ntt", "ntt28"):
     x = torch.randint(0, q, (batch, N), dtype=torch.int64, device="cuda")
     r, p, ir, ip = gpu(t.roots), gpu(t.precon), gpu(t.inv_roots), gpu(t.precon_inv)
     hb.set_option("ntt_variant", variant)
+    if os.environ.get("SMALL_PATH"):
+        hb.set_option("small_path", int(os.environ["SMALL_PATH"]))
     for _ in range(3):
         hb.ntt_fwd(x, r, p, q, N)
         hb.ntt_inv(x, ir, ip, q, t.inv_n, t.inv_n_w, N)

@@ -45,20 +45,23 @@ def main():
         t = ob.Tables(N, q)
         x = torch.randint(0, q, (B, N), dtype=torch.int64, device="cuda")
         r, p, ir, ip = gpu(t.roots), gpu(t.precon), gpu(t.inv_roots), gpu(t.precon_inv)
-        for variant, small in ((1, 1), (3, 1), (1, 2)) if q < 2**30 else ((1, 1), (3, 1)):
+        # (variant, small_path, fp64_path)
+        for variant, small, fp64 in (((1, 1, 1), (3, 1, 1)) if q < 2**30 else ((1, 1, 1), (3, 1, 1), (1, 1, 0))):
             hb.set_option("ntt_variant", variant)
             hb.set_option("small_path", small)
+            hb.set_option("fp64_path", fp64)
             med, best = timeit(lambda: hb.ntt_fwd(x, r, p, q, N))
-            out.append({"op": "ntt_fwd", "q": q, "variant": variant, "small_path": small, "batch": B, "s": med, "best_s": best,
+            out.append({"op": "ntt_fwd", "q": q, "variant": variant, "small_path": small, "fp64_path": fp64, "batch": B, "s": med, "best_s": best,
                         "per_s": B / med, "frac_hbm": B * 262144 / med / PEAK})
             x %= q
             med, best = timeit(lambda: hb.ntt_inv(x, ir, ip, q, t.inv_n, t.inv_n_w, N))
-            out.append({"op": "ntt_inv", "q": q, "variant": variant, "batch": B, "s": med, "best_s": best,
+            out.append({"op": "ntt_inv", "q": q, "variant": variant, "fp64_path": fp64, "batch": B, "s": med, "best_s": best,
                         "per_s": B / med, "frac_hbm": B * 262144 / med / PEAK})
             print(json.dumps(out[-2]), flush=True)
             print(json.dumps(out[-1]), flush=True)
         hb.set_option("ntt_variant", 1)
         hb.set_option("small_path", 1)
+        hb.set_option("fp64_path", 1)
         del x
     # dyadic config 3
     n, M, Bd = 8192, 4, 8192
