@@ -435,7 +435,10 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     const int ks_variant = hb::ks_variant_for((uint32_t)logn);
     const size_t fe = hb::packed_fwd_entries((uint32_t)logn, ks_variant), ie = hb::packed_inv_entries((uint32_t)logn, ks_variant);
     uint64_t* d_raw = nullptr;      // raw tables, only needed while packing
-    if ((e = cudaMalloc(&p->d_packed, K * (fe + ie) * sizeof(hb::TwPair)))) return cleanup(cuda_fail(e, "cudaMalloc tables"));
+    // second half: the same tables in the FP64-pipe format (modarith.cuh)
+    if ((e = cudaMalloc(&p->d_packed, 2 * K * (fe + ie) * sizeof(hb::TwPair)))) return cleanup(cuda_fail(e, "cudaMalloc tables"));
+    bool fp64_all = g_fp64_path.load() != 0;
+    for (uint64_t i = 0; i < K; ++i) fp64_all = fp64_all && hb::fp64_modulus_ok(moduli[i]);
     if ((e = cudaMalloc(&d_raw, K * 4 * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc raw tables"));
     if ((e = cudaMalloc(&p->d_keys, D * 2 * K * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc keys"));
     if ((e = cudaMalloc(&p->d_small, 2 * K * 8))) return cleanup(cuda_fail(e, "cudaMalloc small"));
@@ -456,6 +459,11 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         memcpy(h + 3 * n, t.precon_inv.data(), n * 8);
         hb::TwPair* pk = p->d_packed + i * (fe + ie);
         h_tabs[i] = make_modtab(q, t.inv_n, t.inv_n_w, pk, pk + fe, logn);
+        if (fp64_all) {
+            h_tabs[i].ftwd = pk + K * (fe + ie);
+            h_tabs[i].itwd = pk + K * (fe + ie) + fe;
+            h_tabs[i].fp64_ok = 1;
+        }
         h_divs[i] = hb::make_divisor(q);
         h_small[i] = msf[i] % q;                       // host/src/fpga.cpp:1057-1061
         h_small[K + i] = nt::shoup(h_small[i], q);
@@ -465,11 +473,14 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         const uint64_t* d = d_raw + i * 4 * n;
         hb::TwPair* pk = p->d_packed + i * (fe + ie);
         e = hb::launch_pack_twiddles((uint32_t)logn, ks_variant, d, d + n, pk, d + 2 * n, d + 3 * n, pk + fe, nullptr, 0);
+        if (e == cudaSuccess && fp64_all)
+            e = hb::launch_pack_twiddles_fp64((uint32_t)logn, ks_variant, d, pk + K * (fe + ie), d + 2 * n,
+                                              pk + K * (fe + ie) + fe, moduli[i], 0);
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaFree(d_raw);
     if (e != cudaSuccess) return cleanup(cuda_fail(e, "upload / pack tables"));
-    g_launches += K;
+    g_launches += fp64_all ? 2 * K : K;
     for (uint64_t j = 0; j < D; ++j)
         if ((e = cudaMemcpy(p->d_keys + j * 2 * K * n, keys[j], 2 * K * n * 8, cudaMemcpyHostToDevice)))
             return cleanup(cuda_fail(e, "upload keys"));
@@ -484,7 +495,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     p->dev.fast_ok = 1;
     for (uint64_t i = 0; i < K; ++i)
         if (!h_tabs[i].fwd_fast_ok || !h_tabs[i].inv_fast_ok) p->dev.fast_ok = 0;
-    p->dev.pad = 0;
+    p->dev.fp64_ok = (p->dev.fast_ok && fp64_all) ? 1u : 0u;
     p->dev.logn = (uint32_t)logn;
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;

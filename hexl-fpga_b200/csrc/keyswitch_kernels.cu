@@ -39,10 +39,10 @@ struct JobIntt1 {
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{U + (size_t)item * C::N}; }
 };
-template <class C, int MODE>
+template <class C, int MODE, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobIntt1<C> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, false, MODE>(&tmap, &smap, job, n_items, list);
+    ntt_persistent<C, false, MODE, JobIntt1<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S2 -------------------------------------------------------------------
@@ -82,10 +82,10 @@ struct JobNtt1 {
         return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
     }
 };
-template <class C, int MODE>
+template <class C, int MODE, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobNtt1<C> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
+    ntt_persistent<C, true, MODE, JobNtt1<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S3 -------------------------------------------------------------------
@@ -349,10 +349,10 @@ struct JobIntt2 {
         return OfWordsRound{ACC + (size_t)poly(item) * C::N, qk, qk >> 1};
     }
 };
-template <class C, int MODE>
+template <class C, int MODE, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt2(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobIntt2<C> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, false, MODE>(&tmap, &smap, job, n_items, list);
+    ntt_persistent<C, false, MODE, JobIntt2<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S5 -------------------------------------------------------------------
@@ -437,10 +437,10 @@ struct JobNtt2 {
                          ks.tabs[i].q, ks.msf[i], ks.msf_p[i]};
     }
 };
-template <class C, int MODE>
+template <class C, int MODE, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobNtt2<C> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, true, MODE>(&tmap, &smap, job, n_items, list);
+    ntt_persistent<C, true, MODE, JobNtt2<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 size_t ks_scratch_words_per_item(const KsDev& ks) {
@@ -475,7 +475,14 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     if ((e = make_poly_tmap(&m_vs, V, items * D * D, C::LOGN, 32))) return e;   // staged stores of S2
     uint32_t* list = reinterpret_cast<uint32_t*>(ACC + items * 2 * R * C::N);
     int nl = 0;
-    if (ks.fast_ok) {
+    if (ks.fast_ok && ks.fp64_ok) {
+        // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, q)
+        if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<C, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt1<C, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<C>{ks, V}, items * D * D, list, st))) return e;
+        nl += 3;
+    } else if (ks.fast_ok) {
         // S1 sees caller data: vote + deferred exact pass; the later stages read
         // words this pipeline produced (reduced by their load transforms)
         if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
@@ -509,7 +516,10 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     } else
         k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
-    if (ks.fast_ok) {
+    if (ks.fast_ok && ks.fp64_ok) {
+        if ((e = run_persistent(k_ks_intt2<C, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt2<C, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+    } else if (ks.fast_ok) {
         if ((e = run_persistent(k_ks_intt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
         if ((e = run_persistent(k_ks_ntt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;
     } else {

@@ -14,7 +14,7 @@ namespace hb {
 struct KsDev {
     uint32_t logn, D, K, R;
     uint32_t fast_ok;       // every modulus admits the fast arithmetic (q < 2^58)
-    uint32_t pad;
+    uint32_t fp64_ok;       // ... and the FP64-pipe butterflies (2^36 <= q <= 2^53/3, tables in tabs[])
     const ModTab* tabs;     // [K]
     const Divisor* divs;    // [K]
     const uint64_t* keys;   // [D][2][K][N]  == k_switch_keys[j][(c*K+i)*N + l]

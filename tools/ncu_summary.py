@@ -30,6 +30,9 @@ for r in rows[2:]:
     for k in keys:
         if k in hdr:
             print(f"  {k} = {r[hdr.index(k)]} {units[hdr.index(k)]}")
+    for i, h in enumerate(hdr):
+        if "fp64" in h and h not in keys and ("pct_of_peak" in h or h.endswith(".sum")):
+            print(f"  {h} = {r[i]} {units[i]}")
     st = []
     for i, h in enumerate(hdr):
         if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
