@@ -330,12 +330,12 @@ def run_ours(args, rank, world, local_rank):
                    "n": N, "modulus": Q52, "batch_per_gpu": BATCH, "sharding": f"batch x{world}, no collective",
                    "l2": "working set 512 MiB per GPU > 126 MB L2 (no flush needed)"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_ntt_fwd (forward NTT, one CTA per polynomial)",
+        "roofline": {"bound": "hbm", "kernel": "k_ntt_fwd<.., FP64> (forward NTT, one CTA per polynomial, butterflies on the FP64 pipe)",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "peak_source": peak_src, "traffic": ncu_traffic("ntt_fwd"),
                      "algorithmic_bytes_per_launch": BATCH * NTT_BYTES, "launch_s": fwd_s},
         "clocks": clocks,
-        "kernel_variant": "persistent TMA-fed CTAs, 32 words/thread, fast lazy path with range vote + deferred exact list",
+        "kernel_variant": "persistent TMA-fed CTAs, 32 words/thread, FP64-pipe butterflies on centred integer-valued doubles (bit-exact), range vote + deferred exact list",
     }
     if rank == 0:
         line.update(extras(args, hb, ob, dev, hbm_peak, world))

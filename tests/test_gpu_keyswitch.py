@@ -33,16 +33,46 @@ SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("fp64", [1, 0])
 @pytest.mark.parametrize("n,D,K,batch,bits", SHAPES)
-def test_device_api_vs_oracle(hb, n, D, K, batch, bits):
+def test_device_api_vs_oracle(hb, n, D, K, batch, bits, fp64):
+    """fp64 = 1: the transform stages run on the FP64 pipe (all moduli within 2^36 .. 2^53/3, the
+    default); 0: the integer kernels.  The option is read when the plan is created."""
     p = KsProblem(n, D, K, batch, bits)
-    plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+    hb.set_option("fp64_path", fp64)
+    try:
+        plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+    finally:
+        hb.set_option("fp64_path", 1)
     res = gpu(p.result)
     hb_t = gpu(p.t_target)
     plan.keyswitch(res, hb_t, batch)
     got = res.cpu().numpy().view(np.uint64)
     assert np.array_equal(got, p.expected())
     plan.close()
+
+
+def test_out_of_range_target_words_go_to_the_exact_kernel(hb):
+    """t_target words in [1.25 q, 2q) are outside the FP64 arithmetic's contract but inside the
+    integer kernels': the first stage's range vote must send those digits to the exact kernel, so
+    both arithmetic paths produce the same words (the reference leaves such inputs undefined)."""
+    n, D, K, batch = 16384, 3, 4, 2
+    p = KsProblem(n, D, K, batch, 51)
+    t = p.t_target.reshape(batch, D, n).copy()
+    t[0, 1, 5] += np.uint64(int(p.moduli[1]) // 2)
+    t[1, 2, n - 1] = np.uint64(int(p.moduli[2]) + int(p.moduli[2]) // 2)
+    out = []
+    for fp64 in (1, 0):
+        hb.set_option("fp64_path", fp64)
+        try:
+            plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+        finally:
+            hb.set_option("fp64_path", 1)
+        res = gpu(p.result)
+        plan.keyswitch(res, gpu(t.reshape(batch, -1)), batch)
+        out.append(res.cpu().numpy().view(np.uint64).copy())
+        plan.close()
+    assert np.array_equal(out[0], out[1])
 
 
 def test_caller_twiddle_tables_are_honoured(hb):
