@@ -374,7 +374,7 @@ struct OfKsFinal {
     HB_D void prefetch(uint32_t tid) const {
 #pragma unroll
         for (int ri = 0; ri < C::E / 16; ++ri) {
-            const uint32_t off = (tid + ri * C::NT) * 16;
+            const uint32_t off = tail_row<C>(tid, ri) * 16;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(acc + off));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(result + off));
         }

@@ -84,7 +84,7 @@ struct XfMulGlobal {
         static_assert(C::ROW == 16, "64-bit rows");
 #pragma unroll
         for (int ri = 0; ri < C::E / 16; ++ri) {
-            const uint64_t* p = other + (size_t)(tid + ri * C::NT) * 16;
+            const uint64_t* p = other + (size_t)tail_row<C>(tid, ri) * 16;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2*>(p + 2 * c));
@@ -108,7 +108,8 @@ struct SmemPlan {
     static constexpr uint32_t BAR_WORD = C::N + STAGE_WORDS;
     static constexpr uint32_t FLAG_WORD = BAR_WORD + 1;   // range-vote flag (fast-vote kernels)
     static constexpr uint32_t KQ_WORD = BAR_WORD + 2;     // two tables of k*q, k < 64 (iteration parity)
-    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2 + 128) * 8;
+    static constexpr uint32_t CNT_WORD = BAR_WORD + 2 + 128;   // warps done with the buffer (C::WARPTAIL)
+    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2 + 128 + 1) * 8;
 };
 
 // forward output: the 16 contiguous words of one row per thread
@@ -227,10 +228,29 @@ struct Prefetch {
     uint32_t row;     // first tensor-map row of the next polynomial, or kNoPrefetch
     template <class C>
     HB_D void issue() const {
-        if (row != kNoPrefetch) {
+        if (row != kNoPrefetch && (!C::WARPTAIL || threadIdx.x == 0)) {
             uint64_t* W = smem_poly<C>();
             fence_proxy_async();
             issue_poly_load<C>(W, map, W + SmemPlan<C>::BAR_WORD, row);
+        }
+    }
+    // C::WARPTAIL: no block barrier before the prefetch.  Every warp reports that its words have
+    // left the buffer; the warp that completes the count (it never resets: NT/32 is a power of two)
+    // starts the copy.  `row` is valid in lane 0 of every warp.
+    template <class C>
+    HB_D void issue_when_all_warps_done() const {
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0) {
+            uint64_t* W = smem_poly<C>();
+            uint32_t old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
+                         : "=r"(old)
+                         : "r"(smem_u32(W + SmemPlan<C>::CNT_WORD))
+                         : "memory");
+            if ((old & (C::NT / 32 - 1)) == C::NT / 32 - 1 && row != kNoPrefetch) {
+                fence_proxy_async();
+                issue_poly_load<C>(W, map, W + SmemPlan<C>::BAR_WORD, row);
+            }
         }
     }
 };
@@ -264,7 +284,8 @@ template <class C, int P, class A>
 HB_D void fwd_mid_passes(uint32_t tid, uint64_t* W, const TwPair* tw, const A& a) {
     if constexpr (P < C::NP) {
         fwd_head_pass<C, P>(tid, W, tw, a);
-        __syncthreads();
+        if constexpr (C::WARPTAIL && P == C::NP - 1) __syncwarp();   // the tail reads what this warp wrote
+        else __syncthreads();
         fwd_mid_passes<C, P + 1>(tid, W, tw, a);
     }
 }
@@ -355,10 +376,14 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     }
     fwd_mid_passes<C, 1>(tid, W, ftw, a);
     tail_load<C>(tid, W, v, XfIdent());
-    __syncthreads();        // every word of W is in registers now
-    pf.template issue<C>(); // ... so the buffer can take the next polynomial
+    if constexpr (C::WARPTAIL) {
+        pf.template issue_when_all_warps_done<C>();
+    } else {
+        __syncthreads();        // every word of W is in registers now
+        pf.template issue<C>(); // ... so the buffer can take the next polynomial
+    }
     // each row leaves as soon as it is final: its staged TMA store drains while the next row is computed
-    fwd_tail_compute<C>(tid, v, ftw, a, [&](int ri) { of.template store<C>(tid + ri * C::NT, v + ri * 16); });
+    fwd_tail_compute<C>(tid, v, ftw, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); });
     return true;
 }
 
@@ -393,18 +418,37 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     }
     inv_tail_compute<C>(tid, v, itw, a);
     tail_store<C>(tid, W, v);
-    if constexpr (MODE == kFastVote) vote_raise<C>(bad);   // right before the barrier it rides on
-    __syncthreads();
-    if constexpr (MODE == kFastVote) {
-        if (vote_read<C>()) {
-            pf.template issue<C>();
-            return false;
+    if constexpr (C::WARPTAIL) {
+        // the first head pass stays inside the words this warp has just written: no block barrier
+        // before it, and the range vote rides on the one after it
+        static_assert(C::NP >= 2, "WARPTAIL inverse needs a warp-local head pass");
+        __syncwarp();
+        inv_head_pass<C, 0>(tid, W, itw, a);
+        if constexpr (MODE == kFastVote) vote_raise<C>(bad);
+        __syncthreads();
+        if constexpr (MODE == kFastVote) {
+            if (vote_read<C>()) {
+                pf.template issue<C>();
+                return false;
+            }
         }
+        inv_mid_passes<C, 1>(tid, W, itw, a);
+        head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
+        pf.template issue_when_all_warps_done<C>();
+    } else {
+        if constexpr (MODE == kFastVote) vote_raise<C>(bad);   // right before the barrier it rides on
+        __syncthreads();
+        if constexpr (MODE == kFastVote) {
+            if (vote_read<C>()) {
+                pf.template issue<C>();
+                return false;
+            }
+        }
+        inv_mid_passes<C, 0>(tid, W, itw, a);
+        head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
+        __syncthreads();
+        pf.template issue<C>();
     }
-    inv_mid_passes<C, 0>(tid, W, itw, a);
-    head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
-    __syncthreads();
-    pf.template issue<C>();
     // every pair is stored as soon as its last butterfly has made it final: the stores (32 B/clk
     // per SM at most) drain under the remaining butterflies instead of as one burst at the end
     inv_head_compute<C, C::NP - 1>(tid, v, itw, a, [&](int gi, int k0, int k1) {
@@ -441,6 +485,7 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         if (smem_u32(W) & 1023u) __trap();
         mbar_init(bar, 1);
         W[SmemPlan<C>::FLAG_WORD] = 0;
+        W[SmemPlan<C>::CNT_WORD] = 0;
         fence_barrier_init();
     }
     __syncthreads();
@@ -452,7 +497,8 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         const uint32_t next = i + gridDim.x;
         Prefetch pf;
         pf.map = tmap;
-        pf.row = (tid == 0 && next < n_items) ? job.src_row(item_of(next)) : kNoPrefetch;
+        pf.row = ((C::WARPTAIL ? (tid & 31u) == 0 : tid == 0) && next < n_items) ? job.src_row(item_of(next))
+                                                                                          : kNoPrefetch;
         mbar_wait(bar, parity);
         parity ^= 1;
         const ModTab& t = job.mod(item);

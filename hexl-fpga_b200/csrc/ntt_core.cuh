@@ -43,9 +43,13 @@ namespace hb {
 // LOGROW_ = log2(words per 128-byte shared-memory row): 4 for uint64 words, 5
 // for the uint32 small-modulus path.  The "tail" pass owns the last LOGROW
 // stages (one full row per thread), the head passes the first LOGN - LOGROW.
-template <int LOGN_, int LOGE_, int LOGROW_ = 4>
+// WARPTAIL_ = 1: the tail rows are dealt out by warp (rows 64w .. 64w+63 to warp w) instead of by
+// thread index, so that a warp's tail rows are exactly the words it handled in the last head pass
+// and the block barrier between the two becomes a __syncwarp (ntt_block.cuh).
+template <int LOGN_, int LOGE_, int LOGROW_ = 4, int WARPTAIL_ = 0>
 struct NttCfg {
     static constexpr int LOGN = LOGN_, LOGE = LOGE_, LOGROW = LOGROW_;
+    static constexpr bool WARPTAIL = WARPTAIL_ != 0;
     static constexpr int N = 1 << LOGN, E = 1 << LOGE, NT = N / E, ROW = 1 << LOGROW;
     using elem = typename std::conditional<LOGROW_ == 4, uint64_t, uint32_t>::type;
     // CTAs per SM the register allocation must allow (launch bounds)
@@ -55,6 +59,8 @@ struct NttCfg {
     static constexpr int BASE = HEAD / NP, REM = HEAD % NP;
     static_assert(LOGROW == 4 || LOGROW == 5, "rows hold 16 uint64 or 32 uint32 words");
     static_assert(LOGE >= LOGROW && LOGN >= LOGE + LOGROW, "unsupported NTT shape");
+    // two rows per thread and one full-size group per thread in the last head pass
+    static_assert(!WARPTAIL || (LOGE == LOGROW + 1 && HEAD % LOGE == 0), "WARPTAIL needs E = 2 rows = one last-pass group");
     static constexpr int pass_r(int p) { return BASE + (p < REM ? 1 : 0); }
     static constexpr int pass_s0(int p) {
         int s = 0;
@@ -548,13 +554,19 @@ HB_HD void head_store_word(uint32_t tid, T* sm, int gi, int k, T x) {
     sm[swz_t<T>(Gm::base(tid + (uint32_t)gi * C::NT) + ((uint32_t)k << LS))] = x;
 }
 
-// tail rows: thread tid owns rows tid + ri*NT of ROW contiguous words (128 bytes)
+// tail rows: thread tid owns rows tid + ri*NT of ROW contiguous words (128 bytes); with
+// C::WARPTAIL warp w owns rows 64w + 32*ri + lane (a warp's 32 rows are consecutive either way)
+template <class C>
+HB_HD uint32_t tail_row(uint32_t tid, int ri) {
+    if constexpr (C::WARPTAIL) return ((tid >> 5) << 6) + ((uint32_t)ri << 5) + (tid & 31u);
+    else return tid + (uint32_t)ri * C::NT;
+}
 template <class C, class Xf>
 HB_HD void tail_load(uint32_t tid, const typename C::elem* sm, typename C::elem* v, const Xf& xf) {
     constexpr int PER = 16 / sizeof(typename C::elem);   // words per 16-byte chunk
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
-        const uint32_t row = tid + ri * C::NT;
+        const uint32_t row = tail_row<C>(tid, ri);
         static_for<0, 8>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             typename C::elem t[PER];
@@ -571,7 +583,7 @@ HB_HD void tail_store(uint32_t tid, typename C::elem* sm, const typename C::elem
     constexpr int PER = 16 / sizeof(typename C::elem);
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
-        const uint32_t row = tid + ri * C::NT;
+        const uint32_t row = tail_row<C>(tid, ri);
         static_for<0, 8>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
             st_chunk(sm + row * C::ROW + (((uint32_t)c ^ (row & 7u)) * PER), v + ri * C::ROW + c * PER);
@@ -625,7 +637,7 @@ HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A:
                             const F& after_row) {
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
-        const uint32_t row = tid + ri * C::NT;
+        const uint32_t row = tail_row<C>(tid, ri);
         fwd_group<C::LOGROW, 32>(v + ri * C::ROW, tw + C::fwd_off(C::NP) + tail_tw_base<C>(row), a);
         static_for<0, C::ROW>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
@@ -654,7 +666,7 @@ template <class C, class A>
 HB_HD void inv_tail_compute(uint32_t tid, typename A::elem* v, const typename A::Tw* tw, const A& a) {
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
-        const uint32_t row = tid + ri * C::NT;
+        const uint32_t row = tail_row<C>(tid, ri);
         inv_group<C::LOGROW, false, 32, 1>(v + ri * C::ROW, tw + tail_tw_base<C>(row), a);
     });
     if constexpr (A::kLazyInv) {

@@ -8,6 +8,7 @@
 
 namespace hb {
 
+int g_warp_tail = 1;         // FP64-pipe forward kernel with warp-dealt tail rows (one block barrier per transform instead of three), option "warp_tail"
 int g_small_tma_store = 0;   // small-modulus forward epilogue through TMA stores (option "small_tma_store"): measured 5% slower than the coalesced register stores (slice reuse waits on the store engine), off by default
 
 // ---- plain batched transform, in place ------------------------------------
@@ -80,6 +81,16 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_small3(const __grid_constant__ 
                                                        const ModTab tab, uint32_t n_items, uint32_t* list) {
     ntt_persistent_small3<C32, FWD, MODE>(&tmap, data, tab, n_items, list);
 }
+
+// the configuration with warp-dealt tail rows, where the shape allows it
+template <class C>
+struct WarpTailCfg {
+    using type = C;
+};
+template <>
+struct WarpTailCfg<NttCfg<14, 5, 4, 0>> {
+    using type = NttCfg<14, 5, 4, 1>;
+};
 
 // ---- packed twiddle builder -------------------------------------------------
 template <class C>
@@ -214,6 +225,18 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         job.data = base;
         job.tab = tab;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+            using CW = typename WarpTailCfg<C>::type;
+            if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
+                auto kern = k_ntt_fwd<CW, MODE, true>;
+                const size_t smemw = ntt_smem_bytes<CW>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
+                JobFwd<CW> jobw;
+                jobw.data = base;
+                jobw.tab = tab;
+                kern<<<persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st>>>(tmap, smap, jobw,
+                                                                                                   (uint32_t)cnt, list);
+                return cudaGetLastError();
+            }
             if (tab.fp64_ok) {       // 36..51-bit modulus: butterflies on the FP64 pipe
                 auto kern = k_ntt_fwd<C, MODE, true>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
@@ -231,6 +254,18 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         job.data = base;
         job.tab = tab;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
+            using CW = typename WarpTailCfg<C>::type;
+            if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
+                auto kern = k_ntt_inv<CW, MODE, false, true>;
+                const size_t smemw = ntt_smem_bytes<CW>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
+                JobInv<CW> jobw;
+                jobw.data = base;
+                jobw.tab = tab;
+                kern<<<persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st>>>(tmap, jobw,
+                                                                                                   (uint32_t)cnt, list);
+                return cudaGetLastError();
+            }
             if (tab.fp64_ok) {
                 auto kern = k_ntt_inv<C, MODE, false, true>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;

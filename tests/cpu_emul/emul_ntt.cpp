@@ -66,7 +66,7 @@ void emul_fwd(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const
         T* v = &regs[(size_t)tid * C::E];
         fwd_tail_compute<C>(tid, v, tw, a);
         for (int ri = 0; ri < C::E / C::ROW; ++ri)
-            for (int k = 0; k < C::ROW; ++k) out[(tid + ri * C::NT) * C::ROW + k] = v[ri * C::ROW + k];
+            for (int k = 0; k < C::ROW; ++k) out[tail_row<C>(tid, ri) * C::ROW + k] = v[ri * C::ROW + k];
     }
 }
 
@@ -86,7 +86,7 @@ void emul_inv(const std::vector<uint64_t>& in, std::vector<uint64_t>& out, const
         } else {
             for (int ri = 0; ri < C::E / C::ROW; ++ri)
                 for (int k = 0; k < C::ROW; ++k)
-                    regs[(size_t)tid * C::E + ri * C::ROW + k] = (T)W[swz((tid + ri * C::NT) * C::ROW + k)];
+                    regs[(size_t)tid * C::E + ri * C::ROW + k] = (T)W[swz(tail_row<C>(tid, ri) * C::ROW + k)];
         }
     }
     for (uint32_t tid = 0; tid < (uint32_t)C::NT; ++tid) {
@@ -229,9 +229,9 @@ int run_small_all() {
 }
 
 // FP64-pipe arithmetic (modarith.cuh): words converted on entry as the kernels do after the vote
-template <int LOGN, int LOGE>
+template <int LOGN, int LOGE, int WT = 0>
 int run_fp64(uint64_t q, int kind) {
-    using C = NttCfg<LOGN, LOGE>;
+    using C = NttCfg<LOGN, LOGE, 4, WT>;
     const uint64_t n = C::N;
     if (!fp64_modulus_ok(q)) return 0;
     uint64_t w = ho_min_primitive_root(2 * n, q);
@@ -272,24 +272,24 @@ int run_fp64(uint64_t q, int kind) {
     for (uint64_t i = 0; i < n; ++i) ad[i] = fa.enter_inv(a[i]);
     emul_inv<C, C>(ad, out, itw.data(), fa);
     for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
-    printf("FP64 LOGN=%d LOGE=%d q=%llu in=%d fwd/inv mismatch=%d/%d\n", LOGN, LOGE, (unsigned long long)q, kind, bad,
-           badi);
+    printf("FP64 LOGN=%d LOGE=%d warp-tail=%d q=%llu in=%d fwd/inv mismatch=%d/%d\n", LOGN, LOGE, WT,
+           (unsigned long long)q, kind, bad, badi);
     return bad + badi;
 }
 
-template <int LOGN, int LOGE>
+template <int LOGN, int LOGE, int WT = 0>
 int run_fp64_all() {
     int rc = 0;
     uint64_t p[1];
     size_t bits[] = {36, 44, 50, 51};
     for (size_t b : bits) {
         if (ho_generate_primes(p, 1, b, (size_t)1 << LOGN) != 1) continue;
-        for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE>(p[0], k);
+        for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE, WT>(p[0], k);
     }
     // the largest admissible modulus: the last NTT prime below 2^53 / 3
     for (uint64_t c = (((uint64_t)1 << 53) / 3 / (2ull << LOGN)) * (2ull << LOGN) + 1;; c -= (2ull << LOGN))
         if (c <= (((uint64_t)1 << 53) / 3) && ho_is_prime(c)) {
-            for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE>(c, k);
+            for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE, WT>(c, k);
             break;
         }
     return rc;
@@ -365,6 +365,7 @@ int main() {
     rc += run_small_all<14, 5>();
     rc += run_small_all<13, 5>();
     rc += run_fp64_all<14, 5>();
+    rc += run_fp64_all<14, 5, 1>();     // tail rows dealt out by warp
     rc += run_fp64_all<14, 4>();
     rc += run_fp64_all<12, 4>();
     rc += fp64_properties();

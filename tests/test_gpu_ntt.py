@@ -327,19 +327,25 @@ def test_fp64_pipe_path_matches_oracle_and_integer_path(hb, n, which):
     polys[8][n // 3] = 2**63 + 12345                               # one bad word in an otherwise clean polynomial
     want_f = [ob.fwd_ntt(p, t) for p in polys]
     want_i = [ob.inv_ntt(p, t) for p in polys]
-    for fp64 in (1, 0):
-        for variant in ((1, 0) if n == 16384 else (1,)):
-            hb.set_option("fp64_path", fp64)
-            hb.set_option("ntt_variant", variant)
-            try:
-                got_f = run_fwd(hb, polys, t)
-                got_i = run_inv(hb, polys, t)
-            finally:
-                hb.set_option("fp64_path", 1)
-                hb.set_option("ntt_variant", 1)
-            for i in range(len(polys)):
-                assert np.array_equal(got_f[i], want_f[i]), (which, fp64, variant, "fwd", i)
-                assert np.array_equal(got_i[i], want_i[i]), (which, fp64, variant, "inv", i)
+    # (fp64_path, ntt_variant, warp_tail); warp_tail = 0: the FP64 kernels with three block barriers
+    # per transform instead of the warp-dealt tail rows (n = 16384, 32 words per thread only)
+    combos = [(1, 1, 1), (0, 1, 1)] + ([(1, 0, 1), (0, 0, 1), (1, 1, 0), (1, 3, 1)] if n == 16384 else [])
+    for fp64, variant, warp_tail in combos:
+        hb.set_option("fp64_path", fp64)
+        hb.set_option("ntt_variant", variant)
+        hb.set_option("warp_tail", warp_tail)
+        trusted = (variant & 2) != 0          # no range vote: in-contract polynomials only
+        try:
+            sel = [i for i in range(len(polys)) if not trusted or i < 5]
+            got_f = run_fwd(hb, [polys[i] for i in sel], t)
+            got_i = run_inv(hb, [polys[i] for i in sel], t)
+        finally:
+            hb.set_option("fp64_path", 1)
+            hb.set_option("ntt_variant", 1)
+            hb.set_option("warp_tail", 1)
+        for k, i in enumerate(sel):
+            assert np.array_equal(got_f[k], want_f[i]), (which, fp64, variant, warp_tail, "fwd", i)
+            assert np.array_equal(got_i[k], want_i[i]), (which, fp64, variant, warp_tail, "inv", i)
 
 
 def test_fp64_pipe_path_large_batch_round_trip(hb):
@@ -357,3 +363,12 @@ def test_fp64_pipe_path_large_batch_round_trip(hb):
         assert np.array_equal(to_np(x[r]), ob.fwd_ntt(to_np(x0[r]), t)), r
     hb.ntt_inv(x, to_gpu(t.inv_roots), to_gpu(t.precon_inv), q, t.inv_n, t.inv_n_w, N)
     assert torch.equal(x, x0)
+    # every polynomial of the batch against the three-barrier kernels (same words expected)
+    hb.ntt_fwd(x, to_gpu(t.roots), to_gpu(t.precon), q, N)
+    y = x0.clone()
+    hb.set_option("warp_tail", 0)
+    try:
+        hb.ntt_fwd(y, to_gpu(t.roots), to_gpu(t.precon), q, N)
+    finally:
+        hb.set_option("warp_tail", 1)
+    assert torch.equal(x, y)

@@ -46,7 +46,9 @@ def main():
         x = torch.randint(0, q, (B, N), dtype=torch.int64, device="cuda")
         r, p, ir, ip = gpu(t.roots), gpu(t.precon), gpu(t.inv_roots), gpu(t.precon_inv)
         # (variant, small_path, fp64_path)
-        for variant, small, fp64 in (((1, 1, 1), (3, 1, 1)) if q < 2**30 else ((1, 1, 1), (3, 1, 1), (1, 1, 0))):
+        # fp64 = 2: FP64 kernels without the warp-dealt tail rows
+        for variant, small, fp64 in (((1, 1, 1), (3, 1, 1)) if q < 2**30 else ((1, 1, 1), (3, 1, 1), (1, 1, 2), (1, 1, 0))):
+            hb.set_option("warp_tail", 0 if fp64 == 2 else 1)
             hb.set_option("ntt_variant", variant)
             hb.set_option("small_path", small)
             hb.set_option("fp64_path", fp64)
@@ -62,6 +64,7 @@ def main():
         hb.set_option("ntt_variant", 1)
         hb.set_option("small_path", 1)
         hb.set_option("fp64_path", 1)
+        hb.set_option("warp_tail", 1)
         del x
     # dyadic config 3
     n, M, Bd = 8192, 4, 8192
