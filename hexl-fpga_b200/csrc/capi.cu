@@ -338,18 +338,29 @@ int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint6
     const uint64_t chunk_max = 2048;
     const uint64_t chunk = batch < chunk_max ? batch : chunk_max;
     const size_t list_bytes = ((chunk + 1) * 4 + 255) & ~(size_t)255;
-    const size_t tb_off = (size_t)(1u << 20) + list_bytes;
+    // (same layout as the NTT entry points: [1M,2M) holds the FP64-pipe tables)
+    const size_t tb_off = (size_t)(2u << 20) + list_bytes;
     uint8_t* scratch = nullptr;
     cudaError_t e = g_scratch.get(st, tb_off + (size_t)chunk * n * 8, (void**)&scratch);
     if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: scratch");
     hb::TwPair* pf = reinterpret_cast<hb::TwPair*>(scratch);
     hb::TwPair* pi = reinterpret_cast<hb::TwPair*>(scratch + (1u << 19));
-    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (1u << 20));
+    uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (2u << 20));
     uint64_t* tb = reinterpret_cast<uint64_t*>(scratch + tb_off);
     e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, pf, d_inv_roots, d_precon_inv, pi, list, st);
     if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: pack twiddles");
-    const hb::ModTab t = make_modtab(q, inv_n, inv_n_w, pf, pi, logn, nullptr, nullptr);
+    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, pf, pi, logn, nullptr, nullptr);
     int launches = 1;
+    if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
+        hb::TwPair* pfd = reinterpret_cast<hb::TwPair*>(scratch + (1u << 20));
+        hb::TwPair* pid = reinterpret_cast<hb::TwPair*>(scratch + (3u << 19));
+        e = hb::launch_pack_twiddles_fp64((uint32_t)logn, variant, d_roots, pfd, d_inv_roots, pid, q, st);
+        if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: pack FP64 twiddles");
+        ++launches;
+        t.ftwd = pfd;
+        t.itwd = pid;
+        t.fp64_ok = 1;
+    }
     for (uint64_t off = 0; off < batch; off += chunk) {
         const uint64_t cnt = batch - off < chunk ? batch - off : chunk;
         uint64_t* res = d_result + off * n;

@@ -51,10 +51,10 @@ struct JobInvMul : JobPlain<C> {
     HB_D XfMulGlobal xf(uint32_t item) const { return XfMulGlobal{other + (size_t)item * C::N, dv}; }
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
 };
-template <class C, int MODE>
+template <class C, int MODE, bool FP64 = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv_mul(const __grid_constant__ CUtensorMap tmap,
                                                                    const JobInvMul<C> job, uint32_t n_items) {
-    ntt_persistent<C, false, MODE>(&tmap, nullptr, job, n_items, nullptr);
+    ntt_persistent<C, false, MODE, JobInvMul<C>, false, FP64>(&tmap, nullptr, job, n_items, nullptr);
 }
 
 // small-modulus kernels (q < 2^30): uint32 arithmetic, see ntt_block.cuh
@@ -475,7 +475,11 @@ static cudaError_t launch_inv_mul_one(uint64_t* data, const uint64_t* other, con
     job.tab = tab;
     job.other = other;
     job.dv = make_divisor(tab.q);
-    if (tab.inv_fast_ok) {
+    if (tab.inv_fast_ok && tab.fp64_ok) {
+        auto kern = k_ntt_inv_mul<C, kFastTrust, true>;   // canonical products into the FP64-pipe butterflies
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
+        kern<<<persistent_grid((const void*)kern, C::NT, smem, batch), C::NT, smem, st>>>(tmap, job, (uint32_t)batch);
+    } else if (tab.inv_fast_ok) {
         auto kern = k_ntt_inv_mul<C, kFastTrust>;   // the products are canonical: no range vote needed
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
         kern<<<persistent_grid((const void*)kern, C::NT, smem, batch), C::NT, smem, st>>>(tmap, job, (uint32_t)batch);
