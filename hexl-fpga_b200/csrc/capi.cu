@@ -511,6 +511,13 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     for (uint64_t i = 0; i < K; ++i)
         if (!h_tabs[i].fwd_fast_ok || !h_tabs[i].inv_fast_ok) p->dev.fast_ok = 0;
     p->dev.fp64_ok = (p->dev.fast_ok && fp64_all) ? 1u : 0u;
+    uint64_t qmin = moduli[0], qmax = moduli[0];
+    for (uint64_t i = 1; i < K; ++i) {
+        qmin = moduli[i] < qmin ? moduli[i] : qmin;
+        qmax = moduli[i] > qmax ? moduli[i] : qmax;
+    }
+    p->dev.s2_no_reduce = (p->dev.fp64_ok && qmax <= qmin + (qmin >> 2)) ? 1u : 0u;   // q_j - 1 < vote bound of every q_r
+    p->dev.pad = 0;
     p->dev.logn = (uint32_t)logn;
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;

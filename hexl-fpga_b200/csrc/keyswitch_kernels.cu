@@ -76,7 +76,7 @@ struct JobNtt1 {
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[idx_of(item)]; }
     HB_D XfReduce xf(uint32_t item) const {
         const ModTab& t = ks.tabs[idx_of(item)];
-        return XfReduce{t.q, t.mu};
+        return XfReduce{t.q, t.mu, ks.s2_no_reduce};
     }
     HB_D OfRows of(uint32_t item, const CUtensorMap* smap) const {
         return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
@@ -449,6 +449,15 @@ size_t ks_scratch_words_per_item(const KsDev& ks) {
     return ((size_t)ks.D + (size_t)ks.D * ks.D + 2 * (size_t)ks.R) * n + ks.D + 1;
 }
 
+template <class C>
+struct KsWarpTailCfg {
+    using type = C;
+};
+template <>
+struct KsWarpTailCfg<NttCfg<14, 5, 4, 0>> {
+    using type = NttCfg<14, 5, 4, 1>;
+};
+
 template <class K, class J>
 static cudaError_t run_persistent(K kern, int threads, size_t smem, const CUtensorMap& tmap, const CUtensorMap& smap,
                                   const J& job, uint64_t n_items, uint32_t* list, cudaStream_t st) {
@@ -475,12 +484,14 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     if ((e = make_poly_tmap(&m_vs, V, items * D * D, C::LOGN, 32))) return e;   // staged stores of S2
     uint32_t* list = reinterpret_cast<uint32_t*>(ACC + items * 2 * R * C::N);
     int nl = 0;
+    // FP64 stages: tail rows dealt out by warp where the shape allows it (ntt_core.cuh, NttCfg::WARPTAIL)
+    using CW = typename KsWarpTailCfg<C>::type;
     if (ks.fast_ok && ks.fp64_ok) {
-        // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, q)
+        // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, 1.25q)
         if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
-        if ((e = run_persistent(k_ks_intt1<C, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<CW>{ks, U}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
-        if ((e = run_persistent(k_ks_ntt1<C, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<C>{ks, V}, items * D * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
         nl += 3;
     } else if (ks.fast_ok) {
         // S1 sees caller data: vote + deferred exact pass; the later stages read
@@ -517,8 +528,8 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
     if (ks.fast_ok && ks.fp64_ok) {
-        if ((e = run_persistent(k_ks_intt2<C, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
-        if ((e = run_persistent(k_ks_ntt2<C, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
     } else if (ks.fast_ok) {
         if ((e = run_persistent(k_ks_intt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
         if ((e = run_persistent(k_ks_ntt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;

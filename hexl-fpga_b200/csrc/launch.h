@@ -15,6 +15,11 @@ struct KsDev {
     uint32_t logn, D, K, R;
     uint32_t fast_ok;       // every modulus admits the fast arithmetic (q < 2^58)
     uint32_t fp64_ok;       // ... and the FP64-pipe butterflies (2^36 <= q <= 2^53/3, tables in tabs[])
+    // FP64 path with all moduli within 25 % of each other (same-size primes, the usual case): a digit
+    // reduced mod q_j is below 1.25 q_r for every target modulus, i.e. already inside the forward
+    // transform's input contract, and NTT_r(x) = NTT_r(x mod q_r): stage S2 skips its base conversion
+    uint32_t s2_no_reduce;
+    uint32_t pad;
     const ModTab* tabs;     // [K]
     const Divisor* divs;    // [K]
     const uint64_t* keys;   // [D][2][K][N]  == k_switch_keys[j][(c*K+i)*N + l]

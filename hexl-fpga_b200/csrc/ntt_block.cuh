@@ -43,7 +43,8 @@ struct XfIdent {
 struct XfReduce {
     static constexpr bool kPost = false;
     uint64_t q, mu;
-    HB_D uint64_t operator()(uint64_t x) const { return barrett_reduce64(x, q, mu); }
+    uint32_t skip;   // the words are already inside the transform's input contract (see KsDev::s2_no_reduce)
+    HB_D uint64_t operator()(uint64_t x) const { return skip ? x : barrett_reduce64(x, q, mu); }
 };
 // keyswitch base conversion after the rounding (device/keyswitch/intt2_redu.hpp:
 // 24-51): the stage-S4 output is already v = (x + floor(qk/2)) mod qk; here
