@@ -239,24 +239,22 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: scratch");
     hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch);
     uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (2u << 20));
-    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr, list,
-                                 (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack twiddles");
+    // one launch packs the call's twiddles in every format its kernels may need
+    hb::PackExtra px;
     hb::Tw32* packed32 = nullptr;
-    int launches = 1;
-    if (g_small_path.load() && hb::small_modulus_ok(q) && hb::small_path_available((uint32_t)logn, variant)) {
-        packed32 = reinterpret_cast<hb::Tw32*>(scratch + 300 * 1024);
-        e = hb::launch_pack_twiddles32(d_roots, d_precon, packed32, nullptr, nullptr, nullptr, (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack 32-bit twiddles");
-        ++launches;
-    }
-    hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn, packed32, nullptr);
+    hb::TwPair* packed_d = nullptr;
+    if (g_small_path.load() && hb::small_modulus_ok(q) && hb::small_path_available((uint32_t)logn, variant))
+        px.fwd32 = packed32 = reinterpret_cast<hb::Tw32*>(scratch + 300 * 1024);
     if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
-        hb::TwPair* packed_d = reinterpret_cast<hb::TwPair*>(scratch + (1u << 20));
-        e = hb::launch_pack_twiddles_fp64((uint32_t)logn, variant, d_roots, packed_d, nullptr, nullptr, q,
-                                          (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack FP64 twiddles");
-        ++launches;
+        px.fwd_d = packed_d = reinterpret_cast<hb::TwPair*>(scratch + (1u << 20));
+        px.q = q;
+    }
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, packed, nullptr, nullptr, nullptr, list,
+                                 (cudaStream_t)stream, px);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: pack twiddles");
+    int launches = 1;
+    hb::ModTab t = make_modtab(q, 0, 0, packed, nullptr, logn, packed32, nullptr);
+    if (packed_d) {
         t.ftwd = packed_d;
         t.fp64_ok = 1;
     }
@@ -288,25 +286,21 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
     // second halves, so a forward and an inverse call may be queued back to back
     hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch + (1u << 19));
     uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (2u << 20) + list_bytes);
-    e = hb::launch_pack_twiddles((uint32_t)logn, variant, nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed,
-                                 list, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack twiddles");
+    hb::PackExtra px;
     hb::Tw32* packed32 = nullptr;
-    int launches = 1;
-    if (g_small_path.load() && hb::small_modulus_ok(q) && hb::small_path_available((uint32_t)logn, variant)) {
-        packed32 = reinterpret_cast<hb::Tw32*>(scratch + (1u << 19) + 300 * 1024);
-        e = hb::launch_pack_twiddles32(nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed32,
-                                       (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack 32-bit twiddles");
-        ++launches;
-    }
-    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn, nullptr, packed32);
+    hb::TwPair* packed_d = nullptr;
+    if (g_small_path.load() && hb::small_modulus_ok(q) && hb::small_path_available((uint32_t)logn, variant))
+        px.inv32 = packed32 = reinterpret_cast<hb::Tw32*>(scratch + (1u << 19) + 300 * 1024);
     if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
-        hb::TwPair* packed_d = reinterpret_cast<hb::TwPair*>(scratch + (3u << 19));
-        e = hb::launch_pack_twiddles_fp64((uint32_t)logn, variant, nullptr, nullptr, d_inv_roots, packed_d, q,
-                                          (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack FP64 twiddles");
-        ++launches;
+        px.inv_d = packed_d = reinterpret_cast<hb::TwPair*>(scratch + (3u << 19));
+        px.q = q;
+    }
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, nullptr, nullptr, nullptr, d_inv_roots, d_precon_inv, packed,
+                                 list, (cudaStream_t)stream, px);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: pack twiddles");
+    int launches = 1;
+    hb::ModTab t = make_modtab(q, inv_n, inv_n_w, nullptr, packed, logn, nullptr, packed32);
+    if (packed_d) {
         t.itwd = packed_d;
         t.fp64_ok = 1;
     }
@@ -347,18 +341,19 @@ int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint6
     hb::TwPair* pi = reinterpret_cast<hb::TwPair*>(scratch + (1u << 19));
     uint32_t* list = reinterpret_cast<uint32_t*>(scratch + (2u << 20));
     uint64_t* tb = reinterpret_cast<uint64_t*>(scratch + tb_off);
-    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, pf, d_inv_roots, d_precon_inv, pi, list, st);
+    hb::PackExtra px;
+    if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
+        px.fwd_d = reinterpret_cast<hb::TwPair*>(scratch + (1u << 20));
+        px.inv_d = reinterpret_cast<hb::TwPair*>(scratch + (3u << 19));
+        px.q = q;
+    }
+    e = hb::launch_pack_twiddles((uint32_t)logn, variant, d_roots, d_precon, pf, d_inv_roots, d_precon_inv, pi, list, st, px);
     if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: pack twiddles");
     hb::ModTab t = make_modtab(q, inv_n, inv_n_w, pf, pi, logn, nullptr, nullptr);
     int launches = 1;
-    if (g_fp64_path.load() && hb::fp64_modulus_ok(q)) {
-        hb::TwPair* pfd = reinterpret_cast<hb::TwPair*>(scratch + (1u << 20));
-        hb::TwPair* pid = reinterpret_cast<hb::TwPair*>(scratch + (3u << 19));
-        e = hb::launch_pack_twiddles_fp64((uint32_t)logn, variant, d_roots, pfd, d_inv_roots, pid, q, st);
-        if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: pack FP64 twiddles");
-        ++launches;
-        t.ftwd = pfd;
-        t.itwd = pid;
+    if (px.fwd_d) {
+        t.ftwd = px.fwd_d;
+        t.itwd = px.inv_d;
         t.fp64_ok = 1;
     }
     for (uint64_t off = 0; off < batch; off += chunk) {

@@ -36,9 +36,19 @@ size_t packed_fwd_entries(uint32_t logn, int variant);
 size_t packed_inv_entries(uint32_t logn, int variant);
 // interleave caller tables (roots/precon and/or inv_roots/precon_inv, n words
 // each, device pointers) into the packed per-group layout of ntt_core.cuh
+// optional extra outputs of the same launch: the small-modulus (uint32) tables (n = 16384, 32 words per
+// thread only) and the FP64-pipe tables {centred root, root / q} of modulus q
+struct PackExtra {
+    Tw32* fwd32 = nullptr;
+    Tw32* inv32 = nullptr;
+    TwPair* fwd_d = nullptr;
+    TwPair* inv_d = nullptr;
+    uint64_t q = 0;
+};
 cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
                                  TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
-                                 TwPair* inv_out, uint32_t* zero_count, cudaStream_t st);
+                                 TwPair* inv_out, uint32_t* zero_count, cudaStream_t st,
+                                 const PackExtra& extra = PackExtra());
 
 // FP64-pipe tables (modarith.cuh): same packed geometry, entries {centred root, root / q} as doubles
 cudaError_t launch_pack_twiddles_fp64(uint32_t logn, int variant, const uint64_t* roots, TwPair* fwd_out,

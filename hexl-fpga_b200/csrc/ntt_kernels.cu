@@ -16,7 +16,7 @@ template <class C>
 __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64_t* __restrict__ precon,
                                 TwPair* __restrict__ fwd_out, const uint64_t* __restrict__ inv_roots,
                                 const uint64_t* __restrict__ precon_inv, TwPair* __restrict__ inv_out,
-                                uint32_t* __restrict__ zero_count) {
+                                uint32_t* __restrict__ zero_count, const PackExtra x) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (zero_count && e == 0) *zero_count = 0;   // reset the deferred list of the call that follows
     if (fwd_out && e < (uint32_t)C::FWD_ENTRIES) {
@@ -30,6 +30,30 @@ __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64
         TwPair t = {0, 0};
         if (s >= 0) t = TwPair{inv_roots[s], precon_inv[s]};
         inv_out[e] = t;
+    }
+    // the same call's tables in the other two formats (one launch instead of two or three)
+    auto entry_d = [&](uint64_t r) {
+        const double ws = fp_centred(r < x.q ? r : r % x.q, x.q);
+        return TwPair{d2u(ws), d2u(fp_quot(ws, x.q))};
+    };
+    if (x.fwd_d && e < (uint32_t)C::FWD_ENTRIES) {
+        const int s = fwd_pack_src<C>(e);
+        x.fwd_d[e] = s >= 0 ? entry_d(roots[s]) : TwPair{0, 0};
+    }
+    if (x.inv_d && e < (uint32_t)C::INV_ENTRIES) {
+        const int s = inv_pack_src<C>(e);
+        x.inv_d[e] = s >= 0 ? entry_d(inv_roots[s]) : TwPair{0, 0};
+    }
+    if constexpr (C::LOGN == 14 && C::LOGE == 5) {
+        using C32 = NttCfg<14, 5, 5>;
+        if (x.fwd32 && e < (uint32_t)C32::FWD_ENTRIES) {
+            const int s = fwd_pack_src<C32>(e);
+            x.fwd32[e] = s >= 0 ? Tw32{(uint32_t)roots[s], (uint32_t)(precon[s] >> 32)} : Tw32{0, 0};
+        }
+        if (x.inv32 && e < (uint32_t)C32::INV_ENTRIES) {
+            const int s = inv_pack_src<C32>(e);
+            x.inv32[e] = s >= 0 ? Tw32{(uint32_t)inv_roots[s], (uint32_t)(precon_inv[s] >> 32)} : Tw32{0, 0};
+        }
     }
 }
 
@@ -147,18 +171,25 @@ size_t packed_inv_entries(uint32_t logn, int variant) {
 
 template <class C>
 static cudaError_t pack_one(const uint64_t* roots, const uint64_t* precon, TwPair* fwd_out, const uint64_t* inv_roots,
-                            const uint64_t* precon_inv, TwPair* inv_out, uint32_t* zero_count, cudaStream_t st) {
-    const int total = C::FWD_ENTRIES > C::INV_ENTRIES ? C::FWD_ENTRIES : C::INV_ENTRIES;
+                            const uint64_t* precon_inv, TwPair* inv_out, uint32_t* zero_count, cudaStream_t st,
+                            const PackExtra& x) {
+    int total = C::FWD_ENTRIES > C::INV_ENTRIES ? C::FWD_ENTRIES : C::INV_ENTRIES;
+    if (x.fwd32 || x.inv32) {
+        using C32 = NttCfg<14, 5, 5>;
+        if (!(C::LOGN == 14 && C::LOGE == 5)) return cudaErrorInvalidValue;
+        const int t32 = C32::FWD_ENTRIES > C32::INV_ENTRIES ? C32::FWD_ENTRIES : C32::INV_ENTRIES;
+        total = t32 > total ? t32 : total;
+    }
     k_pack_twiddles<C><<<(total + 255) / 256, 256, 0, st>>>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out,
-                                                            zero_count);
+                                                            zero_count, x);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
                                  TwPair* fwd_out, const uint64_t* inv_roots, const uint64_t* precon_inv,
-                                 TwPair* inv_out, uint32_t* zero_count, cudaStream_t st) {
+                                 TwPair* inv_out, uint32_t* zero_count, cudaStream_t st, const PackExtra& x) {
     HB_DISPATCH_CFG(logn, variant,
-                    return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, zero_count, st));
+                    return pack_one<C>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out, zero_count, st, x));
     return cudaErrorInvalidValue;
 }
 
