@@ -32,6 +32,7 @@ HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
 // ---- S1 -------------------------------------------------------------------
 template <class C>
 struct JobIntt1 {
+    static constexpr bool kOneModulus = false;
     KsDev ks;
     uint64_t* U;
     HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_co
 // ---- S2 -------------------------------------------------------------------
 template <class C>
 struct JobNtt1 {
+    static constexpr bool kOneModulus = false;
     KsDev ks;
     uint64_t* V;
     HB_D void decode(uint32_t item, uint32_t& b, uint32_t& r, uint32_t& j) const {
@@ -338,6 +340,7 @@ cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st
 // ---- S4 -------------------------------------------------------------------
 template <class C>
 struct JobIntt2 {
+    static constexpr bool kOneModulus = false;
     KsDev ks;
     uint64_t* ACC;
     HB_D uint32_t poly(uint32_t item) const { return item * ks.R + ks.D; }   // [b][c][D]
@@ -421,6 +424,7 @@ struct OfKsFinal {
 };
 template <class C>
 struct JobNtt2 {
+    static constexpr bool kOneModulus = false;
     KsDev ks;
     const uint64_t* ACC;
     uint64_t* result;

@@ -111,6 +111,12 @@ struct SmemPlan {
     static constexpr uint32_t KQ_WORD = BAR_WORD + 2;     // two tables of k*q, k < 64 (iteration parity)
     static constexpr uint32_t CNT_WORD = BAR_WORD + 2 + 128;   // warps done with the buffer (C::WARPTAIL)
     static constexpr size_t BYTES = (size_t)(BAR_WORD + 2 + 128 + 1) * 8;
+    // head-pass twiddles of the FP64 plain kernels (Fp64ArithS), 16-byte entries behind everything else
+    static constexpr uint32_t HEAD_TW_FWD = C::fwd_off(C::NP), HEAD_TW_INV = C::INV_ENTRIES - C::N;
+    static constexpr uint32_t HEAD_TW = HEAD_TW_FWD > HEAD_TW_INV ? HEAD_TW_FWD : HEAD_TW_INV;
+    static constexpr uint32_t TW_WORD = (BAR_WORD + 2 + 128 + 1 + 1) & ~1u;
+    static constexpr size_t BYTES_TW = (size_t)TW_WORD * 8 + (size_t)HEAD_TW * 16;
+    static constexpr bool kHeadTwFits = BYTES_TW <= 227u * 1024u;
 };
 
 // forward output: the 16 contiguous words of one row per thread
@@ -360,11 +366,13 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     }
     if constexpr (MODE == kFastVote) vote_raise<C>(bad);
     const TwPair* ftw = A::kFp64 ? t.ftwd : t.ftw;
+    const TwPair* ftw_head = ftw;            // twiddles of the head passes
+    if constexpr (A::kSmemHead) ftw_head = a.fwd_base();
     if constexpr (A::kFp64) {
 #pragma unroll
         for (int e = 0; e < C::E; ++e) v[e] = a.enter_fwd(v[e]);
     }
-    fwd_head_compute<C, 0>(tid, v, ftw, a, [&](int gi, int k0, int k1) {
+    fwd_head_compute<C, 0>(tid, v, ftw_head, a, [&](int gi, int k0, int k1) {
         head_store_word<C, P0::R, P0::LS>(tid, W, gi, k0, v[gi * (1 << P0::R) + k0]);
         head_store_word<C, P0::R, P0::LS>(tid, W, gi, k1, v[gi * (1 << P0::R) + k1]);
     });
@@ -375,7 +383,7 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
             return false;
         }
     }
-    fwd_mid_passes<C, 1>(tid, W, ftw, a);
+    fwd_mid_passes<C, 1>(tid, W, ftw_head, a);
     tail_load<C>(tid, W, v, XfIdent());
     if constexpr (C::WARPTAIL) {
         pf.template issue_when_all_warps_done<C>();
@@ -413,6 +421,8 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         bad = out_of_range<C::E>(v, A::kFp64 ? t.fd.vote : t.twoq);
     }
     const TwPair* itw = A::kFp64 ? t.itwd : t.itw;
+    const TwPair* itw_head = itw;            // twiddles of the head passes
+    if constexpr (A::kSmemHead) itw_head = a.template inv_base<C>();
     if constexpr (A::kFp64) {
 #pragma unroll
         for (int e = 0; e < C::E; ++e) v[e] = a.enter_inv(v[e]);
@@ -424,7 +434,7 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         // before it, and the range vote rides on the one after it
         static_assert(C::NP >= 2, "WARPTAIL inverse needs a warp-local head pass");
         __syncwarp();
-        inv_head_pass<C, 0>(tid, W, itw, a);
+        inv_head_pass<C, 0>(tid, W, itw_head, a);
         if constexpr (MODE == kFastVote) vote_raise<C>(bad);
         __syncthreads();
         if constexpr (MODE == kFastVote) {
@@ -433,7 +443,7 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
                 return false;
             }
         }
-        inv_mid_passes<C, 1>(tid, W, itw, a);
+        inv_mid_passes<C, 1>(tid, W, itw_head, a);
         head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
         pf.template issue_when_all_warps_done<C>();
     } else {
@@ -445,14 +455,14 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
                 return false;
             }
         }
-        inv_mid_passes<C, 0>(tid, W, itw, a);
+        inv_mid_passes<C, 0>(tid, W, itw_head, a);
         head_load<C, PL::R, PL::LS>(tid, W, v, XfIdent());
         __syncthreads();
         pf.template issue<C>();
     }
     // every pair is stored as soon as its last butterfly has made it final: the stores (32 B/clk
     // per SM at most) drain under the remaining butterflies instead of as one burst at the end
-    inv_head_compute<C, C::NP - 1>(tid, v, itw, a, [&](int gi, int k0, int k1) {
+    inv_head_compute<C, C::NP - 1>(tid, v, itw_head, a, [&](int gi, int k0, int k1) {
         of.word(inv_last_index<C>(tid, gi, k0), v[gi * (1 << PL::R) + k0]);
         of.word(inv_last_index<C>(tid, gi, k1), v[gi * (1 << PL::R) + k1]);
     });
@@ -489,7 +499,22 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         W[SmemPlan<C>::CNT_WORD] = 0;
         fence_barrier_init();
     }
+    // FP64 kernels of the plain batched calls (one modulus per launch, launched with BYTES_TW of
+    // shared memory): the twiddles of the head passes move next to the buffer once
+    constexpr bool SMEM_HEAD = FP64 && Job::kOneModulus && SmemPlan<C>::kHeadTwFits;
+    if constexpr (SMEM_HEAD) {
+        const ModTab& t0 = job.mod(0);
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(FWD ? t0.ftwd : t0.itwd + C::inv_off(0));
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(W + SmemPlan<C>::TW_WORD);
+        constexpr uint32_t COUNT = FWD ? SmemPlan<C>::HEAD_TW_FWD : SmemPlan<C>::HEAD_TW_INV;
+        for (uint32_t e = tid; e < COUNT; e += C::NT) dst[e] = src[e];
+    }
     __syncthreads();
+    uint32_t head_s = 0;
+    if constexpr (SMEM_HEAD) {
+        // volatile: the address (and with it every load of these twiddles) stays behind the barrier above
+        asm volatile("mov.u32 %0, %1;" : "=r"(head_s) : "r"(smem_u32(W + SmemPlan<C>::TW_WORD)));
+    }
     uint32_t i = blockIdx.x;
     if (tid == 0 && i < n_items) issue_poly_load<C>(W, tmap, bar, job.src_row(item_of(i)));
     uint32_t parity = 0;
@@ -504,7 +529,13 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         parity ^= 1;
         const ModTab& t = job.mod(item);
         bool done;
-        if constexpr (FP64) {
+        if constexpr (SMEM_HEAD) {
+            Fp64ArithS a;
+            a.m = t.fd;
+            a.head_s = head_s;
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (FP64) {
             const Fp64Arith a = {t.fd};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
@@ -1144,6 +1175,11 @@ HB_D void ntt_persistent_small3(const CUtensorMap* tmap, uint64_t* data, const M
     }
 }
 
+// shared memory of the FP64 kernels of the plain batched calls (head-pass twiddles included when they fit)
+template <class C>
+constexpr size_t ntt_smem_bytes_fp64_plain() {
+    return SmemPlan<C>::kHeadTwFits ? SmemPlan<C>::BYTES_TW : SmemPlan<C>::BYTES;
+}
 template <class C>
 constexpr size_t ntt_smem_bytes() {
     return SmemPlan<C>::BYTES;

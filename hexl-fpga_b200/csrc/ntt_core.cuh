@@ -202,6 +202,8 @@ struct ExactArith {
     using elem = uint64_t;
     using Tw = TwPair;
     static constexpr bool kFp64 = false;
+    static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     uint64_t q, twoq;
     InvScale sc;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
@@ -225,6 +227,8 @@ struct FastArith {
     using elem = uint64_t;
     using Tw = TwPair;
     static constexpr bool kFp64 = false;
+    static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     FastMod m;
     InvScale sc;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
@@ -254,6 +258,8 @@ struct Fp64Arith {
     using elem = uint64_t;
     using Tw = TwPair;
     static constexpr bool kFp64 = true;
+    static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     static constexpr bool kLazyInv = false;
     Fp64Mod m;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
@@ -267,12 +273,41 @@ struct Fp64Arith {
     template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last_bfly_fp64(X, Y, m); }
 };
 
+// Fp64Arith with the twiddles of the head passes in shared memory (plain batched calls: a persistent
+// CTA keeps one modulus, so its ~17 KiB of head-pass twiddles are copied next to the polynomial
+// buffer once per launch).  A broadcast LDS.128 costs 2.9 cycles of the scheduler where an L1 hit
+// costs 4.6-6.5 (tools/ubench4.cu).  The head-pass functions receive a "pointer" whose numeric value
+// is the 32-bit shared-space address of the entry (fwd_base / inv_base below), so the index math
+// of ntt_core.cuh applies unchanged; the tail twiddles stay in global memory.
+struct Fp64ArithS : Fp64Arith {
+    static constexpr bool kSmemHead = true;
+    uint32_t head_s;   // shared-space byte address of head entry 0
+    HB_HD const TwPair* fwd_base() const { return reinterpret_cast<const TwPair*>((uintptr_t)head_s); }
+    template <class C>
+    HB_HD const TwPair* inv_base() const {   // inverse tables start with the N tail entries
+        return reinterpret_cast<const TwPair*>((uintptr_t)head_s - (uintptr_t)C::inv_off(0) * sizeof(TwPair));
+    }
+    HB_HD Tw ld_head(const Tw* p) const {
+#if defined(__CUDA_ARCH__)
+        TwPair t;
+        // volatile: a pure load of a loop-invariant address would be hoisted out of the persistent
+        // loop over the polynomials (all 62 of them, 248 registers)
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(t.w), "=l"(t.wp) : "r"((uint32_t)(uintptr_t)p));
+        return t;
+#else
+        return *p;
+#endif
+    }
+};
+
 // inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
 // E = log2 of the bound (in units of q) of the words entering the stage
 struct LazyInvArith {
     using elem = uint64_t;
     using Tw = TwPair;
     static constexpr bool kFp64 = false;
+    static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     FastMod m;
     InvScale sc;
     static constexpr bool kLazyInv = true;
@@ -343,6 +378,8 @@ HB_HD uint32_t mul_lazy32(uint32_t y, uint32_t w, uint32_t wp, uint32_t nq) {
 struct SmallArith {
     using elem = uint32_t;
     using Tw = Tw32;
+    static constexpr bool kSmemHead = false;
+    HB_HD Tw ld_head(const Tw* p) const { return ld(p); }
     Small32 m;
     HB_HD Tw ld(const Tw* p) const {
 #if defined(__CUDA_ARCH__)
@@ -426,7 +463,7 @@ HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a, c
         constexpr int half = 1 << (R - 1 - d);
         static_for<0, (1 << d)>([&](auto bc) {
             constexpr int blk = decltype(bc)::value;
-            const typename A::Tw t = a.ld(g + ((1 << d) + blk) * TS);
+            const typename A::Tw t = (TS == 1) ? a.ld_head(g + ((1 << d) + blk) * TS) : a.ld(g + ((1 << d) + blk) * TS);
             static_for<0, half>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 a.fwd(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
@@ -454,7 +491,8 @@ HB_HD void inv_group(typename A::elem* v, const typename A::Tw* g, const A& a, c
                     fin(blk * 2 * half + j, blk * 2 * half + j + half);
                 });
             } else {
-                const typename A::Tw t = a.ld(g + ((1 << (R - 1 - d)) + blk) * TS);
+                const typename A::Tw t = (TS == 1) ? a.ld_head(g + ((1 << (R - 1 - d)) + blk) * TS)
+                                                   : a.ld(g + ((1 << (R - 1 - d)) + blk) * TS);
                 static_for<0, half>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     a.template inv_at<E0 + d>(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);

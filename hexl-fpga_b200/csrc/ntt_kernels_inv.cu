@@ -21,8 +21,9 @@ static cudaError_t launch_inv_mul_one(uint64_t* data, const uint64_t* other, con
     job.dv = make_divisor(tab.q);
     if (tab.inv_fast_ok && tab.fp64_ok) {
         auto kern = k_ntt_inv_mul<C, kFastTrust, true>;   // canonical products into the FP64-pipe butterflies
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-        kern<<<persistent_grid((const void*)kern, C::NT, smem, batch), C::NT, smem, st>>>(tmap, job, (uint32_t)batch);
+        const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
+        kern<<<persistent_grid((const void*)kern, C::NT, smemd, batch), C::NT, smemd, st>>>(tmap, job, (uint32_t)batch);
     } else if (tab.inv_fast_ok) {
         auto kern = k_ntt_inv_mul<C, kFastTrust>;   // the products are canonical: no range vote needed
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;

@@ -14,6 +14,7 @@ cudaError_t make_rows32_store_tmap(CUtensorMap* out, const void* base, uint64_t 
 // ---- plain batched transform, in place ------------------------------------
 template <class C>
 struct JobPlain {
+    static constexpr bool kOneModulus = true;   // every item of a launch is transformed under tab
     uint64_t* data;
     ModTab tab;
     HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
@@ -105,7 +106,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
             using CW = typename WarpTailCfg<C>::type;
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
                 auto kern = k_ntt_fwd<CW, MODE, true>;
-                const size_t smemw = ntt_smem_bytes<CW>();
+                const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
                 JobFwd<CW> jobw;
                 jobw.data = base;
@@ -116,9 +117,10 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
             }
             if (tab.fp64_ok) {       // 36..51-bit modulus: butterflies on the FP64 pipe
                 auto kern = k_ntt_fwd<C, MODE, true>;
-                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-                kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, smap, job,
-                                                                                               (uint32_t)cnt, list);
+                const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
+                kern<<<persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st>>>(tmap, smap, job,
+                                                                                                 (uint32_t)cnt, list);
                 return cudaGetLastError();
             }
         }
@@ -134,7 +136,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
             using CW = typename WarpTailCfg<C>::type;
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
                 auto kern = k_ntt_inv<CW, MODE, false, true>;
-                const size_t smemw = ntt_smem_bytes<CW>();
+                const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
                 JobInv<CW> jobw;
                 jobw.data = base;
@@ -145,8 +147,9 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
             }
             if (tab.fp64_ok) {
                 auto kern = k_ntt_inv<C, MODE, false, true>;
-                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-                kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt,
+                const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
+                kern<<<persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st>>>(tmap, job, (uint32_t)cnt,
                                                                                                list);
                 return cudaGetLastError();
             }
