@@ -581,7 +581,12 @@ struct SmallPlan {
     static constexpr uint32_t S_WORD = C32::N;                 // in uint64 words from the base
     static constexpr uint32_t BAR_WORD = C32::N + C32::N / 2;
     static constexpr uint32_t FLAG_WORD = BAR_WORD + 1;
-    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2) * 8;
+    // head-pass twiddles (8-byte entries), copied once per launch (SmallArithS)
+    static constexpr uint32_t HEAD_TW_FWD = C32::fwd_off(C32::NP), HEAD_TW_INV = C32::INV_ENTRIES - C32::N;
+    static constexpr uint32_t HEAD_TW = HEAD_TW_FWD > HEAD_TW_INV ? HEAD_TW_FWD : HEAD_TW_INV;
+    static constexpr uint32_t TW_WORD = BAR_WORD + 2;
+    static constexpr size_t BYTES = (size_t)(TW_WORD + HEAD_TW) * 8;
+    static_assert(BYTES <= 227u * 1024u, "small-modulus shared-memory plan does not fit");
 };
 
 // narrow a landed word to 32 bits while collecting the range vote
@@ -690,17 +695,20 @@ HB_D void store_rows32_tma(uint64_t* slice, const CUtensorMap* smap32, uint32_t 
 // forward, small modulus: base -> dst (bit-reversed order, [0,q)); false = deferred
 template <class C64, class C32, int MODE>
 HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf,
-                            const CUtensorMap* smap32, uint32_t item) {
+                            const CUtensorMap* smap32, uint32_t item, uint32_t head_s) {
     using P0 = FwdPass<C32, 0>;
     const uint32_t tid = threadIdx.x;
     uint32_t* S = reinterpret_cast<uint32_t*>(base + SmallPlan<C32>::S_WORD);
-    const SmallArith a = {t.sm32};
+    SmallArithS a;
+    a.m = t.sm32;
+    a.head_s = head_s;
+    const Tw32* tw_head = a.fwd_base();      // head-pass twiddles: shared memory
     uint32_t v[C32::E];
     uint32_t hi_or = 0, lo_max = 0;
     head_load<C32, P0::R, P0::LS>(tid, base, v, XfNarrowVote{&hi_or, &lo_max});
     if constexpr (MODE == kFastVote)   // forward contract: every word < 4q
         small_vote_raise<C32>((hi_or != 0) | (lo_max >= 2u * t.sm32.twoq), base);
-    fwd_head_compute<C32, 0>(tid, v, t.ftw32, a, [&](int gi, int k0, int k1) {
+    fwd_head_compute<C32, 0>(tid, v, tw_head, a, [&](int gi, int k0, int k1) {
         head_store_word<C32, P0::R, P0::LS>(tid, S, gi, k0, v[gi * (1 << P0::R) + k0]);
         head_store_word<C32, P0::R, P0::LS>(tid, S, gi, k1, v[gi * (1 << P0::R) + k1]);
     });
@@ -709,7 +717,7 @@ HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     if constexpr (MODE == kFastVote) {
         if (small_vote_read<C32>(base)) return false;
     }
-    fwd_mid_passes32<C32, 1>(tid, S, t.ftw32, a);
+    fwd_mid_passes32<C32, 1>(tid, S, tw_head, a);
     tail_load<C32>(tid, S, v, XfSame32());
     __syncthreads();                          // S may be overwritten by the next polynomial's first pass
     // each row leaves as soon as it is final, so its stores drain while the next row is computed
@@ -732,11 +740,15 @@ HB_D bool ntt_fwd_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
 
 // inverse, small modulus: base (bit-reversed order) -> dst (natural order, [0,q))
 template <class C64, class C32, int MODE>
-HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf) {
+HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, const PrefetchSmall& pf,
+                            uint32_t head_s) {
     using PL = InvPass<C32, C32::NP - 1>;
     const uint32_t tid = threadIdx.x;
     uint32_t* S = reinterpret_cast<uint32_t*>(base + SmallPlan<C32>::S_WORD);
-    const SmallArith a = {t.sm32};
+    SmallArithS a;
+    a.m = t.sm32;
+    a.head_s = head_s;
+    const Tw32* tw_head = a.template inv_base<C32>();   // head-pass twiddles: shared memory
     uint32_t v[C32::E];
     uint32_t hi_or = 0, lo_max = 0;
     const XfNarrowVote xf = {&hi_or, &lo_max};
@@ -763,10 +775,10 @@ HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
     if constexpr (MODE == kFastVote) {
         if (small_vote_read<C32>(base)) return false;
     }
-    inv_mid_passes32<C32, 0>(tid, S, t.itw32, a);
+    inv_mid_passes32<C32, 0>(tid, S, tw_head, a);
     head_load<C32, PL::R, PL::LS>(tid, S, v, XfSame32());
     __syncthreads();
-    inv_head_compute<C32, C32::NP - 1>(tid, v, t.itw32, a, [&](int gi, int k0, int k1) {
+    inv_head_compute<C32, C32::NP - 1>(tid, v, tw_head, a, [&](int gi, int k0, int k1) {
         dst[inv_last_index<C32>(tid, gi, k0)] = v[gi * (1 << PL::R) + k0];
         dst[inv_last_index<C32>(tid, gi, k1)] = v[gi * (1 << PL::R) + k1];
     });
@@ -787,7 +799,16 @@ HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const Mo
         base[SmallPlan<C32>::FLAG_WORD] = 0;
         fence_barrier_init();
     }
+    {   // the twiddles of the head passes move next to the buffers once per launch
+        const uint2* src = reinterpret_cast<const uint2*>(FWD ? t.ftw32 : t.itw32 + C32::inv_off(0));
+        uint2* dstw = reinterpret_cast<uint2*>(base + SmallPlan<C32>::TW_WORD);
+        constexpr uint32_t COUNT = FWD ? SmallPlan<C32>::HEAD_TW_FWD : SmallPlan<C32>::HEAD_TW_INV;
+        for (uint32_t e = tid; e < COUNT; e += C32::NT) dstw[e] = src[e];
+    }
     __syncthreads();
+    uint32_t head_s;
+    // volatile: the address (and every load through it) stays behind the barrier above
+    asm volatile("mov.u32 %0, %1;" : "=r"(head_s) : "r"(smem_u32(base + SmallPlan<C32>::TW_WORD)));
     uint32_t item = blockIdx.x;
     if (tid == 0 && item < n_items) issue_poly_load<C64>(base, tmap, bar, item * ROWS);
     uint32_t parity = 0;
@@ -800,8 +821,8 @@ HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const Mo
         parity ^= 1;
         uint64_t* dst = data + (size_t)item * C64::N;
         bool done;
-        if constexpr (FWD) done = ntt_fwd_small_cta<C64, C32, MODE>(base, t, dst, pf, smap32, item);
-        else done = ntt_inv_small_cta<C64, C32, MODE>(base, t, dst, pf);
+        if constexpr (FWD) done = ntt_fwd_small_cta<C64, C32, MODE>(base, t, dst, pf, smap32, item, head_s);
+        else done = ntt_inv_small_cta<C64, C32, MODE>(base, t, dst, pf, head_s);
         if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
         // the next transform's first pass writes S: everyone must have left this one
         // (its last reads of S are followed by a block barrier inside the cta functions)

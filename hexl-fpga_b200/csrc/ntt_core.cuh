@@ -414,6 +414,26 @@ struct SmallArith {
     template <int E> HB_HD void inv_at(uint32_t& X, uint32_t& Y, const Tw32& t) const { inv(X, Y, t); }
     template <int E> HB_HD void inv_last_at(uint32_t& X, uint32_t& Y) const { inv_last(X, Y); }
 };
+// SmallArith with the head-pass twiddles in shared memory (cf. Fp64ArithS: the "pointers" handed to
+// the head-pass functions carry 32-bit shared-space addresses)
+struct SmallArithS : SmallArith {
+    static constexpr bool kSmemHead = true;
+    uint32_t head_s;
+    HB_HD const Tw32* fwd_base() const { return reinterpret_cast<const Tw32*>((uintptr_t)head_s); }
+    template <class C>
+    HB_HD const Tw32* inv_base() const {
+        return reinterpret_cast<const Tw32*>((uintptr_t)head_s - (uintptr_t)C::inv_off(0) * sizeof(Tw32));
+    }
+    HB_HD Tw32 ld_head(const Tw32* p) const {
+#if defined(__CUDA_ARCH__)
+        Tw32 t;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t.w), "=r"(t.wp) : "r"((uint32_t)(uintptr_t)p));
+        return t;
+#else
+        return *p;
+#endif
+    }
+};
 HB_HD bool small_modulus_ok(uint64_t q) { return q < ((uint64_t)1 << 30); }
 HB_HD Small32 make_small32(uint64_t q, const InvScale& sc) {
     Small32 m;
