@@ -166,6 +166,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         hb::g_small_tma_store = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "pdl")) {
+        hb::g_pdl = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "warp_tail")) {
         hb::g_warp_tail = value ? 1 : 0;
         return 0;

@@ -92,6 +92,7 @@ cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op
 extern int g_ks_mac_items;
 extern int g_small_tma_store;
 extern int g_warp_tail;
+extern int g_pdl;
 size_t ks_scratch_words_per_item(const KsDev& ks);
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);
 cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,

@@ -484,6 +484,10 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     static_assert(!FP64 || (!LAZY && (MODE == kFastVote || MODE == kFastTrust)), "FP64 is a fast-path option");
     // The 128-byte TMA swizzle needs the buffer 1024-byte aligned; the dynamic
     // shared window of a kernel without static shared memory starts aligned.
+    // launched with programmatic stream serialization (ntt_launch.cuh): wait for the kernel in front
+    // of us (a no-op otherwise), then let the one behind us be scheduled
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     uint64_t* W = smem_poly<C>();
     uint64_t* bar = W + SmemPlan<C>::BAR_WORD;
     const uint32_t tid = threadIdx.x;
@@ -789,6 +793,8 @@ HB_D bool ntt_inv_small_cta(uint64_t* base, const ModTab& t, uint64_t* dst, cons
 template <class C64, class C32, bool FWD, int MODE>
 HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const ModTab& t, uint32_t n_items,
                                uint32_t* list, const CUtensorMap* smap32) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // see ntt_persistent
+    asm volatile("griddepcontrol.launch_dependents;");
     uint64_t* base = smem_poly<C64>();
     uint64_t* bar = base + SmallPlan<C32>::BAR_WORD;
     const uint32_t tid = threadIdx.x;

@@ -93,11 +93,35 @@ struct WarpTailCfg<NttCfg<14, 5, 4, 0>> {
     using type = NttCfg<14, 5, 4, 1>;
 };
 
+// Launch with programmatic stream serialization (option "pdl"): the grid may be scheduled while the
+// kernel in front of it in the stream (this call's pack kernel, or the main kernel in front of the
+// deferred-list pass) is still running; its CTAs execute griddepcontrol.wait before they touch
+// anything (ntt_persistent*), so only launch latency and the drain between the kernels overlap.
+template <class... KArgs, class... Args>
+static cudaError_t launch_dep(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    if (!g_pdl) {
+        kern<<<grid, block, smem, st>>>(KArgs(args)...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <class C, bool FWD, int MODE>
 static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap, uint64_t* base, const ModTab& tab,
                                uint64_t cnt, uint32_t* list, cudaStream_t st) {
     const size_t smem = ntt_smem_bytes<C>();
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
     if constexpr (FWD) {
         JobFwd<C> job;
         job.data = base;
@@ -111,23 +135,20 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 JobFwd<CW> jobw;
                 jobw.data = base;
                 jobw.tab = tab;
-                kern<<<persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st>>>(tmap, smap, jobw,
-                                                                                                   (uint32_t)cnt, list);
-                return cudaGetLastError();
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st, tmap, smap, jobw, (uint32_t)cnt, list);
+                return e != cudaSuccess ? e : cudaGetLastError();
             }
             if (tab.fp64_ok) {       // 36..51-bit modulus: butterflies on the FP64 pipe
                 auto kern = k_ntt_fwd<C, MODE, true>;
                 const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
-                kern<<<persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st>>>(tmap, smap, job,
-                                                                                                 (uint32_t)cnt, list);
-                return cudaGetLastError();
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st, tmap, smap, job, (uint32_t)cnt, list);
+                return e != cudaSuccess ? e : cudaGetLastError();
             }
         }
         auto kern = k_ntt_fwd<C, MODE>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-        kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, smap, job, (uint32_t)cnt,
-                                                                                       list);
+        e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st, tmap, smap, job, (uint32_t)cnt, list);
     } else {
         JobInv<C> job;
         job.data = base;
@@ -141,31 +162,28 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 JobInv<CW> jobw;
                 jobw.data = base;
                 jobw.tab = tab;
-                kern<<<persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st>>>(tmap, jobw,
-                                                                                                   (uint32_t)cnt, list);
-                return cudaGetLastError();
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st, tmap, jobw, (uint32_t)cnt, list);
+                return e != cudaSuccess ? e : cudaGetLastError();
             }
             if (tab.fp64_ok) {
                 auto kern = k_ntt_inv<C, MODE, false, true>;
                 const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
-                kern<<<persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st>>>(tmap, job, (uint32_t)cnt,
-                                                                                               list);
-                return cudaGetLastError();
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st, tmap, job, (uint32_t)cnt, list);
+                return e != cudaSuccess ? e : cudaGetLastError();
             }
             if (tab.inv_lazy_ok) {   // q < 2^52: butterflies without per-stage corrections
                 auto kern = k_ntt_inv<C, MODE, true>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-                kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt,
-                                                                                               list);
-                return cudaGetLastError();
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st, tmap, job, (uint32_t)cnt, list);
+                return e != cudaSuccess ? e : cudaGetLastError();
             }
         }
         auto kern = k_ntt_inv<C, MODE>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-        kern<<<persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st>>>(tmap, job, (uint32_t)cnt, list);
+        e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st, tmap, job, (uint32_t)cnt, list);
     }
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // `list`: device scratch of 1 + batch words whose first word is zero on entry
@@ -238,16 +256,14 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
             if (trust) {
                 auto kern = k_ntt_small<C, C32, FWD, kFastTrust>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-                kern<<<persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st>>>(
-                    tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st, tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
                 *launches += 1;
-                return cudaGetLastError();
+                return e != cudaSuccess ? e : cudaGetLastError();
             }
             auto kern = k_ntt_small<C, C32, FWD, kFastVote>;
             if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
-            kern<<<persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st>>>(
-                tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
-            if ((e = cudaGetLastError())) return e;
+            e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st, tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
+            if (e != cudaSuccess || (e = cudaGetLastError())) return e;
             *launches += 2;
             return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
         }

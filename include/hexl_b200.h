@@ -136,6 +136,8 @@ int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, ui
  *   "inv_lazy"         1: correction-free inverse butterflies for q < 2^52 (default 0)
  *   "fp64_path"        1 (default): hexl_b200_ntt_fwd / _inv run their butterflies on the FP64
  *                      pipe when 2^36 <= q <= 2^53 / 3 (bit-identical results); 0: integer kernels
+ *   "pdl"              1 (default): the plain NTT kernels are launched with programmatic stream
+ *                      serialization (launch latency overlaps the kernel in front); 0: plain launches
  *   "warp_tail"        1 (default): the FP64-pipe kernels at n = 16384 deal the tail rows out by warp
  *                      (one block barrier per transform instead of three); 0: by thread index
  *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16)

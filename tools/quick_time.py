@@ -40,6 +40,8 @@ def timeit(fn, reps=10, warm=3):
 
 def main():
     out = []
+    if os.environ.get("QT_PDL"):
+        hb.set_option("pdl", int(os.environ["QT_PDL"]))
     N, B = 16384, 4096
     for q in (2251799814045697, 136314881):
         t = ob.Tables(N, q)
