@@ -71,6 +71,7 @@ struct XfKsConvert {
 struct XfMulGlobal {
     static constexpr bool kPost = true;
     const uint64_t* other;   // NTT(b) of this item, same (bit-reversed) order
+    const uint64_t* next;    // NTT(b) of the item this CTA transforms next (L2 prefetch), or nullptr
     Divisor dv;
     HB_D uint64_t operator()(uint64_t x) const { return x; }
     HB_D uint64_t mul(uint64_t x, uint64_t y) const {
@@ -81,19 +82,7 @@ struct XfMulGlobal {
         return mulmod_preshifted(x << dv.s, y, dv);
     }
     template <class C>
-    HB_D void post(uint32_t tid, uint64_t* v) const {
-        static_assert(C::ROW == 16, "64-bit rows");
-#pragma unroll
-        for (int ri = 0; ri < C::E / 16; ++ri) {
-            const uint64_t* p = other + (size_t)tail_row<C>(tid, ri) * 16;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2*>(p + 2 * c));
-                v[ri * 16 + 2 * c] = mul(v[ri * 16 + 2 * c], y.x);
-                v[ri * 16 + 2 * c + 1] = mul(v[ri * 16 + 2 * c + 1], y.y);
-            }
-        }
-    }
+    HB_D void post(uint32_t tid, uint64_t* v) const;
 };
 
 // ---- output functors ----
@@ -261,6 +250,64 @@ struct Prefetch {
         }
     }
 };
+
+// A thread's row of NTT(b) is 128 contiguous bytes, so reading it directly makes every 16-byte
+// load of a warp touch 32 different lines, each of which is fetched eight times (the lines of 16
+// warps do not survive in the L1 left next to the buffer).  The warp's 32 rows are 4 KiB contiguous:
+// they are loaded with coalesced 512-byte accesses and transposed through the warp's staging slice
+// (which the inverse kernels do not use otherwise), same chunk swizzle as the polynomial buffer.
+template <class C>
+HB_D void XfMulGlobal::post(uint32_t tid, uint64_t* v) const {
+    static_assert(C::ROW == 16, "64-bit rows");
+    if constexpr (SmemPlan<C>::kStagedStore) {
+        const uint32_t lane = tid & 31u;
+        uint64_t* slice = smem_poly<C>() + C::N + (tid >> 5) * 512;
+#pragma unroll
+        for (int ri = 0; ri < C::E / 16; ++ri) {
+            const uint32_t row0 = tail_row<C>(tid, ri) - lane;
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(other + (size_t)row0 * 16);
+            ulonglong2 t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = __ldg(src + i * 32 + lane);
+            // the same rows of the next item towards L2, a whole transform ahead (one line per lane)
+            if (next) asm volatile("prefetch.global.L2 [%0];" ::"l"(next + (size_t)row0 * 16 + lane * 16));
+            __syncwarp();                      // the slice's previous contents have been read
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t j = (uint32_t)i * 32 + lane, r = j >> 3, c = j & 7u;
+                st2(slice + r * 16 + ((c ^ (r & 7u)) << 1), t[i].x, t[i].y);
+            }
+            __syncwarp();
+            // one test for the whole row: with the (rare) unreduced-operand branch inside every product
+            // the 16 products end up in separate basic blocks and run one dependent chain at a time
+            uint64_t y[16];
+            uint32_t top = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                ld2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), y[2 * c], y[2 * c + 1]);
+                top |= (uint32_t)((v[ri * 16 + 2 * c] | y[2 * c] | v[ri * 16 + 2 * c + 1] | y[2 * c + 1]) >> 32);
+            }
+            if (top < (uint32_t)(dv.q >> 32)) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[ri * 16 + e] = mulmod_preshifted(v[ri * 16 + e] << dv.s, y[e], dv);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[ri * 16 + e] = mul(v[ri * 16 + e], y[e]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ri = 0; ri < C::E / 16; ++ri) {
+            const uint64_t* p = other + (size_t)tail_row<C>(tid, ri) * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const ulonglong2 y = __ldg(reinterpret_cast<const ulonglong2*>(p + 2 * c));
+                v[ri * 16 + 2 * c] = mul(v[ri * 16 + 2 * c], y.x);
+                v[ri * 16 + 2 * c + 1] = mul(v[ri * 16 + 2 * c + 1], y.y);
+            }
+        }
+    }
+}
 
 template <class C>
 HB_D void OfRows::store(uint32_t row, const uint64_t* v) const {

@@ -19,6 +19,7 @@ static cudaError_t launch_inv_mul_one(uint64_t* data, const uint64_t* other, con
     job.tab = tab;
     job.other = other;
     job.dv = make_divisor(tab.q);
+    job.n_items = (uint32_t)batch;
     if (tab.inv_fast_ok && tab.fp64_ok) {
         auto kern = k_ntt_inv_mul<C, kFastTrust, true>;   // canonical products into the FP64-pipe butterflies
         const size_t smemd = ntt_smem_bytes_fp64_plain<C>();

@@ -49,7 +49,11 @@ template <class C>
 struct JobInvMul : JobPlain<C> {
     const uint64_t* other;
     Divisor dv;
-    HB_D XfMulGlobal xf(uint32_t item) const { return XfMulGlobal{other + (size_t)item * C::N, dv}; }
+    uint32_t n_items;
+    HB_D XfMulGlobal xf(uint32_t item) const {
+        const uint32_t nxt = item + gridDim.x;      // the persistent loop's stride
+        return XfMulGlobal{other + (size_t)item * C::N, nxt < n_items ? other + (size_t)nxt * C::N : nullptr, dv};
+    }
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
 };
 template <class C, int MODE, bool FP64 = false>
