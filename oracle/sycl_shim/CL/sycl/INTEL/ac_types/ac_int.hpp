@@ -1,0 +1,2 @@
+#pragma once
+#include "../../../../ac_int_shim.hpp"
