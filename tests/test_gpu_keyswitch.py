@@ -52,6 +52,18 @@ def test_device_api_vs_oracle(hb, n, D, K, batch, bits, fp64):
     plan.close()
 
 
+@pytest.mark.parametrize("n,D,K", [(16384, 7, 8), (16384, 6, 7), (8192, 5, 7)])
+def test_device_api_vs_second_restatement(hb, n, D, K):
+    """The independently structured CPU restatement (ho_keyswitch_alt, hexl order with lazy 128-bit
+    accumulation) at the headline shapes."""
+    p = KsProblem(n, D, K, 2, 51, seed=4242)
+    plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+    res = gpu(p.result)
+    plan.keyswitch(res, gpu(p.t_target), 2)
+    assert np.array_equal(res.cpu().numpy().view(np.uint64), p.expected(alt=True))
+    plan.close()
+
+
 def test_out_of_range_target_words_go_to_the_exact_kernel(hb):
     """t_target words in [1.25 q, 2q) are outside the FP64 arithmetic's contract but inside the
     integer kernels': the first stage's range vote must send those digits to the exact kernel, so

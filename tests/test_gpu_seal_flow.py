@@ -23,10 +23,12 @@ pytestmark = pytest.mark.gpu
 
 def pmul(a, b, q):
     """pointwise product mod q of uint64 vectors (q < 2^61) via Python ints"""
-    return np.array([(int(x) * int(y)) % q for x, y in zip(a, b)], dtype=np.uint64)
+    return np.array((a.astype(object) * b.astype(object)) % q, dtype=np.uint64)
 
 
-@pytest.mark.parametrize("n,D,K,bits", [(2048, 3, 4, 40), (4096, 2, 4, 50)])
+# the last two: the reference's largest shape 6/7/7/2 and BASELINE's decomp 7 / key 8 at N = 16384 -- an
+# algebraic check at the headline size that does not route through the oracle's keyswitch formula
+@pytest.mark.parametrize("n,D,K,bits", [(2048, 3, 4, 40), (4096, 2, 4, 50), (16384, 6, 7, 51), (16384, 7, 8, 51)])
 def test_relinearize_like_seal(acquired, n, D, K, bits):
     hb = acquired
     rng = np.random.default_rng(7 * n + D)
@@ -59,7 +61,7 @@ def test_relinearize_like_seal(acquired, n, D, K, bits):
     msf[K - 1] = 0
     mod_arr = np.array(moduli, dtype=np.uint64)
     # a batch of size-3 "ciphertexts" (uniform limbs; the identity holds for any c)
-    B = 3
+    B = 3 if n < 16384 else 2
     key_arr = hb.KeyArray(keys)
     cts = []
     hb.set_worksize_KeySwitch(B)
