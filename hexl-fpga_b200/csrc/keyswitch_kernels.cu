@@ -173,6 +173,17 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
             a1[it][0] += mul_shoup_approx(x0[it], w0.w, w0.wp, fm.nq);
             a1[it][1] += mul_shoup_approx(x1[it], w1.w, w1.wp, fm.nq);
         }
+        // every term is below 4q and reduce_small_multiple takes sums below 64q: with more than 15 digits
+        // (the reference stops at 6, plan_create admits up to 63) the sums are folded every 15 terms
+        if ((j & 15u) == 14u) {
+#pragma unroll
+            for (int it = 0; it < kMacItems; ++it) {
+                a0[it][0] = reduce_small_multiple(a0[it][0], fm);
+                a0[it][1] = reduce_small_multiple(a0[it][1], fm);
+                a1[it][0] = reduce_small_multiple(a1[it][0], fm);
+                a1[it][1] = reduce_small_multiple(a1[it][1], fm);
+            }
+        }
     }
 #pragma unroll
     for (int it = 0; it < kMacItems; ++it) {

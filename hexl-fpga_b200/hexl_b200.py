@@ -63,6 +63,7 @@ _SIGNATURES = {
     "hexl_b200_host_dyadic_multiply_many": ([vp, vp, vp, u64, u64, vp, u64], C.c_int),
     "hexl_b200_host_keyswitch_many": ([vp, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, vp], C.c_int),
     "hexl_b200_get_stats": ([vp], C.c_int),
+    "hexl_b200_host_device_stats": ([C.c_int, vp], C.c_int),
     "hexl_b200_reset_stats": ([], C.c_int),
 }
 
@@ -119,6 +120,17 @@ def get_stats():
     s = Stats()
     _check(lib().hexl_b200_get_stats(C.byref(s)), "get_stats")
     return {"kernel_launches": s.kernel_launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}
+
+
+class DeviceStats(C.Structure):
+    _fields_ = [("device", C.c_int32), ("batches", C.c_uint64), ("items", C.c_uint64)]
+
+
+def device_stats(worker):
+    """work done by worker `worker` (0 .. NUM_DEV-1) of the host-pointer runtime since acquire"""
+    st = DeviceStats()
+    _check(lib().hexl_b200_host_device_stats(worker, C.addressof(st)), "device_stats")
+    return {"device": st.device, "batches": st.batches, "items": st.items}
 
 
 def reset_stats():

@@ -22,6 +22,7 @@ bool is_primitive_root(uint64_t r, uint64_t degree, uint64_t q);
 // two dividing q-1); 0 if none.  Same value as the reference's
 // MinimalPrimitiveRoot (number_theory_util.cpp:95-116) whatever generator is
 // found first.
+bool is_prime(uint64_t q);
 uint64_t min_primitive_root(uint64_t degree, uint64_t q);
 
 struct Tables {

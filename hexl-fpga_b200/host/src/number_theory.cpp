@@ -34,11 +34,37 @@ bool is_primitive_root(uint64_t r, uint64_t degree, uint64_t q) {
     return r && pow_mod(r, degree / 2, q) == q - 1;
 }
 
+// deterministic Miller-Rabin for 64-bit integers (the first twelve primes as bases)
+bool is_prime(uint64_t q) {
+    if (q < 2) return false;
+    for (uint64_t p : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        if (q == p) return true;
+        if (q % p == 0) return false;
+    }
+    uint64_t d = q - 1;
+    int s = 0;
+    while (!(d & 1)) d >>= 1, ++s;
+    for (uint64_t a : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+        uint64_t x = pow_mod(a, d, q);
+        if (x == 1 || x == q - 1) continue;
+        bool composite = true;
+        for (int i = 1; i < s && composite; ++i) {
+            x = mul_mod(x, x, q);
+            if (x == q - 1) composite = false;
+        }
+        if (composite) return false;
+    }
+    return true;
+}
+
 uint64_t min_primitive_root(uint64_t degree, uint64_t q) {
     if (degree < 2 || (q - 1) % degree) return 0;
+    // Z_q^* is cyclic only for a prime q: a composite modulus has no use here, and the search below
+    // would not terminate in any reasonable time (half of all candidates work when q is prime)
+    if (!is_prime(q)) return 0;
     const uint64_t cofactor = (q - 1) / degree;
     uint64_t g = 0;
-    for (uint64_t c = 2; c < q && !g; ++c) {
+    for (uint64_t c = 2; c < q && c < 4096 && !g; ++c) {
         uint64_t r = pow_mod(c, cofactor, q);
         if (is_primitive_root(r, degree, q)) g = r;
     }

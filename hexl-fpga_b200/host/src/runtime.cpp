@@ -13,10 +13,21 @@
 // reference's "fence" rule, fpga_int.cpp:339-354,429-448) and streams them
 // through a ring of device slots on three CUDA streams, so the H2D copy of
 // chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap.
-// Batching is by what is queued, not by a compile-time BATCH_SIZE.
+// Batching is by what is queued, not by a compile-time BATCH_SIZE; with several
+// workers (NUM_DEV > 1) a run is dealt out in equal shares.
+//
+// Caller memory: pinned (cudaHostAlloc / cudaHostRegister) buffers are the
+// source / target of the DMA directly.  PAGEABLE buffers -- what every caller of
+// the reference passes (std::vector, benchmark/bench_fwd_ntt.cpp:19-21) -- go
+// through a ring of pinned staging buffers, filled and drained by a small pool
+// of copy threads (the reference stages every batch the same way,
+// FPGAObject_*::fill_in_data, fpga.cpp:329-413), so that the three-stream
+// overlap survives: a cudaMemcpyAsync straight from pageable memory is staged
+// synchronously by the driver and serialises everything.
 //
 // There is no CPU compute path here: without a CUDA device acquire() fails.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
 #include <atomic>
@@ -26,10 +37,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
+#include <list>
 #include <map>
 #include <memory>
-#include <string>
 #include <mutex>
+#include <set>
+#include <string>
 #include <thread>
 #include <tuple>
 #include <vector>
@@ -62,6 +76,13 @@ struct Request {
     const uint64_t** keys = nullptr;
     const uint64_t* msf = nullptr;
     const uint64_t* twiddles = nullptr;
+    size_t out_words() const {
+        switch (op) {
+            case OP_DYADIC: return 3 * n_moduli * n;
+            case OP_KEYSWITCH: return 2 * D * n;
+            default: return n;
+        }
+    }
 };
 
 // two requests may share one device batch
@@ -74,8 +95,13 @@ bool compatible(const Request& a, const Request& b) {
                    a.inv_n_w == b.inv_n_w;
         case OP_DYADIC: return a.n_moduli == b.n_moduli;
         case OP_KEYSWITCH:
+            // the reference fences on shape and on the key-set POINTER (fpga_int.cpp:429-448) and rebuilds
+            // the modulus metadata from the current contents; the small arrays are compared by VALUE here,
+            // so per-call copies of the same moduli / factors (SEAL-style callers) still share a batch
             return a.D == b.D && a.K == b.K && a.R == b.R && a.C == b.C && a.keys == b.keys &&
-                   a.moduli == b.moduli && a.msf == b.msf && a.twiddles == b.twiddles;
+                   a.twiddles == b.twiddles &&
+                   (a.moduli == b.moduli || !memcmp(a.moduli, b.moduli, a.K * 8)) &&
+                   (a.msf == b.msf || !memcmp(a.msf, b.msf, a.K * 8));
         default: return false;
     }
 }
@@ -95,26 +121,150 @@ uint64_t env_u64(const char* name, uint64_t dflt) {
     } while (0)
 
 // ---------------------------------------------------------------------------
+// copy threads: caller memory <-> pinned staging
+// ---------------------------------------------------------------------------
+struct CopyJob {
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
+
+class CopyPool {
+public:
+    explicit CopyPool(unsigned threads) {
+        for (unsigned i = 0; i < threads; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // copies every job (split into pieces) and returns when all of them are done
+    void run(const std::vector<CopyJob>& jobs) {
+        constexpr size_t kPiece = (size_t)2 << 20;
+        Group g;
+        size_t pieces = 0;
+        for (const CopyJob& j : jobs) pieces += (j.bytes + kPiece - 1) / kPiece;
+        if (pieces == 0) return;
+        if (workers_.empty() || pieces == 1) {
+            for (const CopyJob& j : jobs) memcpy(j.dst, j.src, j.bytes);
+            return;
+        }
+        g.remaining = pieces;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (const CopyJob& j : jobs)
+                for (size_t off = 0; off < j.bytes; off += kPiece)
+                    q_.push_back(Piece{(char*)j.dst + off, (const char*)j.src + off, std::min(kPiece, j.bytes - off), &g});
+        }
+        cv_.notify_all();
+        help(&g);     // the submitting thread copies too
+        std::unique_lock<std::mutex> lk(g.mu);
+        g.cv.wait(lk, [&] { return g.remaining == 0; });
+    }
+
+private:
+    struct Group {
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t remaining = 0;
+    };
+    struct Piece {
+        char* dst;
+        const char* src;
+        size_t bytes;
+        Group* g;
+    };
+    void finish(const Piece& p) {
+        memcpy(p.dst, p.src, p.bytes);
+        std::lock_guard<std::mutex> lk(p.g->mu);
+        if (--p.g->remaining == 0) p.g->cv.notify_all();
+    }
+    void help(Group* g) {
+        for (;;) {
+            Piece p;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                auto it = std::find_if(q_.begin(), q_.end(), [&](const Piece& x) { return x.g == g; });
+                if (it == q_.end()) return;
+                p = *it;
+                q_.erase(it);
+            }
+            finish(p);
+        }
+    }
+    void loop() {
+        for (;;) {
+            Piece p;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                p = q_.front();
+                q_.pop_front();
+            }
+            finish(p);
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Piece> q_;
+    bool stop_ = false;
+    std::vector<std::thread> workers_;
+};
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------------------
 // per-GPU worker
 // ---------------------------------------------------------------------------
+// Keys are cached on the device per key-set identity: the k_switch_keys pointer plus the shape, as in the
+// reference (keys_map_, fpga.cpp:1158-1165).  Everything else a plan depends on is compared BY VALUE on
+// every hit -- moduli, modswitch factors, the per-digit key pointers and a hash of a caller-supplied twiddle
+// table -- so a reused address with new contents rebuilds the plan instead of computing with stale
+// constants (the reference's load-once twiddles, fpga.cpp:1251-1255, have exactly that bug).
 struct PlanKey {
     const uint64_t** keys;
-    const uint64_t* moduli;
-    const uint64_t* msf;
-    const uint64_t* twiddles;
     uint64_t n, D, K, R;
     bool operator<(const PlanKey& o) const {
-        return std::tie(keys, moduli, msf, twiddles, n, D, K, R) <
-               std::tie(o.keys, o.moduli, o.msf, o.twiddles, o.n, o.D, o.K, o.R);
+        return std::tie(keys, n, D, K, R) < std::tie(o.keys, o.n, o.D, o.K, o.R);
     }
 };
 struct CachedPlan {
     hexl_b200_ks_plan* plan = nullptr;
-    std::vector<uint64_t> moduli_copy;  // value check: pointer reuse with new moduli => rebuild
+    std::vector<uint64_t> moduli, msf;
     std::vector<const uint64_t*> key_ptrs;
+    bool has_twiddles = false;
+    uint64_t twiddle_hash = 0;
+    uint64_t last_used = 0;
 };
 
+uint64_t hash_words(const uint64_t* p, size_t n) {
+    uint64_t h[4] = {0x9E3779B97F4A7C15ull, 0xBF58476D1CE4E5B9ull, 0x94D049BB133111EBull, 0x2545F4914F6CDD1Dull};
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4)
+        for (int l = 0; l < 4; ++l) h[l] = (h[l] ^ p[i + l]) * 0x100000001B3ull + (h[l] >> 29);
+    for (; i < n; ++i) h[0] = (h[0] ^ p[i]) * 0x100000001B3ull + (h[0] >> 29);
+    return h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7);
+}
+
 constexpr int kSlots = 3;
+
+struct Seg {            // one contiguous piece of caller memory and its place in the device slot
+    uint64_t* host;
+    size_t dev_off;     // words from the slot base
+    size_t words;
+};
 
 struct DeviceCtx {
     int dev = 0;
@@ -124,15 +274,47 @@ struct DeviceCtx {
     size_t slot_words = 0;
     uint64_t* d_small = nullptr;      // twiddles (2 * 16384 words) or per-item moduli
     size_t small_words = 0;
-    std::map<PlanKey, CachedPlan> plans;   // keys cached per key-set identity
-                                           // (reference: keys_map_, fpga.cpp:1158-1165)
-    int init(int device, size_t slot_bytes);
+    std::map<PlanKey, CachedPlan> plans;
+    size_t max_plans = 8;
+    uint64_t plan_clock = 0;
+    // pinned staging for pageable callers (allocated on first use)
+    uint64_t* h_in[kSlots]{};
+    uint64_t* h_out[kSlots]{};
+    bool h_in_used[kSlots]{};         // an H2D out of h_in[s] has been queued (ev_h2d[s] guards its reuse)
+    CopyPool* pool = nullptr;
+    // drain thread: waits for the D2H of a slot, then copies pinned -> caller memory
+    struct DrainItem {
+        int slot;
+        std::vector<Seg> segs;
+        size_t base_off;
+    };
+    std::thread drain_thread;
+    std::mutex dmu;
+    std::condition_variable dcv;
+    std::deque<DrainItem> dq;
+    bool out_busy[kSlots]{};
+    bool drain_stop = false;
+    int drain_error = 0;
+    // statistics
+    std::atomic<uint64_t> batches{0}, items{0};
+
+    int init(int device, size_t slot_bytes, CopyPool* p, size_t plan_cap);
     void destroy();
     int ensure_small(size_t words);
+    int ensure_staging();
+    void drain_main();
+    int wait_drained();
+    void sync_streams() {
+        cudaStreamSynchronize(s_h2d);
+        cudaStreamSynchronize(s_comp);
+        cudaStreamSynchronize(s_d2h);
+    }
 };
 
-int DeviceCtx::init(int device, size_t slot_bytes) {
+int DeviceCtx::init(int device, size_t slot_bytes, CopyPool* p, size_t plan_cap) {
     dev = device;
+    pool = p;
+    max_plans = plan_cap ? plan_cap : 1;
     CU_TRY(cudaSetDevice(dev));
     CU_TRY(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
@@ -158,13 +340,68 @@ int DeviceCtx::ensure_small(size_t words) {
     small_words = words;
     return 0;
 }
+int DeviceCtx::ensure_staging() {
+    if (h_in[0]) return 0;
+    for (int i = 0; i < kSlots; ++i) {
+        CU_TRY(cudaHostAlloc(&h_in[i], slot_words * 8, cudaHostAllocDefault));
+        CU_TRY(cudaHostAlloc(&h_out[i], slot_words * 8, cudaHostAllocDefault));
+    }
+    drain_thread = std::thread([this] { drain_main(); });
+    return 0;
+}
+void DeviceCtx::drain_main() {
+    cudaSetDevice(dev);
+    for (;;) {
+        DrainItem it;
+        {
+            std::unique_lock<std::mutex> lk(dmu);
+            dcv.wait(lk, [&] { return drain_stop || !dq.empty(); });
+            if (dq.empty()) return;
+            it = std::move(dq.front());
+        }
+        cudaError_t e = cudaEventSynchronize(ev_free[it.slot]);   // the D2H into h_out[slot] has landed
+        if (e == cudaSuccess) {
+            std::vector<CopyJob> jobs;
+            jobs.reserve(it.segs.size());
+            for (const Seg& s : it.segs) jobs.push_back({s.host, h_out[it.slot] + (s.dev_off - it.base_off), s.words * 8});
+            pool->run(jobs);
+        }
+        {
+            std::lock_guard<std::mutex> lk(dmu);
+            if (e != cudaSuccess && !drain_error) drain_error = (int)e;
+            dq.pop_front();
+            out_busy[it.slot] = false;
+        }
+        dcv.notify_all();
+    }
+}
+int DeviceCtx::wait_drained() {
+    std::unique_lock<std::mutex> lk(dmu);
+    dcv.wait(lk, [&] { return dq.empty(); });
+    if (drain_error) {
+        const int e = drain_error;
+        drain_error = 0;
+        return cuda_fail((cudaError_t)e, "device-to-host staging");
+    }
+    return 0;
+}
 void DeviceCtx::destroy() {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
+    if (drain_thread.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(dmu);
+            drain_stop = true;
+        }
+        dcv.notify_all();
+        drain_thread.join();
+    }
     for (auto& kv : plans) hexl_b200_ks_plan_destroy(kv.second.plan);
     plans.clear();
     for (int i = 0; i < kSlots; ++i) {
         if (slot[i]) cudaFree(slot[i]);
+        if (h_in[i]) cudaFreeHost(h_in[i]);
+        if (h_out[i]) cudaFreeHost(h_out[i]);
         if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
         if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
         if (ev_free[i]) cudaEventDestroy(ev_free[i]);
@@ -188,12 +425,14 @@ struct Runtime {
     uint64_t expected[OP_COUNT]{};      // calls still promised by set_worksize
     uint64_t worksize[OP_COUNT] = {1, 1, 1, 1};
     size_t capacity = 4096;             // FPGA_BUFSIZE
-    uint64_t batch_cap[OP_COUNT]{};     // BATCH_SIZE_* (0 = as much as fits a slot ring)
+    uint64_t batch_cap[OP_COUNT]{};     // BATCH_SIZE_* (0 = a fair share of what is queued / promised)
     bool stop = false;
-    int error = 0;                      // first asynchronous failure
-    std::string error_msg;
+    size_t idle_workers = 0;            // workers currently gathering (not executing a batch)
+    int error[OP_COUNT]{};              // first asynchronous failure per operation, reported once
+    std::string error_msg[OP_COUNT];
     std::vector<std::thread> workers;
     std::vector<std::unique_ptr<DeviceCtx>> ctxs;
+    std::unique_ptr<CopyPool> pool;
     int debug = 0;
 };
 Runtime* g_rt = nullptr;
@@ -201,29 +440,93 @@ std::mutex g_life;   // acquire / release
 
 // ---- batch execution -------------------------------------------------------
 
-// copy helper: one cudaMemcpyAsync per maximal run of items that are adjacent
-// both on the host and in the device slot (the reference assumes the whole
-// batch is contiguous, fpga.cpp:385-388,405-406; we only exploit it).
-template <class HostPtr>
-int copy_runs(cudaStream_t st, bool to_device, uint64_t* dbase, size_t d_stride_words,
-              size_t words, size_t count, HostPtr host_of) {
-    size_t i = 0;
-    while (i < count) {
-        size_t j = i + 1;
-        const uint64_t* h0 = host_of(i);
-        while (j < count && d_stride_words == words && host_of(j) == h0 + (j - i) * words) ++j;
-        const size_t bytes = ((j - i - 1) * d_stride_words + words) * 8;
-        uint64_t* d = dbase + i * d_stride_words;
-        if (to_device) {
-            CU_TRY(cudaMemcpyAsync(d, h0, bytes, cudaMemcpyHostToDevice, st));
-            g_h2d += bytes;
-        } else {
-            CU_TRY(cudaMemcpyAsync(const_cast<uint64_t*>(h0), d, bytes, cudaMemcpyDeviceToHost, st));
-            g_d2h += bytes;
+// One chunk of a batch: host pieces to upload, kernels, host pieces to download.  `in` and `out` are
+// sorted by dev_off and each covers one dense region of the slot, so the staged path moves each
+// direction with a single DMA.
+struct ChunkIO {
+    std::vector<Seg> in, out;
+};
+
+// merge pieces that are adjacent both in caller memory and in the slot (the reference assumes the whole
+// batch is contiguous, fpga.cpp:385-388,405-406; we only exploit it)
+void push_seg(std::vector<Seg>& v, uint64_t* host, size_t dev_off, size_t words) {
+    if (!v.empty()) {
+        Seg& b = v.back();
+        if (b.host + b.words == host && b.dev_off + b.words == dev_off) {
+            b.words += words;
+            return;
         }
-        i = j;
     }
-    return 0;
+    v.push_back({host, dev_off, words});
+}
+
+// Streams `n_chunks` chunks through the slot ring.  io(chunk, slot) describes the copies of a chunk,
+// launch(chunk, slot) queues its kernels on s_comp.
+int run_chunks(DeviceCtx& c, size_t n_chunks, bool pinned_in, bool pinned_out,
+               const std::function<void(size_t, ChunkIO&)>& io, const std::function<int(size_t, int)>& launch) {
+    if (!pinned_in || !pinned_out)
+        if (int rc = c.ensure_staging()) return rc;
+    ChunkIO cio;
+    for (size_t chunk = 0; chunk < n_chunks; ++chunk) {
+        const int s = (int)(chunk % kSlots);
+        cio.in.clear();
+        cio.out.clear();
+        io(chunk, cio);
+        // ---- upload ----
+        if (pinned_in) {
+            if (chunk >= kSlots) CU_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_free[s], 0));
+            for (const Seg& g : cio.in) {
+                CU_TRY(cudaMemcpyAsync(c.slot[s] + g.dev_off, g.host, g.words * 8, cudaMemcpyHostToDevice, c.s_h2d));
+                g_h2d += g.words * 8;
+            }
+        } else if (!cio.in.empty()) {
+            // the previous DMA out of this staging buffer must have finished before it is refilled
+            if (c.h_in_used[s]) CU_TRY(cudaEventSynchronize(c.ev_h2d[s]));
+            const size_t lo = cio.in.front().dev_off, hi = cio.in.back().dev_off + cio.in.back().words;
+            std::vector<CopyJob> jobs;
+            jobs.reserve(cio.in.size());
+            for (const Seg& g : cio.in) jobs.push_back({c.h_in[s] + (g.dev_off - lo), g.host, g.words * 8});
+            c.pool->run(jobs);
+            if (chunk >= kSlots) CU_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_free[s], 0));
+            CU_TRY(cudaMemcpyAsync(c.slot[s] + lo, c.h_in[s], (hi - lo) * 8, cudaMemcpyHostToDevice, c.s_h2d));
+            c.h_in_used[s] = true;
+            g_h2d += (hi - lo) * 8;
+        }
+        CU_TRY(cudaEventRecord(c.ev_h2d[s], c.s_h2d));
+        CU_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[s], 0));
+        // ---- kernels ----
+        if (int rc = launch(chunk, s)) return rc;
+        CU_TRY(cudaEventRecord(c.ev_comp[s], c.s_comp));
+        CU_TRY(cudaStreamWaitEvent(c.s_d2h, c.ev_comp[s], 0));
+        // ---- download ----
+        if (pinned_out) {
+            for (const Seg& g : cio.out) {
+                CU_TRY(cudaMemcpyAsync(g.host, c.slot[s] + g.dev_off, g.words * 8, cudaMemcpyDeviceToHost, c.s_d2h));
+                g_d2h += g.words * 8;
+            }
+            CU_TRY(cudaEventRecord(c.ev_free[s], c.s_d2h));
+        } else {
+            {   // the drain thread must have emptied this slot's staging buffer
+                std::unique_lock<std::mutex> lk(c.dmu);
+                c.dcv.wait(lk, [&] { return !c.out_busy[s]; });
+                c.out_busy[s] = true;
+            }
+            const size_t lo = cio.out.front().dev_off, hi = cio.out.back().dev_off + cio.out.back().words;
+            CU_TRY(cudaMemcpyAsync(c.h_out[s], c.slot[s] + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, c.s_d2h));
+            CU_TRY(cudaEventRecord(c.ev_free[s], c.s_d2h));
+            g_d2h += (hi - lo) * 8;
+            {
+                std::lock_guard<std::mutex> lk(c.dmu);
+                c.dq.push_back({s, cio.out, lo});
+            }
+            c.dcv.notify_all();
+        }
+    }
+    if (pinned_out) {
+        CU_TRY(cudaStreamSynchronize(c.s_d2h));
+        return 0;
+    }
+    return c.wait_drained();
 }
 
 int run_ntt_batch(DeviceCtx& c, const std::vector<Request>& rs, bool inverse) {
@@ -234,30 +537,22 @@ int run_ntt_batch(DeviceCtx& c, const std::vector<Request>& rs, bool inverse) {
     CU_TRY(cudaMemcpyAsync(c.d_small + n, r0.tw_p, n * 8, cudaMemcpyHostToDevice, c.s_h2d));
     g_h2d += 2 * n * 8;
     const size_t per_chunk = std::max<size_t>(1, c.slot_words / n);
-    size_t chunk_id = 0;
-    for (size_t off = 0; off < rs.size(); off += per_chunk, ++chunk_id) {
-        const size_t cnt = std::min(per_chunk, rs.size() - off);
-        const int s = (int)(chunk_id % kSlots);
-        if (chunk_id >= kSlots) CU_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_free[s], 0));
-        if (int rc = copy_runs(c.s_h2d, true, c.slot[s], n, n, cnt,
-                               [&](size_t i) { return (const uint64_t*)rs[off + i].out; }))
-            return rc;
-        CU_TRY(cudaEventRecord(c.ev_h2d[s], c.s_h2d));
-        CU_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[s], 0));
-        int rc = inverse ? hexl_b200_ntt_inv(c.slot[s], c.d_small, c.d_small + n, r0.q, r0.inv_n,
-                                             r0.inv_n_w, n, cnt, c.s_comp)
-                         : hexl_b200_ntt_fwd(c.slot[s], c.d_small, c.d_small + n, r0.q, n, cnt,
-                                             c.s_comp);
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(c.ev_comp[s], c.s_comp));
-        CU_TRY(cudaStreamWaitEvent(c.s_d2h, c.ev_comp[s], 0));
-        if (int rc2 = copy_runs(c.s_d2h, false, c.slot[s], n, n, cnt,
-                                [&](size_t i) { return (const uint64_t*)rs[off + i].out; }))
-            return rc2;
-        CU_TRY(cudaEventRecord(c.ev_free[s], c.s_d2h));
-    }
-    CU_TRY(cudaStreamSynchronize(c.s_d2h));
-    return 0;
+    const size_t n_chunks = (rs.size() + per_chunk - 1) / per_chunk;
+    const bool pinned = is_pinned(r0.out) && is_pinned(rs.back().out);
+    auto count_of = [&](size_t chunk) { return std::min(per_chunk, rs.size() - chunk * per_chunk); };
+    return run_chunks(
+        c, n_chunks, pinned, pinned,
+        [&](size_t chunk, ChunkIO& io) {
+            const size_t off = chunk * per_chunk, cnt = count_of(chunk);
+            for (size_t i = 0; i < cnt; ++i) push_seg(io.in, rs[off + i].out, i * n, n);
+            io.out = io.in;
+        },
+        [&](size_t chunk, int s) {
+            const size_t cnt = count_of(chunk);
+            return inverse ? hexl_b200_ntt_inv(c.slot[s], c.d_small, c.d_small + n, r0.q, r0.inv_n, r0.inv_n_w, n, cnt,
+                                               c.s_comp)
+                           : hexl_b200_ntt_fwd(c.slot[s], c.d_small, c.d_small + n, r0.q, n, cnt, c.s_comp);
+        });
 }
 
 int run_dyadic_batch(DeviceCtx& c, const std::vector<Request>& rs) {
@@ -275,59 +570,63 @@ int run_dyadic_batch(DeviceCtx& c, const std::vector<Request>& rs) {
     CU_TRY(cudaStreamSynchronize(c.s_h2d));  // `mods` is pageable and dies with this frame
     g_h2d += mods.size() * 8;
     const size_t per_chunk = std::max<size_t>(1, c.slot_words / item_w);
-    size_t chunk_id = 0;
-    for (size_t off = 0; off < rs.size(); off += per_chunk, ++chunk_id) {
-        const size_t cnt = std::min(per_chunk, rs.size() - off);
-        const int s = (int)(chunk_id % kSlots);
-        uint64_t* d_op1 = c.slot[s];
-        uint64_t* d_op2 = d_op1 + cnt * in_w;
-        uint64_t* d_res = d_op2 + cnt * in_w;
-        if (chunk_id >= kSlots) CU_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_free[s], 0));
-        if (int rc = copy_runs(c.s_h2d, true, d_op1, in_w, in_w, cnt,
-                               [&](size_t i) { return rs[off + i].in1; }))
-            return rc;
-        if (int rc = copy_runs(c.s_h2d, true, d_op2, in_w, in_w, cnt,
-                               [&](size_t i) { return rs[off + i].in2; }))
-            return rc;
-        CU_TRY(cudaEventRecord(c.ev_h2d[s], c.s_h2d));
-        CU_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[s], 0));
-        if (int rc = hexl_b200_dyadic_multiply(d_res, d_op1, d_op2, n, c.d_small + off * M, M, cnt, 1,
-                                               c.s_comp))
-            return rc;
-        CU_TRY(cudaEventRecord(c.ev_comp[s], c.s_comp));
-        CU_TRY(cudaStreamWaitEvent(c.s_d2h, c.ev_comp[s], 0));
-        if (int rc = copy_runs(c.s_d2h, false, d_res, out_w, out_w, cnt,
-                               [&](size_t i) { return (const uint64_t*)rs[off + i].out; }))
-            return rc;
-        CU_TRY(cudaEventRecord(c.ev_free[s], c.s_d2h));
-    }
-    CU_TRY(cudaStreamSynchronize(c.s_d2h));
-    return 0;
+    const size_t n_chunks = (rs.size() + per_chunk - 1) / per_chunk;
+    const bool pinned_in = is_pinned(r0.in1) && is_pinned(r0.in2) && is_pinned(rs.back().in1);
+    const bool pinned_out = is_pinned(r0.out) && is_pinned(rs.back().out);
+    auto count_of = [&](size_t chunk) { return std::min(per_chunk, rs.size() - chunk * per_chunk); };
+    return run_chunks(
+        c, n_chunks, pinned_in, pinned_out,
+        [&](size_t chunk, ChunkIO& io) {
+            const size_t off = chunk * per_chunk, cnt = count_of(chunk);
+            for (size_t i = 0; i < cnt; ++i) push_seg(io.in, const_cast<uint64_t*>(rs[off + i].in1), i * in_w, in_w);
+            for (size_t i = 0; i < cnt; ++i)
+                push_seg(io.in, const_cast<uint64_t*>(rs[off + i].in2), (cnt + i) * in_w, in_w);
+            for (size_t i = 0; i < cnt; ++i) push_seg(io.out, rs[off + i].out, 2 * cnt * in_w + i * out_w, out_w);
+        },
+        [&](size_t chunk, int s) {
+            const size_t off = chunk * per_chunk, cnt = count_of(chunk);
+            uint64_t* d_op1 = c.slot[s];
+            return hexl_b200_dyadic_multiply(d_op1 + 2 * cnt * in_w, d_op1, d_op1 + cnt * in_w, n, c.d_small + off * M, M,
+                                             cnt, 1, c.s_comp);
+        });
 }
 
 int get_plan(DeviceCtx& c, const Request& r, hexl_b200_ks_plan** out) {
-    PlanKey key{r.keys, r.moduli, r.msf, r.twiddles, r.n, r.D, r.K, r.R};
+    PlanKey key{r.keys, r.n, r.D, r.K, r.R};
+    const uint64_t th = r.twiddles ? hash_words(r.twiddles, r.K * 4 * r.n) : 0;
     auto it = c.plans.find(key);
     if (it != c.plans.end()) {
-        // The reference caches by pointer only (fpga.cpp:1158-1165) and loads
-        // twiddles once per process (fpga.cpp:1251-1255).  We additionally
-        // compare the moduli and key pointers by value so a reused address
-        // with new contents rebuilds the plan instead of computing garbage.
-        bool same = !memcmp(it->second.moduli_copy.data(), r.moduli, r.K * 8);
-        for (uint64_t j = 0; same && j < r.D; ++j) same = it->second.key_ptrs[j] == r.keys[j];
+        CachedPlan& cp = it->second;
+        bool same = !memcmp(cp.moduli.data(), r.moduli, r.K * 8) && !memcmp(cp.msf.data(), r.msf, r.K * 8) &&
+                    cp.has_twiddles == (r.twiddles != nullptr) && cp.twiddle_hash == th;
+        for (uint64_t j = 0; same && j < r.D; ++j) same = cp.key_ptrs[j] == r.keys[j];
         if (same) {
-            *out = it->second.plan;
+            cp.last_used = ++c.plan_clock;
+            *out = cp.plan;
             return 0;
         }
-        hexl_b200_ks_plan_destroy(it->second.plan);
+        c.sync_streams();
+        hexl_b200_ks_plan_destroy(cp.plan);
         c.plans.erase(it);
+    }
+    while (c.plans.size() >= c.max_plans) {   // bounded cache: drop the least recently used key set
+        auto lru = c.plans.begin();
+        for (auto p = c.plans.begin(); p != c.plans.end(); ++p)
+            if (p->second.last_used < lru->second.last_used) lru = p;
+        c.sync_streams();
+        hexl_b200_ks_plan_destroy(lru->second.plan);
+        c.plans.erase(lru);
     }
     CachedPlan cp;
     if (int rc = hexl_b200_ks_plan_create(&cp.plan, r.n, r.D, r.K, r.R, r.C, r.moduli, r.keys, r.msf,
                                           r.twiddles))
         return rc;
-    cp.moduli_copy.assign(r.moduli, r.moduli + r.K);
+    cp.moduli.assign(r.moduli, r.moduli + r.K);
+    cp.msf.assign(r.msf, r.msf + r.K);
     cp.key_ptrs.assign(r.keys, r.keys + r.D);
+    cp.has_twiddles = r.twiddles != nullptr;
+    cp.twiddle_hash = th;
+    cp.last_used = ++c.plan_clock;
     *out = cp.plan;
     c.plans.emplace(key, std::move(cp));
     return 0;
@@ -339,77 +638,98 @@ int run_keyswitch_batch(DeviceCtx& c, const std::vector<Request>& rs) {
     if (int rc = get_plan(c, r0, &plan)) return rc;
     const size_t n = r0.n, D = r0.D;
     const size_t t_w = D * n, res_w = 2 * D * n, item_w = t_w + res_w;
-    const size_t per_chunk = std::max<size_t>(1, c.slot_words / item_w);
     if (item_w > c.slot_words)
         return fail(HEXL_B200_EINVAL, "KeySwitch: one item exceeds the device slot");
-    size_t chunk_id = 0;
-    for (size_t off = 0; off < rs.size(); off += per_chunk, ++chunk_id) {
-        const size_t cnt = std::min(per_chunk, rs.size() - off);
-        const int s = (int)(chunk_id % kSlots);
-        uint64_t* d_t = c.slot[s];
-        uint64_t* d_res = d_t + cnt * t_w;
-        if (chunk_id >= kSlots) CU_TRY(cudaStreamWaitEvent(c.s_h2d, c.ev_free[s], 0));
-        if (int rc = copy_runs(c.s_h2d, true, d_t, t_w, t_w, cnt,
-                               [&](size_t i) { return rs[off + i].in1; }))
-            return rc;
-        // result is read-modify-write (accumulate, fpga.cpp:453-468)
-        if (int rc = copy_runs(c.s_h2d, true, d_res, res_w, res_w, cnt,
-                               [&](size_t i) { return (const uint64_t*)rs[off + i].out; }))
-            return rc;
-        CU_TRY(cudaEventRecord(c.ev_h2d[s], c.s_h2d));
-        CU_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_h2d[s], 0));
-        if (int rc = hexl_b200_keyswitch(plan, d_res, d_t, cnt, c.s_comp)) return rc;
-        CU_TRY(cudaEventRecord(c.ev_comp[s], c.s_comp));
-        CU_TRY(cudaStreamWaitEvent(c.s_d2h, c.ev_comp[s], 0));
-        if (int rc = copy_runs(c.s_d2h, false, d_res, res_w, res_w, cnt,
-                               [&](size_t i) { return (const uint64_t*)rs[off + i].out; }))
-            return rc;
-        CU_TRY(cudaEventRecord(c.ev_free[s], c.s_d2h));
+    const size_t per_chunk = std::max<size_t>(1, c.slot_words / item_w);
+    const size_t n_chunks = (rs.size() + per_chunk - 1) / per_chunk;
+    const bool pinned = is_pinned(r0.in1) && is_pinned(r0.out) && is_pinned(rs.back().in1) && is_pinned(rs.back().out);
+    auto count_of = [&](size_t chunk) { return std::min(per_chunk, rs.size() - chunk * per_chunk); };
+    return run_chunks(
+        c, n_chunks, pinned, pinned,
+        [&](size_t chunk, ChunkIO& io) {
+            const size_t off = chunk * per_chunk, cnt = count_of(chunk);
+            for (size_t i = 0; i < cnt; ++i) push_seg(io.in, const_cast<uint64_t*>(rs[off + i].in1), i * t_w, t_w);
+            // result is read-modify-write (accumulate, fpga.cpp:453-468)
+            for (size_t i = 0; i < cnt; ++i) {
+                push_seg(io.in, rs[off + i].out, cnt * t_w + i * res_w, res_w);
+                push_seg(io.out, rs[off + i].out, cnt * t_w + i * res_w, res_w);
+            }
+        },
+        [&](size_t chunk, int s) {
+            const size_t cnt = count_of(chunk);
+            return hexl_b200_keyswitch(plan, c.slot[s] + cnt * t_w, c.slot[s], cnt, c.s_comp);
+        });
+}
+
+// Number of requests at the head of the queue that may run as one batch: compatible with the first, and no
+// output range touched twice (two queued calls that accumulate into the same `result`, or transform the
+// same operand, must run one after the other -- the reference's host loop is sequential, fpga.cpp:441-475).
+size_t head_run(const std::deque<Request>& q, size_t cap, bool* fenced) {
+    *fenced = false;
+    size_t run = 0;
+    std::set<uintptr_t> starts;
+    const Request& f = q.front();
+    const uintptr_t len = f.out_words() * 8;
+    for (const Request& r : q) {
+        if (!compatible(f, r)) {
+            *fenced = true;
+            break;
+        }
+        const uintptr_t a = (uintptr_t)r.out;
+        auto hi = starts.lower_bound(a);
+        bool clash = (hi != starts.end() && *hi < a + len);
+        if (!clash && hi != starts.begin()) clash = *std::prev(hi) + len > a;
+        if (clash) {
+            *fenced = true;
+            break;
+        }
+        starts.insert(a);
+        if (++run == cap) break;
     }
-    CU_TRY(cudaStreamSynchronize(c.s_d2h));
-    return 0;
+    return run;
 }
 
 void worker_main(Runtime* rt, DeviceCtx* ctx) {
     cudaSetDevice(ctx->dev);
+    const size_t n_workers = rt->ctxs.size();
     std::vector<Request> batch;
     for (;;) {
         batch.clear();
         {
             std::unique_lock<std::mutex> lk(rt->mu);
+            rt->idle_workers++;
             rt->cv_work.wait(lk, [&] { return rt->stop || !rt->queue.empty(); });
             if (rt->queue.empty()) return;  // stop requested and drained
-            const Op op = rt->queue.front().op;
-            const uint64_t cap = rt->batch_cap[op] ? rt->batch_cap[op] : (uint64_t)1 << 20;
-            // Gather a run of compatible requests.  Keep waiting while the
-            // caller still owes calls of this worksize and no fence (an
-            // incompatible request) has shown up -- Buffer::pop semantics,
-            // fpga.cpp:107-180 -- but never longer than a short grace period.
+            // Gather a run of compatible requests.  Keep waiting while the caller still owes calls of
+            // this worksize and no fence (an incompatible request) has shown up -- Buffer::pop semantics,
+            // fpga.cpp:107-180 -- but never longer than a short grace period.  Everything is recomputed
+            // from the queue after every wait: with several workers the queue changes under our feet.
+            bool quiet = false;
             for (;;) {
-                size_t run = 0;
+                if (rt->queue.empty()) break;
+                const Op op = rt->queue.front().op;
                 bool fenced = false;
-                for (const Request& r : rt->queue) {
-                    if (!compatible(rt->queue.front(), r)) {
-                        fenced = true;
-                        break;
-                    }
-                    if (++run == cap) break;
+                const size_t run_all = head_run(rt->queue, (size_t)1 << 20, &fenced);
+                // share of one worker: BATCH_SIZE_* when set, else an equal part, among the workers that are
+                // free right now, of what this run will be (queued + still promised), so that NUM_DEV
+                // workers all get work without any tuning
+                size_t cap = rt->batch_cap[op];
+                if (!cap) {
+                    const size_t total = run_all + (fenced ? 0 : (size_t)rt->expected[op]);
+                    const size_t share = std::max<size_t>(1, std::min(n_workers, rt->idle_workers));
+                    cap = n_workers > 1 ? std::max<size_t>(1, (total + share - 1) / share) : (size_t)1 << 20;
                 }
-                if (run == cap || fenced || rt->expected[op] == 0 || rt->stop) {
+                const size_t run = std::min(run_all, cap);
+                if (run == cap || fenced || rt->expected[op] == 0 || rt->stop || quiet) {
                     batch.assign(rt->queue.begin(), rt->queue.begin() + run);
                     rt->queue.erase(rt->queue.begin(), rt->queue.begin() + run);
                     break;
                 }
-                const size_t before = rt->queue.size();
+                const size_t before = rt->submitted[op];
                 rt->cv_work.wait_for(lk, std::chrono::milliseconds(2));
-                if (rt->queue.size() == before && !rt->queue.empty()) {
-                    // producer went quiet: run what we have
-                    size_t take = std::min<size_t>(run, rt->queue.size());
-                    batch.assign(rt->queue.begin(), rt->queue.begin() + take);
-                    rt->queue.erase(rt->queue.begin(), rt->queue.begin() + take);
-                    break;
-                }
+                quiet = rt->submitted[op] == before;   // producer went quiet: run what is there
             }
+            rt->idle_workers--;
             rt->cv_space.notify_all();
         }
         if (batch.empty()) continue;
@@ -422,6 +742,16 @@ void worker_main(Runtime* rt, DeviceCtx* ctx) {
             case OP_KEYSWITCH: rc = run_keyswitch_batch(*ctx, batch); break;
             default: rc = HEXL_B200_EINVAL;
         }
+        std::string msg;
+        if (rc) {
+            msg = hexl_b200_last_error();
+            // nothing may still be in flight towards caller memory or the slots when we report
+            ctx->sync_streams();
+            if (ctx->h_in[0]) ctx->wait_drained();
+            cudaGetLastError();
+        }
+        ctx->batches++;
+        ctx->items += batch.size();
         if (rt->debug) {
             double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             fprintf(stderr, "[hexl_b200] dev %d %s batch=%zu %.3f ms rc=%d\n", ctx->dev,
@@ -429,14 +759,26 @@ void worker_main(Runtime* rt, DeviceCtx* ctx) {
         }
         {
             std::lock_guard<std::mutex> lk(rt->mu);
-            if (rc && !rt->error) {
-                rt->error = rc;
-                rt->error_msg = hexl_b200_last_error();
+            const Op op = batch[0].op;
+            if (rc && !rt->error[op]) {
+                rt->error[op] = rc;
+                rt->error_msg[op] = msg;
             }
-            rt->completed[batch[0].op] += batch.size();
+            rt->completed[op] += batch.size();
         }
         rt->cv_done.notify_all();
     }
+}
+
+// the first asynchronous failure of an operation is handed to ONE caller (the completer, or the
+// synchronous submitter) and then forgotten: later calls start clean
+int take_error(Runtime* rt, Op op) {
+    if (!rt->error[op]) return 0;
+    const int rc = rt->error[op];
+    const std::string msg = rt->error_msg[op];
+    rt->error[op] = 0;
+    rt->error_msg[op].clear();
+    return fail(rc, "%s", msg.c_str());
 }
 
 int submit(const Request& r) {
@@ -455,7 +797,7 @@ int submit(const Request& r) {
     if (sync) {
         std::unique_lock<std::mutex> lk(rt->mu);
         rt->cv_done.wait(lk, [&] { return rt->completed[r.op] == rt->submitted[r.op]; });
-        if (rt->error) return fail(rt->error, "%s", rt->error_msg.c_str());
+        return take_error(rt, r.op);
     }
     return 0;
 }
@@ -468,8 +810,7 @@ int completed(Op op) {
     rt->worksize[op] = 1;   // reset, fpga_int.cpp:229
     rt->cv_work.notify_all();
     rt->cv_done.wait(lk, [&] { return rt->completed[op] == rt->submitted[op]; });
-    if (rt->error) return fail(rt->error, "%s", rt->error_msg.c_str());
-    return 0;
+    return take_error(rt, op);
 }
 
 int set_worksize(Op op, uint64_t ws) {
@@ -511,9 +852,17 @@ int hexl_b200_host_acquire(void) {
     rt->batch_cap[OP_KEYSWITCH] = env_u64("BATCH_SIZE_KEYSWITCH", 0);
     rt->debug = (int)env_u64("FPGA_DEBUG", 0);
     const size_t slot_bytes = (size_t)env_u64("HEXL_B200_SLOT_MB", 64) << 20;
+    // copy threads for pageable callers: enough to keep a Gen5 x16 link busy in both directions, but
+    // never more than the cores this process may use
+    unsigned hw = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) hw = (unsigned)CPU_COUNT(&set);
+    const unsigned copy_threads = (unsigned)env_u64("HEXL_B200_COPY_THREADS", std::max(1u, std::min(8u, hw / 2)));
+    rt->pool = std::make_unique<CopyPool>(copy_threads);
+    const size_t plan_cap = (size_t)env_u64("HEXL_B200_PLAN_CACHE", 8);
     for (uint64_t d = 0; d < ndev; ++d) {
         auto ctx = std::make_unique<DeviceCtx>();
-        if (int rc = ctx->init(base + (int)d, slot_bytes)) {
+        if (int rc = ctx->init(base + (int)d, slot_bytes, rt->pool.get(), plan_cap)) {
             ctx->destroy();
             for (auto& c : rt->ctxs) c->destroy();
             cudaSetDevice(base);
@@ -524,8 +873,8 @@ int hexl_b200_host_acquire(void) {
     cudaSetDevice(base);
     for (auto& c : rt->ctxs) rt->workers.emplace_back(worker_main, rt.get(), c.get());
     if (rt->debug)
-        fprintf(stderr, "[hexl_b200] acquired %llu CUDA device(s) starting at %d, slot %zu MiB x %d\n",
-                (unsigned long long)ndev, base, slot_bytes >> 20, kSlots);
+        fprintf(stderr, "[hexl_b200] acquired %llu CUDA device(s) starting at %d, slot %zu MiB x %d, %u copy threads\n",
+                (unsigned long long)ndev, base, slot_bytes >> 20, kSlots, copy_threads);
     g_rt = rt.release();
     return 0;
 }
@@ -543,6 +892,19 @@ int hexl_b200_host_release(void) {
     for (auto& c : rt->ctxs) c->destroy();
     g_rt = nullptr;
     delete rt;
+    return 0;
+}
+
+int hexl_b200_host_device_stats(int worker, hexl_b200_device_stats* out) {
+    std::lock_guard<std::mutex> lk(g_life);
+    Runtime* rt = g_rt;
+    if (!rt) return fail(HEXL_B200_ENODEV, "device_stats: library not acquired");
+    if (!out || worker < 0 || (size_t)worker >= rt->ctxs.size())
+        return fail(HEXL_B200_EINVAL, "device_stats: worker %d out of range (NUM_DEV = %zu)", worker, rt->ctxs.size());
+    DeviceCtx& c = *rt->ctxs[worker];
+    out->device = c.dev;
+    out->batches = c.batches.load();
+    out->items = c.items.load();
     return 0;
 }
 

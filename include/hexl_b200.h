@@ -211,6 +211,17 @@ typedef struct {
 int hexl_b200_get_stats(hexl_b200_stats* out);
 int hexl_b200_reset_stats(void);
 
+/* Work done so far by worker `worker` (0 .. NUM_DEV-1) of the host-pointer runtime since acquire: which
+ * CUDA device it drives, how many batches and how many requests it has executed.  The reference's
+ * DevicePool (host/src/fpga.cpp:1646-1673) has no such counter; tests use it to check that a run is dealt
+ * out over all NUM_DEV workers. */
+typedef struct {
+    int32_t device;
+    uint64_t batches;
+    uint64_t items;
+} hexl_b200_device_stats;
+int hexl_b200_host_device_stats(int worker, hexl_b200_device_stats* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,3 +90,14 @@ def test_product_twiddles_equal_oracle_tables(hb, n, bits):
     assert np.array_equal(roots, t.roots) and np.array_equal(precon, t.precon)
     assert np.array_equal(inv_roots, t.inv_roots) and np.array_equal(precon_inv, t.precon_inv)
     assert (inv_n, inv_n_w) == (t.inv_n, t.inv_n_w)
+
+
+def test_composite_modulus_is_rejected_quickly(hb):
+    """a composite modulus = 1 mod 2n has no use (and once sent the root search on a 2^40-step walk)"""
+    import time
+
+    q = 1099511687169           # = 1 mod 2048, composite
+    t0 = time.time()
+    with pytest.raises(hb.HexlB200Error):
+        hb.compute_twiddles(1024, q)
+    assert time.time() - t0 < 5

@@ -1,7 +1,8 @@
 """NUM_DEV=2: the library's own multi-GPU mode (one worker thread per GPU popping the
 shared request queue, like the reference's DevicePool, host/src/fpga.cpp:1646-1673).
 Runs in a subprocess because NUM_DEV is read when the resources are acquired; skipped
-on single-GPU boxes."""
+on single-GPU boxes.  No BATCH_SIZE_* is set: the runtime deals every run out over the workers by itself,
+and the per-worker counters (hexl_b200_host_device_stats) must show it."""
 import os
 import subprocess
 import sys
@@ -44,6 +45,12 @@ try:
         hb.KeySwitch(out[b], p.t_target[b], 4096, 3, 4, 4, 2, p.moduli, keys, p.msf)
     hb.KeySwitchCompleted()
     assert np.array_equal(out, p.expected()), "keyswitch mismatch with NUM_DEV=2"
+    st = [hb.device_stats(w) for w in range(2)]
+    print("DEVICE_STATS", st)
+    assert st[0]["device"] != st[1]["device"]
+    # no BATCH_SIZE_* knob is set: every run must have been dealt out over both workers
+    assert min(s["items"] for s in st) >= 0.3 * sum(s["items"] for s in st), st
+    assert min(s["batches"] for s in st) >= 6, st
 finally:
     hb.release_FPGA_resources()
 print("MULTI_DEVICE_OK")
@@ -55,7 +62,9 @@ def test_two_worker_gpus():
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    env = dict(os.environ, NUM_DEV="2", BATCH_SIZE_NTT="16", BATCH_SIZE_INTT="16")
+    env = dict(os.environ, NUM_DEV="2")
+    for k in ("BATCH_SIZE_NTT", "BATCH_SIZE_INTT", "BATCH_SIZE_KEYSWITCH"):
+        env.pop(k, None)
     out = subprocess.run([sys.executable, "-c", WORKER % {"root": ROOT}], env=env, capture_output=True, text=True,
                          timeout=600)
     assert "MULTI_DEVICE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
