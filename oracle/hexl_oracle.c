@@ -607,6 +607,15 @@ int ho_keyswitch_batch(uint64_t* result, const uint64_t* t_target,
                   msf, threads);
 }
 
+int ho_keyswitch_alt_batch(uint64_t* result, const uint64_t* t_target,
+                           uint64_t batch, uint64_t n, uint64_t D, uint64_t K,
+                           uint64_t R, uint64_t C, const uint64_t* moduli,
+                           const uint64_t* const* keys, const uint64_t* msf,
+                           int threads) {
+    return ks_run(ks_impl_alt, result, t_target, batch, n, D, K, R, C, moduli,
+                  keys, msf, threads);
+}
+
 /* ------------------------------------------------------------------------ */
 /* helpers                                                                   */
 /* ------------------------------------------------------------------------ */

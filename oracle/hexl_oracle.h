@@ -126,6 +126,16 @@ int ho_keyswitch_batch(uint64_t* result, const uint64_t* t_target,
                        const uint64_t* const* k_switch_keys,
                        const uint64_t* modswitch_factors, int threads);
 
+/* the same over the second restatement (the cheaper of the two: digit reuse, lazy
+ * transforms) -- bench.py's CPU keyswitch baseline */
+int ho_keyswitch_alt_batch(uint64_t* result, const uint64_t* t_target,
+                           uint64_t batch, uint64_t n,
+                           uint64_t decomp_modulus_size, uint64_t key_modulus_size,
+                           uint64_t rns_modulus_size,
+                           uint64_t key_component_count, const uint64_t* moduli,
+                           const uint64_t* const* k_switch_keys,
+                           const uint64_t* modswitch_factors, int threads);
+
 /* ---- helpers shared by tests ---- */
 /* 64-bit FNV-1a over the little-endian bytes of v[0..n). */
 uint64_t ho_fnv1a(const uint64_t* v, size_t n);

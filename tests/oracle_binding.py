@@ -48,6 +48,8 @@ def oracle():
         o.ho_keyswitch_alt.argtypes = ks; o.ho_keyswitch_alt.restype = C.c_int
         o.ho_keyswitch_batch.argtypes = [vp, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, C.c_int]
         o.ho_keyswitch_batch.restype = C.c_int
+        o.ho_keyswitch_alt_batch.argtypes = [vp, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, C.c_int]
+        o.ho_keyswitch_alt_batch.restype = C.c_int
         o.ho_fnv1a.argtypes = [vp, C.c_size_t]; o.ho_fnv1a.restype = u64
         o.ho_splitmix_fill.argtypes = [vp, C.c_size_t, u64, u64]; o.ho_splitmix_fill.restype = u64
         o.ho_max_threads.restype = C.c_int
@@ -149,8 +151,8 @@ def keyswitch(result, t_target, n, D, K, moduli, keys, msf, batch=1, alt=False, 
     keys = [np.ascontiguousarray(k, dtype=np.uint64) for k in keys]
     arr = (vp * len(keys))(*[k.ctypes.data for k in keys])
     if alt:
-        assert batch == 1
-        rc = o.ho_keyswitch_alt(P(res), P(t_target), n, D, K, D + 1, 2, P(moduli), C.cast(arr, vp), P(msf))
+        rc = o.ho_keyswitch_alt_batch(P(res), P(t_target), batch, n, D, K, D + 1, 2, P(moduli), C.cast(arr, vp),
+                                      P(msf), threads or o.ho_max_threads())
     else:
         rc = o.ho_keyswitch_batch(P(res), P(t_target), batch, n, D, K, D + 1, 2, P(moduli), C.cast(arr, vp),
                                   P(msf), threads or o.ho_max_threads())
