@@ -77,6 +77,7 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.ftwd = nullptr;
     t.itwd = nullptr;
     t.fp64_ok = 0;          // set by the callers that build the FP64 tables
+    t.lazy_out = 0;
     return t;
 }
 
@@ -107,6 +108,62 @@ struct StreamScratch {
 };
 static StreamScratch g_scratch;
 
+// N = 32768 (csrc/ntt_big.cu): stage 0 / the last stage as a streaming kernel, the two halves of every
+// polynomial on the 16384-point shared-memory kernels.  Scratch (per stream): raw sub-tables of both halves
+// (2 x 2 x 16384 words), per half the packed tables (integer + FP64 format) and a deferred list.
+static int ntt_big(bool fwd, uint64_t* d_operand, const uint64_t* d_tab, const uint64_t* d_tab_p, uint64_t q,
+                   uint64_t inv_n, uint64_t inv_n_w, uint64_t batch, uint32_t lazy_out, cudaStream_t st) {
+    const uint32_t logh = 14, nh = 1u << logh;
+    const int variant = 1;
+    if (lazy_out) return fail(HEXL_B200_EINVAL, "n = 32768: output_mod_factor must be 1");
+    const size_t raw_bytes = (size_t)4 * nh * 8, half_bytes = (size_t)2 << 20;
+    const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
+    uint8_t* scratch = nullptr;
+    cudaError_t e = g_scratch.get(st, raw_bytes + 2 * half_bytes + 2 * list_bytes, (void**)&scratch);
+    if (e != cudaSuccess) return cuda_fail(e, "ntt (n = 32768): scratch");
+    uint64_t* sub = reinterpret_cast<uint64_t*>(scratch);
+    if ((e = hb::launch_big_split(fwd, d_tab, d_tab_p, sub, nh, st))) return cuda_fail(e, "ntt (n = 32768): table split");
+    int launches = 1;
+    if (fwd) {
+        if ((e = hb::launch_big_stage0_fwd(d_operand, d_tab, d_tab_p, q, nh, batch, st)))
+            return cuda_fail(e, "ntt (n = 32768): stage 0");
+        ++launches;
+    }
+    for (uint32_t h = 0; h < 2; ++h) {
+        uint8_t* blk = scratch + raw_bytes + h * half_bytes;
+        hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(blk);
+        hb::TwPair* packed_d = reinterpret_cast<hb::TwPair*>(blk + (1u << 20));
+        uint32_t* list = reinterpret_cast<uint32_t*>(scratch + raw_bytes + 2 * half_bytes + h * list_bytes);
+        const uint64_t* r = sub + (size_t)h * 2 * nh;
+        hb::PackExtra px;
+        const bool fp64 = g_fp64_path.load() && hb::fp64_modulus_ok(q);
+        if (fp64) {
+            (fwd ? px.fwd_d : px.inv_d) = packed_d;
+            px.q = q;
+        }
+        e = fwd ? hb::launch_pack_twiddles(logh, variant, r, r + nh, packed, nullptr, nullptr, nullptr, list, st, px)
+                : hb::launch_pack_twiddles(logh, variant, nullptr, nullptr, nullptr, r, r + nh, packed, list, st, px);
+        if (e != cudaSuccess) return cuda_fail(e, "ntt (n = 32768): pack twiddles");
+        ++launches;
+        // the sub-transforms' own last stage is scaled by 1: the big transform's twiddle of that stage and
+        // n^-1 are applied by the last-stage kernel
+        hb::ModTab t = fwd ? make_modtab(q, 0, 0, packed, nullptr, (int)logh) : make_modtab(q, 1 % q, 1 % q, nullptr, packed, (int)logh);
+        if (fp64) {
+            (fwd ? t.ftwd : t.itwd) = packed_d;
+            t.fp64_ok = 1;
+        }
+        if ((e = hb::launch_ntt_half(fwd, d_operand, t, logh, batch, variant, list, st, &launches, h)))
+            return cuda_fail(e, "ntt (n = 32768): sub-transforms");
+    }
+    if (!fwd) {
+        if ((e = hb::launch_big_last_inv(d_operand, d_tab, q, inv_n, inv_n_w, nh, batch, st)))
+            return cuda_fail(e, "ntt (n = 32768): last stage");
+        ++launches;
+    }
+    g_launches += launches;
+    return 0;
+}
+
 }  // namespace hexl_b200
 
 using namespace hexl_b200;
@@ -119,6 +176,7 @@ struct hexl_b200_ks_plan {
     hb::TwPair* d_packed = nullptr; // K * (FWD_ENTRIES + INV_ENTRIES) packed twiddles
     uint64_t* d_keys = nullptr;     // D * 2 * K * n
     hb::TwPair* d_keys_sh = nullptr;  // same, with Shoup factors (fast path)
+    void* d_keys_fused = nullptr;     // key quads in the fused kernel's layout (keyswitch_fused.cu)
     uint64_t* d_small = nullptr;    // msf, msf_p
     hb::ModTab* d_tabs = nullptr;
     hb::Divisor* d_divs = nullptr;
@@ -143,12 +201,24 @@ int hexl_b200_device_count(void) {
     return n;
 }
 
+#ifdef HB_EXPERIMENTAL_VARIANTS
+static const bool kExperimental = true;
+#else
+static const bool kExperimental = false;
+#endif
+#define HB_NEEDS_EXPERIMENTAL(cond)                                                                              \
+    if ((cond) && !kExperimental)                                                                                \
+        return fail(HEXL_B200_EINVAL, "option '%s' = %lld selects a kernel variant that is only compiled with "   \
+                                      "make EXPERIMENTAL=1 (measured slower than the default)", name, (long long)value)
+
 int hexl_b200_set_option(const char* name, int64_t value) {
     if (!name) return fail(HEXL_B200_EINVAL, "option name is NULL");
     if (!strcmp(name, "ntt_variant")) {
         // bit 0: 32 words/thread at N=16384; bit 1 (perf exploration only): skip the
         // input-range vote, i.e. the caller guarantees in-contract inputs
         if (value < 0 || value > 3) return fail(HEXL_B200_EINVAL, "ntt_variant must be 0..3");
+        // (N = 16384 with 16 words per thread needs the experimental build; other sizes ignore the difference)
+        (void)kExperimental;
         g_ntt_variant = (int)value;
         return 0;
     }
@@ -159,6 +229,7 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "small_path")) {
         if (value < 0 || value > 3) return fail(HEXL_B200_EINVAL, "small_path must be 0, 1, 2 or 3");
+        HB_NEEDS_EXPERIMENTAL(value >= 2);
         g_small_path = (int)value;
         return 0;
     }
@@ -179,12 +250,27 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "inv_lazy")) {
+        HB_NEEDS_EXPERIMENTAL(value != 0);
         g_inv_lazy = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "polymul_fused")) {
+        hb::g_polymul_fused = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "ks_fused")) {
+        hb::g_ks_fused = value ? 1 : 0;     // read when a plan is created and on every call
+        return 0;
+    }
+    if (!strcmp(name, "ks_sub_items")) {
+        if (value < 0 || value > 65535) return fail(HEXL_B200_EINVAL, "ks_sub_items must be 0..65535");
+        hb::g_ks_sub_items = (int)value;
         return 0;
     }
     if (!strcmp(name, "ks_mac_items")) {
         if (value != 1 && value != 2 && value != 4 && value != 8)
             return fail(HEXL_B200_EINVAL, "ks_mac_items must be 1, 2, 4 or 8");
+        HB_NEEDS_EXPERIMENTAL(value != 4);
         hb::g_ks_mac_items = (int)value;
         return 0;
     }
@@ -225,14 +311,26 @@ int hexl_b200_reset_stats(void) {
 
 int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64_t* d_precon,
                       uint64_t q, uint64_t n, uint64_t batch, void* stream) {
+    return hexl_b200_ntt_fwd_ex(d_operand, d_roots, d_precon, q, n, batch, 1, 1, stream);
+}
+
+int hexl_b200_ntt_fwd_ex(uint64_t* d_operand, const uint64_t* d_roots, const uint64_t* d_precon, uint64_t q, uint64_t n,
+                         uint64_t batch, uint64_t input_mod_factor, uint64_t output_mod_factor, void* stream) {
+    // reference: tests/test_utils/ntt.cpp:442-455 (ComputeForward argument checks)
+    if (input_mod_factor != 1 && input_mod_factor != 2 && input_mod_factor != 4)
+        return fail(HEXL_B200_EINVAL, "ntt_fwd: input_mod_factor must be 1, 2 or 4");
+    if (output_mod_factor != 1 && output_mod_factor != 4)
+        return fail(HEXL_B200_EINVAL, "ntt_fwd: output_mod_factor must be 1 or 4");
     const int logn = ilog2_exact(n);
-    if (logn < 0 || !hb::ntt_shape_supported((uint32_t)logn))
-        return fail(HEXL_B200_EINVAL, "ntt_fwd: n=%llu unsupported (power of two in [1024,16384])",
+    if (logn < 0 || !(hb::ntt_shape_supported((uint32_t)logn) || logn == 15))
+        return fail(HEXL_B200_EINVAL, "ntt_fwd: n=%llu unsupported (power of two in [1024,32768])",
                     (unsigned long long)n);
     if (!d_operand || !d_roots || !d_precon) return fail(HEXL_B200_EINVAL, "ntt_fwd: NULL pointer");
     if (!aligned16(d_operand)) return fail(HEXL_B200_EINVAL, "ntt_fwd: operand not 16-byte aligned");
     if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "ntt_fwd: modulus must be in [2, 2^62)");
     if (batch == 0) return 0;
+    if (logn == 15)
+        return ntt_big(true, d_operand, d_roots, d_precon, q, 0, 0, batch, output_mod_factor == 4, (cudaStream_t)stream);
     const int variant = g_ntt_variant.load();
     // per-stream scratch: [0,512K) packed forward twiddles, [512K,1M) packed
     // inverse twiddles, [1M,1.5M) / [1.5M,2M) the same for the FP64 path, then
@@ -262,6 +360,9 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
         t.ftwd = packed_d;
         t.fp64_ok = 1;
     }
+    // output_mod_factor 4: the words of the Harvey butterflies as they stand, in [0, 4q) (ntt.cpp:535): only
+    // the reference op sequence defines them, so the exact kernel runs for every item
+    t.lazy_out = output_mod_factor == 4 ? 1u : 0u;
     e = hb::launch_ntt_fwd(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd launch");
     g_launches += launches;
@@ -271,9 +372,20 @@ int hexl_b200_ntt_fwd(uint64_t* d_operand, const uint64_t* d_roots, const uint64
 int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const uint64_t* d_precon_inv,
                       uint64_t q, uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch,
                       void* stream) {
+    return hexl_b200_ntt_inv_ex(d_operand, d_inv_roots, d_precon_inv, q, inv_n, inv_n_w, n, batch, 1, 1, stream);
+}
+
+int hexl_b200_ntt_inv_ex(uint64_t* d_operand, const uint64_t* d_inv_roots, const uint64_t* d_precon_inv, uint64_t q,
+                         uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch, uint64_t input_mod_factor,
+                         uint64_t output_mod_factor, void* stream) {
+    // reference: tests/test_utils/ntt.cpp:457-470 (ComputeInverse argument checks)
+    if (input_mod_factor != 1 && input_mod_factor != 2)
+        return fail(HEXL_B200_EINVAL, "ntt_inv: input_mod_factor must be 1 or 2");
+    if (output_mod_factor != 1 && output_mod_factor != 2)
+        return fail(HEXL_B200_EINVAL, "ntt_inv: output_mod_factor must be 1 or 2");
     const int logn = ilog2_exact(n);
-    if (logn < 0 || !hb::ntt_shape_supported((uint32_t)logn))
-        return fail(HEXL_B200_EINVAL, "ntt_inv: n=%llu unsupported (power of two in [1024,16384])",
+    if (logn < 0 || !(hb::ntt_shape_supported((uint32_t)logn) || logn == 15))
+        return fail(HEXL_B200_EINVAL, "ntt_inv: n=%llu unsupported (power of two in [1024,32768])",
                     (unsigned long long)n);
     if (!d_operand || !d_inv_roots || !d_precon_inv)
         return fail(HEXL_B200_EINVAL, "ntt_inv: NULL pointer");
@@ -282,6 +394,9 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
     if (inv_n >= q || inv_n_w >= q)
         return fail(HEXL_B200_EINVAL, "ntt_inv: inv_n / inv_n_w must be reduced mod q");
     if (batch == 0) return 0;
+    if (logn == 15)
+        return ntt_big(false, d_operand, d_inv_roots, d_precon_inv, q, inv_n, inv_n_w, batch, output_mod_factor == 2,
+                       (cudaStream_t)stream);
     const int variant = g_ntt_variant.load();
     uint8_t* scratch = nullptr;
     const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
@@ -308,6 +423,7 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_roots, const ui
         t.itwd = packed_d;
         t.fp64_ok = 1;
     }
+    t.lazy_out = output_mod_factor == 2 ? 1u : 0u;   // words left in [0, 2q) (ntt.cpp:648-657): exact kernel
     e = hb::launch_ntt_inv(d_operand, t, (uint32_t)logn, batch, variant, list, (cudaStream_t)stream, &launches);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv launch");
     g_launches += launches;
@@ -360,9 +476,21 @@ int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint6
         t.itwd = px.inv_d;
         t.fp64_ok = 1;
     }
+    const bool fused = (variant & 1) && hb::polymul_fused_available(t, (uint32_t)logn);
     for (uint64_t off = 0; off < batch; off += chunk) {
         const uint64_t cnt = batch - off < chunk ? batch - off : chunk;
         uint64_t* res = d_result + off * n;
+        if (fused) {
+            // one launch: NTT(a) parked in tensor memory, NTT(b), product, INTT (polymul_fused.cu); items with
+            // out-of-contract words go through the exact kernels behind it (deferred list, normally empty)
+            if (off && (e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
+            e = hb::launch_polymul_fused(res, d_a + off * n, d_b + off * n, t, cnt, list, st);
+            if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: fused kernel");
+            e = hb::launch_polymul_deferred(res, tb, d_a + off * n, d_b + off * n, t, cnt, list, st);
+            if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: deferred items");
+            launches += 4;
+            continue;
+        }
         // NTT(a) -> result, NTT(b) -> scratch; out-of-contract words take the exact kernel (deferred list)
         if (off && (e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
         e = hb::launch_ntt_fwd(res, t, (uint32_t)logn, cnt, variant, list, st, &launches, d_a + off * n);
@@ -530,13 +658,26 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         p->dev.keys_sh = p->d_keys_sh;
         g_launches += 1;
     }
+    p->dev.keys_fused = nullptr;
+    {
+        hb::KsDev probe = p->dev;
+        probe.keys_fused = (const void*)1;
+        if (hb::g_ks_fused && hb::ks_fused_available(probe, probe.keys_fused)) {
+            if ((e = cudaMalloc(&p->d_keys_fused, hb::ks_fused_key_bytes(p->dev))))
+                return cleanup(cuda_fail(e, "cudaMalloc fused keys"));
+            if ((e = hb::launch_ks_prepare_keys_fused(p->dev, p->d_keys_fused, 0)) || (e = cudaDeviceSynchronize()))
+                return cleanup(cuda_fail(e, "prepare fused keys"));
+            p->dev.keys_fused = p->d_keys_fused;
+            g_launches += 1;
+        }
+    }
     *out = p;
     return 0;
 }
 
 int hexl_b200_ks_plan_destroy(hexl_b200_ks_plan* p) {
     if (!p) return 0;
-    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_keys_sh); cudaFree(p->d_small);
+    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_keys_sh); cudaFree(p->d_keys_fused); cudaFree(p->d_small);
     cudaFree(p->d_tabs); cudaFree(p->d_divs); cudaFree(p->ws);
     delete p;
     return 0;

@@ -23,6 +23,15 @@
 
 namespace hb {
 
+// Stages S2 + S3 + S4 in one kernel with the sums in tensor memory (keyswitch_fused.cu), option "ks_fused".
+// Bit-exact and without the V scratch, but MEASURED SLOWER than the staged kernels (72k vs 93k KeySwitch/s at
+// N = 16384, D = 7: every transform has to pull its own 512 KiB of key quads from L2, where the staged
+// multiply-accumulate shares one key load among four items), so it is off by default.
+int g_ks_fused = 0;
+// Items per S2 + S3 round (option "ks_sub_items", 0 = the whole chunk): small rounds keep the NTT'd digits
+// (V, D*D polynomials per item) inside the 126 MB L2 between the transform that writes them and the
+// multiply-accumulate that reads them, so they never travel to HBM.
+int g_ks_sub_items = 0;
 int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys, 2 = 128-bit accumulators (both slower: latency bound)
 
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
@@ -52,8 +61,10 @@ struct JobNtt1 {
     static constexpr bool kOneModulus = false;
     KsDev ks;
     uint64_t* V;
+    uint32_t item0 = 0;     // first (item, pair) index of this launch (rounds of a few items)
     HB_D void decode(uint32_t item, uint32_t& b, uint32_t& r, uint32_t& j) const {
         const uint32_t D = ks.D, per = D * D;
+        item += item0;
         b = item / per;
         const uint32_t y = item % per;
         if (y < D * (D - 1)) {
@@ -81,6 +92,7 @@ struct JobNtt1 {
         return XfReduce{t.q, t.mu, ks.s2_no_reduce};
     }
     HB_D OfRows of(uint32_t item, const CUtensorMap* smap) const {
+        item += item0;
         return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
     }
 };
@@ -197,6 +209,7 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
     }
 }
 
+#ifdef HB_EXPERIMENTAL_VARIANTS
 // Wide-accumulator version (all moduli < 2^58, D <= 16): no per-term reduction at
 // all.  Every term is a plain 64x64 product of a reduced operand and a reduced
 // key, accumulated as three partial sums by weight (2^0 as 96 bits, 2^32 and
@@ -326,6 +339,8 @@ k_ks_mac_regkeys(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t
         ACC[(((size_t)b * 2 + 1) * ks.R + r) * N + l] = reduce_small_multiple(a1, fm);
     }
 }
+
+#endif  // HB_EXPERIMENTAL_VARIANTS
 
 // one-time per plan: keys_sh from the raw keys
 __global__ void k_ks_prepare_keys(KsDev ks, TwPair* __restrict__ out) {
@@ -458,10 +473,14 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt2(const __grid_con
     ntt_persistent<C, true, MODE, JobNtt2<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
+static bool use_fused(const KsDev& ks) { return g_ks_fused && ks_fused_available(ks, ks.keys_fused); }
+
 size_t ks_scratch_words_per_item(const KsDev& ks) {
     const size_t n = (size_t)1 << ks.logn;
-    // U + V + ACC, plus room for the deferred list of stage S1 (D entries and the count)
-    return ((size_t)ks.D + (size_t)ks.D * ks.D + 2 * (size_t)ks.R) * n + ks.D + 1;
+    // U + V + ACC, plus room for the deferred list of stage S1 (D entries and the count); the fused
+    // kernel has no V
+    const size_t v = use_fused(ks) ? 0 : (size_t)ks.D * ks.D;
+    return ((size_t)ks.D + v + 2 * (size_t)ks.R) * n + ks.D + 1;
 }
 
 template <class C>
@@ -488,26 +507,56 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
                             uint64_t* scratch, cudaStream_t st, int* launches) {
     const size_t smem = ntt_smem_bytes<C>();
     const uint64_t D = ks.D, R = ks.R;
+    const bool fused = use_fused(ks);
     uint64_t* U = scratch;
     uint64_t* V = U + items * D * C::N;
-    uint64_t* ACC = V + items * D * D * C::N;
+    uint64_t* ACC = V + (fused ? 0 : items * D * D * C::N);
     CUtensorMap m_t, m_u, m_acc, m_vs;
     cudaError_t e;
     if ((e = make_poly_tmap(&m_t, t_target, items * D, C::LOGN))) return e;
     if ((e = make_poly_tmap(&m_u, U, items * D, C::LOGN))) return e;
     if ((e = make_poly_tmap(&m_acc, ACC, items * 2 * R, C::LOGN))) return e;
-    if ((e = make_poly_tmap(&m_vs, V, items * D * D, C::LOGN, 32))) return e;   // staged stores of S2
+    if (!fused && (e = make_poly_tmap(&m_vs, V, items * D * D, C::LOGN, 32))) return e;   // staged stores of S2
     uint32_t* list = reinterpret_cast<uint32_t*>(ACC + items * 2 * R * C::N);
     int nl = 0;
     // FP64 stages: tail rows dealt out by warp where the shape allows it (ntt_core.cuh, NttCfg::WARPTAIL)
     using CW = typename KsWarpTailCfg<C>::type;
+    if (fused) {
+        // S1, then S2 + S3 + S4 in one kernel (the sums in tensor memory), then S5
+        if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<CW>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        if ((e = launch_ks_fused(ks, ks.keys_fused, t_target, U, ACC, items, st))) return e;
+        if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+        if (launches) *launches = 4;
+        return cudaSuccess;
+    }
     if (ks.fast_ok && ks.fp64_ok) {
         // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, 1.25q)
         if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
         if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<CW>{ks, U}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        nl += 2;
+        if (g_ks_sub_items > 0 && ks.keys_sh && (uint64_t)g_ks_sub_items < items) {
+            // S2 + S3 in rounds of a few items: V is written and read back while it is still in L2
+            for (uint64_t off = 0; off < items; off += (uint64_t)g_ks_sub_items) {
+                const uint64_t cnt = items - off < (uint64_t)g_ks_sub_items ? items - off : (uint64_t)g_ks_sub_items;
+                JobNtt1<CW> job{ks, V};
+                job.item0 = (uint32_t)(off * D * D);
+                if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, job, cnt * D * D, list, st))) return e;
+                dim3 gf(C::N / 512, ks.R, (unsigned)((cnt + 3) / 4));
+                k_ks_mac_fast<4><<<gf, 256, 0, st>>>(ks, t_target + off * D * C::N, V + off * D * D * C::N,
+                                                     ACC + off * 2 * R * C::N, (uint32_t)cnt);
+                if ((e = cudaGetLastError())) return e;
+                nl += 2;
+            }
+            if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+            if (launches) *launches = nl + 2;
+            return cudaSuccess;
+        }
         if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
-        nl += 3;
+        nl += 1;
     } else if (ks.fast_ok) {
         // S1 sees caller data: vote + deferred exact pass; the later stages read
         // words this pipeline produced (reduced by their load transforms)
@@ -522,6 +571,7 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         nl += 2;
     }
     dim3 g(C::N / 512, ks.R, (unsigned)items);
+#ifdef HB_EXPERIMENTAL_VARIANTS
     if (ks.fast_ok && ks.keys_sh && g_ks_mac_items == 1 && ks.D <= 8) {
         // register-resident keys: ~8 item slices keep the grid several waves deep
         const uint32_t slices = (uint32_t)(items < 8 ? items : 8);
@@ -531,14 +581,14 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     } else if (ks.fast_ok && ks.keys_sh && g_ks_mac_items == 2 && ks.D <= 16) {
         dim3 gw(C::N / 512, ks.R, (unsigned)((items + 1) / 2));
         k_ks_mac_wide<2><<<gw, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
-    } else if (ks.fast_ok && ks.keys_sh) {
-        if (g_ks_mac_items == 8) {
-            dim3 gf(C::N / 512, ks.R, (unsigned)((items + 7) / 8));
-            k_ks_mac_fast<8><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
-        } else {
-            dim3 gf(C::N / 512, ks.R, (unsigned)((items + 3) / 4));
-            k_ks_mac_fast<4><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
-        }
+    } else if (ks.fast_ok && ks.keys_sh && g_ks_mac_items == 8) {
+        dim3 gf(C::N / 512, ks.R, (unsigned)((items + 7) / 8));
+        k_ks_mac_fast<8><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
+    } else
+#endif
+    if (ks.fast_ok && ks.keys_sh) {
+        dim3 gf(C::N / 512, ks.R, (unsigned)((items + 3) / 4));
+        k_ks_mac_fast<4><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
     } else
         k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;

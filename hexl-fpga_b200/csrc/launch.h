@@ -26,6 +26,7 @@ struct KsDev {
     const TwPair* keys_sh;  // same index space: {key mod q_i, Shoup factor}; null if !fast_ok
     const uint64_t* msf;    // [K] modswitch_factors[i] mod q_i
     const uint64_t* msf_p;  // [K] Shoup factors of msf
+    const void* keys_fused; // key quads in the layout of the fused kernel (keyswitch_fused.cu), or null
 };
 
 bool ntt_shape_supported(uint32_t logn);
@@ -81,6 +82,24 @@ cudaError_t launch_ntt_inv_mul(uint64_t* data, const uint64_t* other, const ModT
 cudaError_t launch_ntt_inv(uint64_t* data, const ModTab& tab, uint32_t logn, uint64_t batch, int variant,
                            uint32_t* list, cudaStream_t st, int* launches);
 
+// single-launch polynomial multiply (polymul_fused.cu): N = 16384, FP64-contract moduli
+extern int g_polymul_fused;
+bool polymul_fused_available(const ModTab& tab, uint32_t logn);
+cudaError_t launch_polymul_fused(uint64_t* res, const uint64_t* a, const uint64_t* b, const ModTab& tab, uint64_t batch,
+                                 uint32_t* list, cudaStream_t st);
+cudaError_t launch_polymul_deferred(uint64_t* res, uint64_t* tb, const uint64_t* a, const uint64_t* b, const ModTab& tab,
+                                    uint64_t batch, uint32_t* list, cudaStream_t st);
+
+// N = 32768 (ntt_big.cu): table split, the streaming first / last stage, the half-size sub-transforms
+cudaError_t launch_big_split(bool fwd, const uint64_t* tab0, const uint64_t* tab1, uint64_t* sub, uint32_t n_half,
+                             cudaStream_t st);
+cudaError_t launch_big_stage0_fwd(uint64_t* data, const uint64_t* roots, const uint64_t* precon, uint64_t q,
+                                  uint32_t n_half, uint64_t batch, cudaStream_t st);
+cudaError_t launch_big_last_inv(uint64_t* data, const uint64_t* inv_roots, uint64_t q, uint64_t inv_n, uint64_t inv_n_w,
+                                uint32_t n_half, uint64_t batch, cudaStream_t st);
+cudaError_t launch_ntt_half(bool fwd, uint64_t* data, const ModTab& tab, uint32_t logn_half, uint64_t batch, int variant,
+                            uint32_t* list, cudaStream_t st, int* launches, uint32_t half);
+
 size_t dyadic_scratch_bytes(uint64_t n_moduli, uint64_t batch, int moduli_per_item);
 // `scratch`: dyadic_scratch_bytes() of device memory, 16-byte aligned (per-modulus reciprocals)
 cudaError_t launch_dyadic(uint64_t* res, const uint64_t* op1, const uint64_t* op2, uint64_t n,
@@ -97,6 +116,15 @@ size_t ks_scratch_words_per_item(const KsDev& ks);
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);
 cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
                             uint64_t* scratch, cudaStream_t st, int* launches);
+
+// fused S2 + S3 + S4 (keyswitch_fused.cu)
+extern int g_ks_fused;
+extern int g_ks_sub_items;
+bool ks_fused_available(const KsDev& ks, const void* keys_f);
+size_t ks_fused_key_bytes(const KsDev& ks);
+cudaError_t launch_ks_prepare_keys_fused(const KsDev& ks, void* out, cudaStream_t st);
+cudaError_t launch_ks_fused(const KsDev& ks, const void* keys_f, const uint64_t* t_target, const uint64_t* U,
+                            uint64_t* ACC, uint64_t items, cudaStream_t st);
 
 int persistent_grid(const void* kernel, int threads, size_t smem, uint64_t items);
 

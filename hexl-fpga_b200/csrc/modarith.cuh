@@ -67,16 +67,17 @@ HB_HD void inv_bfly(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wp,
 
 // Last inverse stage fused with the n^-1 scaling, ntt.cpp:640-657 /
 // device/inv_ntt.cpp:400-437.  Outputs are fully reduced to [0,q).
+// lazy_out: output_mod_factor = 2 of the reference (ntt.cpp:648-657): the words stay in [0, 2q)
 HB_HD void inv_last_bfly(uint64_t& X, uint64_t& Y, uint64_t inv_n,
                          uint64_t inv_n_p, uint64_t inv_n_w, uint64_t inv_n_w_p,
-                         uint64_t q, uint64_t twoq) {
+                         uint64_t q, uint64_t twoq, bool lazy_out = false) {
     uint64_t tx = X + Y;
     tx -= (tx >= twoq) ? twoq : 0;
     uint64_t ty = X + twoq - Y;
     uint64_t x = mul_lazy(tx, inv_n, inv_n_p, q);
     uint64_t y = mul_lazy(ty, inv_n_w, inv_n_w_p, q);
-    X = x - ((x >= q) ? q : 0);
-    Y = y - ((y >= q) ? q : 0);
+    X = x - ((x >= q && !lazy_out) ? q : 0);
+    Y = y - ((y >= q && !lazy_out) ? q : 0);
 }
 
 // ---------------------------------------------------------------------------

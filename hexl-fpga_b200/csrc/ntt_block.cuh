@@ -31,6 +31,7 @@ struct ModTab {
     const TwPair* ftwd;
     const TwPair* itwd;
     uint32_t fp64_ok;       // 2^36 <= q <= 2^53 / 3 and the tables above are there
+    uint32_t lazy_out;      // the caller wants the lazy words of the reference's output_mod_factor 4 / 2: exact kernels only
 };
 
 // ---- load transforms (applied to each word as it enters the transform) ----
@@ -610,7 +611,7 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
                 done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             }
         } else {
-            const ExactArith a = {t.q, t.twoq, t.sc};
+            const ExactArith a = {t.q, t.twoq, t.sc, t.lazy_out};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
         }
@@ -882,6 +883,7 @@ HB_D void ntt_persistent_small(const CUtensorMap* tmap, uint64_t* data, const Mo
     }
 }
 
+#ifdef HB_EXPERIMENTAL_VARIANTS
 // ---------------------------------------------------------------------------
 // small-modulus path, second generation ("small2"): no landing buffer
 // ---------------------------------------------------------------------------
@@ -1248,6 +1250,8 @@ HB_D void ntt_persistent_small3(const CUtensorMap* tmap, uint64_t* data, const M
         if (gtid == 0 && item_at(j + 1) < n_items) land(j + 1);
     }
 }
+
+#endif  // HB_EXPERIMENTAL_VARIANTS
 
 // shared memory of the FP64 kernels of the plain batched calls (head-pass twiddles included when they fit)
 template <class C>

@@ -206,16 +206,18 @@ struct ExactArith {
     HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     uint64_t q, twoq;
     InvScale sc;
+    uint32_t lazy_out;     // output_mod_factor 4 (forward) / 2 (inverse) of the reference: no final correction
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly(X, Y, t.w, t.wp, q, twoq); }
     HB_HD uint64_t fwd_final(uint64_t x) const {      // ntt.cpp:535-546
+        if (lazy_out) return x;
         x -= (x >= twoq) ? twoq : 0;
         x -= (x >= q) ? q : 0;
         return x;
     }
     HB_HD void inv(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv_bfly(X, Y, t.w, t.wp, q, twoq); }
     HB_HD void inv_last(uint64_t& X, uint64_t& Y) const {
-        inv_last_bfly(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, q, twoq);
+        inv_last_bfly(X, Y, sc.inv_n, sc.inv_n_p, sc.inv_n_w, sc.inv_n_w_p, q, twoq, lazy_out != 0);
     }
     static constexpr bool kLazyInv = false;
     template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv(X, Y, t); }

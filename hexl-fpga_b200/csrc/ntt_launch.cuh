@@ -17,19 +17,25 @@ struct JobPlain {
     static constexpr bool kOneModulus = true;   // every item of a launch is transformed under tab
     uint64_t* data;
     ModTab tab;
-    HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
+    // item i is polynomial offset + i * stride of the array (1, 0: a plain batch; 2, h: the half-size
+    // sub-transforms of an N = 2 * C::N transform, ntt_big.cu)
+    uint32_t stride = 1, offset = 0;
+    HB_D uint32_t poly(uint32_t item) const { return offset + item * stride; }
+    HB_D uint32_t src_row(uint32_t item) const { return poly(item) * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t) const { return tab; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
 };
 template <class C>
 struct JobFwd : JobPlain<C> {
     HB_D OfRows of(uint32_t item, const CUtensorMap* smap) const {
-        return OfRows{this->data + (size_t)item * C::N, smap, item * (C::N / 16)};
+        return OfRows{this->data + (size_t)this->poly(item) * C::N, smap, this->poly(item) * (C::N / 16)};
     }
 };
 template <class C>
 struct JobInv : JobPlain<C> {
-    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
+    HB_D OfWords of(uint32_t item, const CUtensorMap*) const {
+        return OfWords{this->data + (size_t)this->poly(item) * C::N};
+    }
 };
 
 template <class C, int MODE, bool FP64 = false>
@@ -62,6 +68,14 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv_mul(const __grid
     ntt_persistent<C, false, MODE, JobInvMul<C>, false, FP64>(&tmap, nullptr, job, n_items, nullptr);
 }
 
+// the same over the items of a deferred list, reference op sequence (polymul_fused.cu)
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv_mul_list(const __grid_constant__ CUtensorMap tmap,
+                                                                        const JobInvMul<C> job, uint32_t n_items,
+                                                                        uint32_t* list) {
+    ntt_persistent<C, false, kExactList, JobInvMul<C>>(&tmap, nullptr, job, n_items, list);
+}
+
 // small-modulus kernels (q < 2^30): uint32 arithmetic, see ntt_block.cuh
 // smap32: 3-D store map of the forward epilogue (use_tma_store = 0: plain coalesced stores)
 template <class C64, class C32, bool FWD, int MODE>
@@ -73,6 +87,10 @@ __global__ void __launch_bounds__(C32::NT, 1) k_ntt_small(const __grid_constant_
                                               (FWD && use_tma_store) ? &smap32 : nullptr);
 }
 
+// Kernel variants that were built, verified and MEASURED SLOWER than the defaults are only
+// compiled with -DHB_EXPERIMENTAL_VARIANTS (make EXPERIMENTAL=1): small_path 2 / 3, the lazy inverse,
+// the 16-words-per-thread configuration at N >= 8192, ks_mac_items 1 / 2 / 8.
+#ifdef HB_EXPERIMENTAL_VARIANTS
 // second generation: no landing buffer, two CTAs per SM (ntt_block.cuh)
 template <class C32, bool FWD, int MODE>
 __global__ void __launch_bounds__(C32::NT, 2) k_ntt_small2(uint64_t* data, const ModTab tab, uint32_t n_items,
@@ -86,6 +104,7 @@ __global__ void __launch_bounds__(1024, 1) k_ntt_small3(const __grid_constant__ 
                                                        const ModTab tab, uint32_t n_items, uint32_t* list) {
     ntt_persistent_small3<C32, FWD, MODE>(&tmap, data, tab, n_items, list);
 }
+#endif  // HB_EXPERIMENTAL_VARIANTS
 
 // the configuration with warp-dealt tail rows, where the shape allows it
 template <class C>
@@ -123,13 +142,15 @@ static cudaError_t launch_dep(void (*kern)(KArgs...), unsigned grid, unsigned bl
 
 template <class C, bool FWD, int MODE>
 static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap, uint64_t* base, const ModTab& tab,
-                               uint64_t cnt, uint32_t* list, cudaStream_t st) {
+                               uint64_t cnt, uint32_t* list, cudaStream_t st, uint32_t stride = 1, uint32_t offset = 0) {
     const size_t smem = ntt_smem_bytes<C>();
     cudaError_t e = cudaSuccess;
     if constexpr (FWD) {
         JobFwd<C> job;
         job.data = base;
         job.tab = tab;
+        job.stride = stride;
+        job.offset = offset;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
             using CW = typename WarpTailCfg<C>::type;
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
@@ -139,6 +160,8 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 JobFwd<CW> jobw;
                 jobw.data = base;
                 jobw.tab = tab;
+                jobw.stride = stride;
+                jobw.offset = offset;
                 e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st, tmap, smap, jobw, (uint32_t)cnt, list);
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
@@ -157,6 +180,8 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         JobInv<C> job;
         job.data = base;
         job.tab = tab;
+        job.stride = stride;
+        job.offset = offset;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
             using CW = typename WarpTailCfg<C>::type;
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
@@ -166,6 +191,8 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 JobInv<CW> jobw;
                 jobw.data = base;
                 jobw.tab = tab;
+                jobw.stride = stride;
+                jobw.offset = offset;
                 e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st, tmap, jobw, (uint32_t)cnt, list);
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
@@ -176,12 +203,14 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smemd, cnt), C::NT, smemd, st, tmap, job, (uint32_t)cnt, list);
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
+#ifdef HB_EXPERIMENTAL_VARIANTS
             if (tab.inv_lazy_ok) {   // q < 2^52: butterflies without per-stage corrections
                 auto kern = k_ntt_inv<C, MODE, true>;
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
                 e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C::NT, smem, cnt), C::NT, smem, st, tmap, job, (uint32_t)cnt, list);
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
+#endif
         }
         auto kern = k_ntt_inv<C, MODE>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return e;
@@ -195,24 +224,26 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
 // `src`: where the polynomials are read from (nullptr: in place, from `data`)
 template <class C, bool FWD>
 static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch, bool trust, uint32_t* list,
-                              cudaStream_t st, int* launches, const uint64_t* src = nullptr) {
+                              cudaStream_t st, int* launches, const uint64_t* src = nullptr, uint32_t stride = 1,
+                              uint32_t offset = 0) {
     CUtensorMap tmap, smap;
     cudaError_t e;
     // the tensor map's row coordinate is 32 bits
     const uint64_t kMaxPolys = ((1ull << 32) - 1) / (C::N / 16);
-    if (batch > kMaxPolys) return cudaErrorInvalidValue;
-    if ((e = make_poly_tmap(&tmap, src ? src : data, batch, C::LOGN)) != cudaSuccess) return e;
-    if ((e = make_poly_tmap(&smap, data, batch, C::LOGN, 32)) != cudaSuccess) return e;
-    const bool fast = FWD ? tab.fwd_fast_ok : tab.inv_fast_ok;
+    if (batch * stride > kMaxPolys) return cudaErrorInvalidValue;
+    if ((e = make_poly_tmap(&tmap, src ? src : data, batch * stride, C::LOGN)) != cudaSuccess) return e;
+    if ((e = make_poly_tmap(&smap, data, batch * stride, C::LOGN, 32)) != cudaSuccess) return e;
+    const bool fast = (FWD ? tab.fwd_fast_ok : tab.inv_fast_ok) && !tab.lazy_out;
     if (!fast) {
         *launches += 1;
-        return launch_mode<C, FWD, kExactAll>(tmap, smap, data, tab, batch, list, st);
+        return launch_mode<C, FWD, kExactAll>(tmap, smap, data, tab, batch, list, st, stride, offset);
     }
     if constexpr (C::LOGN == 14 && C::LOGE == 5) {
         // q < 2^30: the 32-bit kernels (out-of-contract items still go to the
         // 64-bit exact kernel through the deferred list)
-        if (tab.small_ok) {
+        if (tab.small_ok && stride == 1) {
             using C32 = NttCfg<14, 5, 5>;
+#ifdef HB_EXPERIMENTAL_VARIANTS
             if (tab.small_ok == 3) {
                 const size_t smem3 = Small3Plan<C32>::BYTES;
                 int sms = 0, dev = 0;
@@ -232,7 +263,7 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
                 kern<<<grid3, 1024, smem3, st>>>(tmap, data, tab, (uint32_t)batch, list);
                 if ((e = cudaGetLastError())) return e;
                 *launches += 2;
-                return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+                return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st, stride, offset);
             }
             if (tab.small_ok == 2) {
                 const size_t smem2 = Small2Plan<C32>::BYTES;
@@ -251,8 +282,9 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
                     data, tab, (uint32_t)batch, list);
                 if ((e = cudaGetLastError())) return e;
                 *launches += 2;
-                return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+                return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st, stride, offset);
             }
+#endif
             const size_t smem = SmallPlan<C32>::BYTES;
             CUtensorMap smap32;
             const int tma_store = FWD && g_small_tma_store;
@@ -269,20 +301,21 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
             e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, C32::NT, smem, batch), C32::NT, smem, st, tmap, smap32, data, tab, (uint32_t)batch, list, tma_store);
             if (e != cudaSuccess || (e = cudaGetLastError())) return e;
             *launches += 2;
-            return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+            return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st, stride, offset);
         }
     }
     if (trust) {
         *launches += 1;
-        return launch_mode<C, FWD, kFastTrust>(tmap, smap, data, tab, batch, list, st);
+        return launch_mode<C, FWD, kFastTrust>(tmap, smap, data, tab, batch, list, st, stride, offset);
     }
     if ((e = launch_mode<C, FWD, kFastVote>(tmap, smap, data, tab, batch, list, st))) return e;
     // polynomials with out-of-contract words (none in normal use): exact pass
     // over the deferred list; exits at once when the list is empty
     *launches += 2;
-    return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st);
+    return launch_mode<C, FWD, kExactList>(tmap, smap, data, tab, batch, list, st, stride, offset);
 }
 
+#ifdef HB_EXPERIMENTAL_VARIANTS
 #define HB_DISPATCH_CFG(logn, variant, CALL)                                   \
     switch (logn) {                                                            \
         case 10: { using C = NttCfg<10, 4>; CALL; } break;                     \
@@ -298,5 +331,21 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
             break;                                                             \
         default: break;                                                        \
     }
+#else
+// default build: N = 16384 only with 32 words per thread (N = 8192 keeps both: the plain calls use 32
+// words per thread, the keyswitch stages 16)
+#define HB_DISPATCH_CFG(logn, variant, CALL)                                   \
+    switch (logn) {                                                            \
+        case 10: { using C = NttCfg<10, 4>; CALL; } break;                     \
+        case 11: { using C = NttCfg<11, 4>; CALL; } break;                     \
+        case 12: { using C = NttCfg<12, 4>; CALL; } break;                     \
+        case 13:                                                               \
+            if (((variant) & 1) == 1) { using C = NttCfg<13, 5>; CALL; }       \
+            else { using C = NttCfg<13, 4>; CALL; }                            \
+            break;                                                             \
+        case 14: { using C = NttCfg<14, 5>; CALL; } break;                     \
+        default: break;                                                        \
+    }
+#endif
 
 }  // namespace hb

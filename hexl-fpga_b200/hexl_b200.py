@@ -37,6 +37,8 @@ _SIGNATURES = {
     "hexl_b200_device_count": ([], C.c_int),
     "hexl_b200_ntt_fwd": ([vp, vp, vp, u64, u64, u64, vp], C.c_int),
     "hexl_b200_ntt_inv": ([vp, vp, vp, u64, u64, u64, u64, u64, vp], C.c_int),
+    "hexl_b200_ntt_fwd_ex": ([vp, vp, vp, u64, u64, u64, u64, u64, vp], C.c_int),
+    "hexl_b200_ntt_inv_ex": ([vp, vp, vp, u64, u64, u64, u64, u64, u64, u64, vp], C.c_int),
     "hexl_b200_dyadic_multiply": ([vp, vp, vp, u64, vp, u64, u64, C.c_int, vp], C.c_int),
     "hexl_b200_poly_multiply": ([vp, vp, vp, vp, vp, vp, vp, u64, u64, u64, u64, u64, vp], C.c_int),
     "hexl_b200_ks_plan_create": ([C.POINTER(vp), u64, u64, u64, u64, u64, vp, vp, vp, vp], C.c_int),
@@ -156,17 +158,18 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def ntt_fwd(operand, roots, precon, q, n):
-    """In-place batched forward NTT of `operand` ([batch, n] on the GPU)."""
+def ntt_fwd(operand, roots, precon, q, n, input_mod_factor=1, output_mod_factor=1):
+    """In-place batched forward NTT of `operand` ([batch, n] on the GPU); mod factors as in the reference's
+    NTT::ComputeForward (tests/test_utils/ntt.cpp:442-455)."""
     batch = operand.numel() // n
-    _check(lib().hexl_b200_ntt_fwd(_dptr(operand), _dptr(roots), _dptr(precon), q, n, batch, _stream()),
-           "ntt_fwd")
+    _check(lib().hexl_b200_ntt_fwd_ex(_dptr(operand), _dptr(roots), _dptr(precon), q, n, batch, input_mod_factor,
+                                      output_mod_factor, _stream()), "ntt_fwd")
 
 
-def ntt_inv(operand, inv_roots, precon_inv, q, inv_n, inv_n_w, n):
+def ntt_inv(operand, inv_roots, precon_inv, q, inv_n, inv_n_w, n, input_mod_factor=1, output_mod_factor=1):
     batch = operand.numel() // n
-    _check(lib().hexl_b200_ntt_inv(_dptr(operand), _dptr(inv_roots), _dptr(precon_inv), q, inv_n, inv_n_w,
-                                   n, batch, _stream()), "ntt_inv")
+    _check(lib().hexl_b200_ntt_inv_ex(_dptr(operand), _dptr(inv_roots), _dptr(precon_inv), q, inv_n, inv_n_w, n, batch,
+                                      input_mod_factor, output_mod_factor, _stream()), "ntt_inv")
 
 
 def poly_multiply(result, a, b, roots, precon, inv_roots, precon_inv, q, inv_n, inv_n_w, n):

@@ -428,6 +428,7 @@ struct Runtime {
     uint64_t batch_cap[OP_COUNT]{};     // BATCH_SIZE_* (0 = a fair share of what is queued / promised)
     bool stop = false;
     size_t idle_workers = 0;            // workers currently gathering (not executing a batch)
+    uint64_t pop_gen = 0;               // bumped whenever a worker takes requests off the queue
     int error[OP_COUNT]{};              // first asynchronous failure per operation, reported once
     std::string error_msg[OP_COUNT];
     std::vector<std::thread> workers;
@@ -661,42 +662,56 @@ int run_keyswitch_batch(DeviceCtx& c, const std::vector<Request>& rs) {
         });
 }
 
-// Number of requests at the head of the queue that may run as one batch: compatible with the first, and no
-// output range touched twice (two queued calls that accumulate into the same `result`, or transform the
-// same operand, must run one after the other -- the reference's host loop is sequential, fpga.cpp:441-475).
-size_t head_run(const std::deque<Request>& q, size_t cap, bool* fenced) {
-    *fenced = false;
+// Incremental scan of the head of the queue: how many requests may run as one batch -- compatible with
+// the first, and no output range touched twice (two queued calls that accumulate into the same `result`,
+// or transform the same operand, must run one after the other: the reference's host loop is sequential,
+// fpga.cpp:441-475).  The scan resumes where it stopped as long as nobody has popped the queue in
+// between (Runtime::pop_gen), so gathering a run of n requests costs O(n log n) in total, not per wake-up.
+struct HeadScan {
+    uint64_t gen = ~(uint64_t)0;
     size_t run = 0;
+    bool fenced = false;
     std::set<uintptr_t> starts;
-    const Request& f = q.front();
-    const uintptr_t len = f.out_words() * 8;
-    for (const Request& r : q) {
-        if (!compatible(f, r)) {
-            *fenced = true;
-            break;
+    void update(const std::deque<Request>& q, uint64_t pop_gen) {
+        if (gen != pop_gen) {
+            gen = pop_gen;
+            run = 0;
+            fenced = false;
+            starts.clear();
         }
-        const uintptr_t a = (uintptr_t)r.out;
-        auto hi = starts.lower_bound(a);
-        bool clash = (hi != starts.end() && *hi < a + len);
-        if (!clash && hi != starts.begin()) clash = *std::prev(hi) + len > a;
-        if (clash) {
-            *fenced = true;
-            break;
+        if (fenced || q.empty()) return;
+        const Request& f = q.front();
+        const uintptr_t len = f.out_words() * 8;
+        while (run < q.size()) {
+            const Request& r = q[run];
+            if (!compatible(f, r)) {
+                fenced = true;
+                return;
+            }
+            const uintptr_t a = (uintptr_t)r.out;
+            auto hi = starts.lower_bound(a);
+            bool clash = (hi != starts.end() && *hi < a + len);
+            if (!clash && hi != starts.begin()) clash = *std::prev(hi) + len > a;
+            if (clash) {
+                fenced = true;
+                return;
+            }
+            starts.insert(hi, a);
+            ++run;
         }
-        starts.insert(a);
-        if (++run == cap) break;
     }
-    return run;
-}
+};
 
 void worker_main(Runtime* rt, DeviceCtx* ctx) {
     cudaSetDevice(ctx->dev);
     const size_t n_workers = rt->ctxs.size();
     std::vector<Request> batch;
+    HeadScan scan;
     for (;;) {
         batch.clear();
         {
             std::unique_lock<std::mutex> lk(rt->mu);
+            int quiet_polls = 0;
             rt->idle_workers++;
             rt->cv_work.wait(lk, [&] { return rt->stop || !rt->queue.empty(); });
             if (rt->queue.empty()) return;  // stop requested and drained
@@ -708,8 +723,9 @@ void worker_main(Runtime* rt, DeviceCtx* ctx) {
             for (;;) {
                 if (rt->queue.empty()) break;
                 const Op op = rt->queue.front().op;
-                bool fenced = false;
-                const size_t run_all = head_run(rt->queue, (size_t)1 << 20, &fenced);
+                scan.update(rt->queue, rt->pop_gen);
+                const size_t run_all = scan.run;
+                const bool fenced = scan.fenced;
                 // share of one worker: BATCH_SIZE_* when set, else an equal part, among the workers that are
                 // free right now, of what this run will be (queued + still promised), so that NUM_DEV
                 // workers all get work without any tuning
@@ -720,14 +736,18 @@ void worker_main(Runtime* rt, DeviceCtx* ctx) {
                     cap = n_workers > 1 ? std::max<size_t>(1, (total + share - 1) / share) : (size_t)1 << 20;
                 }
                 const size_t run = std::min(run_all, cap);
-                if (run == cap || fenced || rt->expected[op] == 0 || rt->stop || quiet) {
+                if (run >= cap || fenced || rt->expected[op] == 0 || rt->stop || quiet) {
                     batch.assign(rt->queue.begin(), rt->queue.begin() + run);
                     rt->queue.erase(rt->queue.begin(), rt->queue.begin() + run);
+                    rt->pop_gen++;
                     break;
                 }
+                // the producer is still submitting this run: poll (it does not wake us for every request)
                 const size_t before = rt->submitted[op];
-                rt->cv_work.wait_for(lk, std::chrono::milliseconds(2));
-                quiet = rt->submitted[op] == before;   // producer went quiet: run what is there
+                rt->cv_work.wait_for(lk, std::chrono::microseconds(quiet_polls < 8 ? 100 : 500));
+                ++quiet_polls;
+                quiet = rt->submitted[op] == before && quiet_polls >= 4;   // nothing new for a while: run what is there
+                if (rt->submitted[op] != before) quiet_polls = 0;
             }
             rt->idle_workers--;
             rt->cv_space.notify_all();
@@ -784,16 +804,20 @@ int take_error(Runtime* rt, Op op) {
 int submit(const Request& r) {
     Runtime* rt = g_rt;
     if (!rt) return fail(HEXL_B200_ENODEV, "%s: acquire_FPGA_resources() has not been called", kOpName[r.op]);
-    bool sync;
+    bool sync, wake;
     {
         std::unique_lock<std::mutex> lk(rt->mu);
         rt->cv_space.wait(lk, [&] { return rt->queue.size() < rt->capacity; });
+        const bool was_empty = rt->queue.empty();
         rt->queue.push_back(r);
         rt->submitted[r.op]++;
         sync = rt->worksize[r.op] <= 1;   // worksize 1 => synchronous call (fpga_int.cpp:190-192)
         if (rt->expected[r.op]) rt->expected[r.op]--;
+        // a worker that is gathering this run polls the queue; wake the workers only for what changes
+        // their decision: the first request of a run, the last one, and synchronous calls
+        wake = was_empty || sync || rt->expected[r.op] == 0;
     }
-    rt->cv_work.notify_all();
+    if (wake) rt->cv_work.notify_all();
     if (sync) {
         std::unique_lock<std::mutex> lk(rt->mu);
         rt->cv_done.wait(lk, [&] { return rt->completed[r.op] == rt->submitted[r.op]; });
@@ -955,9 +979,9 @@ int hexl_b200_host_keyswitch(uint64_t* result, const uint64_t* t_target_iter_ptr
 
 int hexl_b200_host_ntt(uint64_t* operand, const uint64_t* roots, const uint64_t* precon, uint64_t q,
                        uint64_t n) {
-    // reference check: host/src/ntt.cpp:18-26 (n == 16384); we accept 2^10..2^14
+    // reference check: host/src/ntt.cpp:18-26 (n == 16384); we accept 2^10..2^15
     if (!operand || !roots || !precon) return fail(HEXL_B200_EINVAL, "NTT: NULL pointer");
-    if (!pow2_in(n, 1024, 16384)) return fail(HEXL_B200_EINVAL, "NTT: n must be a power of two in [1024,16384]");
+    if (!pow2_in(n, 1024, 32768)) return fail(HEXL_B200_EINVAL, "NTT: n must be a power of two in [1024,32768]");
     if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "NTT: modulus out of range");
     Request r;
     r.op = OP_NTT;
@@ -969,7 +993,7 @@ int hexl_b200_host_intt(uint64_t* operand, const uint64_t* inv_roots, const uint
                         uint64_t inv_n, uint64_t inv_n_w, uint64_t n) {
     // reference check: host/src/intt.cpp:18-27
     if (!operand || !inv_roots || !precon_inv) return fail(HEXL_B200_EINVAL, "INTT: NULL pointer");
-    if (!pow2_in(n, 1024, 16384)) return fail(HEXL_B200_EINVAL, "INTT: n must be a power of two in [1024,16384]");
+    if (!pow2_in(n, 1024, 32768)) return fail(HEXL_B200_EINVAL, "INTT: n must be a power of two in [1024,32768]");
     if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "INTT: modulus out of range");
     if (inv_n >= q || inv_n_w >= q) return fail(HEXL_B200_EINVAL, "INTT: inv_n / inv_n_w not reduced");
     Request r;

@@ -67,6 +67,20 @@ int hexl_b200_ntt_inv(uint64_t* d_operand, const uint64_t* d_inv_root_of_unity_p
                       const uint64_t* d_precon_inv_root_of_unity_powers, uint64_t coeff_modulus,
                       uint64_t inv_n, uint64_t inv_n_w, uint64_t n, uint64_t batch, void* stream);
 
+/* The same with the mod factors of the reference's own NTT class (tests/test_utils/ntt.cpp:442-470,
+ * hetest::utils::NTT::ComputeForward / ComputeInverse): input_mod_factor in {1, 2, 4} (forward) / {1, 2}
+ * (inverse) is the caller's promise about the input range (operand < input_mod_factor * q; checked by
+ * the range vote like every input); output_mod_factor = 4 (forward) / 2 (inverse) skips the final
+ * correction and returns the lazy words of the Harvey butterflies exactly as the reference leaves them
+ * (ntt.cpp:535-546, 648-657); 1 = fully reduced, what hexl_b200_ntt_fwd / _inv do. */
+int hexl_b200_ntt_fwd_ex(uint64_t* d_operand, const uint64_t* d_root_of_unity_powers,
+                         const uint64_t* d_precon_root_of_unity_powers, uint64_t coeff_modulus, uint64_t n,
+                         uint64_t batch, uint64_t input_mod_factor, uint64_t output_mod_factor, void* stream);
+int hexl_b200_ntt_inv_ex(uint64_t* d_operand, const uint64_t* d_inv_root_of_unity_powers,
+                         const uint64_t* d_precon_inv_root_of_unity_powers, uint64_t coeff_modulus, uint64_t inv_n,
+                         uint64_t inv_n_w, uint64_t n, uint64_t batch, uint64_t input_mod_factor,
+                         uint64_t output_mod_factor, void* stream);
+
 /* Batched negacyclic polynomial multiply  result = a * b  mod (x^n + 1, q):
  * INTT(NTT(a) (.) NTT(b)) with the dyadic product fused into the first pass
  * of the inverse transform (no HBM round trip of the product).  The step on

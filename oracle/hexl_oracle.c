@@ -235,6 +235,31 @@ static inline uint64_t mul_lazy(uint64_t x, uint64_t y, uint64_t y_precon,
 
 /* tests/test_utils/ntt.cpp:474-548 (ForwardTransformToBitReverse64 with
  * output_mod_factor == 1); same op order as device/fwd_ntt.cpp:282-386. */
+/* tests/test_utils/ntt.cpp:474-548 with output_mod_factor = 4: the final correction loop (:535-546)
+ * is skipped and the lazy words in [0, 4q) are the result. */
+void ho_fwd_ntt_lazy(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* roots,
+                     const uint64_t* precon) {
+    uint64_t twice_q = q << 1;
+    uint64_t t = n >> 1;
+    for (uint64_t m = 1; m < n; m <<= 1) {
+        uint64_t j1 = 0;
+        for (uint64_t i = 0; i < m; ++i) {
+            uint64_t W = roots[m + i], Wp = precon[m + i];
+            uint64_t* X = a + j1;
+            uint64_t* Y = X + t;
+            for (uint64_t j = 0; j < t; ++j) {
+                uint64_t x = X[j];
+                uint64_t tx = (x >= twice_q) ? x - twice_q : x;
+                uint64_t T = mul_lazy(Y[j], W, Wp, q);
+                X[j] = tx + T;
+                Y[j] = tx + twice_q - T;
+            }
+            j1 += t << 1;
+        }
+        t >>= 1;
+    }
+}
+
 void ho_fwd_ntt(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* roots,
                 const uint64_t* precon) {
     uint64_t twice_q = q << 1;
@@ -323,6 +348,42 @@ void ho_inv_ntt(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* inv_roots,
     }
     for (uint64_t i = 0; i < n; ++i)
         if (a[i] >= q) a[i] -= q;
+}
+
+/* tests/test_utils/ntt.cpp:580-659 with output_mod_factor = 2: the final loop (:648-657) is skipped and
+ * the words stay in [0, 2q). */
+void ho_inv_ntt_lazy(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* inv_roots,
+                     const uint64_t* precon_inv, uint64_t inv_n, uint64_t inv_n_w) {
+    uint64_t twice_q = q << 1;
+    uint64_t t = 1;
+    uint64_t r = 1;
+    for (uint64_t m = n >> 1; m > 1; m >>= 1) {
+        uint64_t j1 = 0;
+        for (uint64_t i = 0; i < m; ++i, ++r) {
+            uint64_t W = inv_roots[r], Wp = precon_inv[r];
+            uint64_t* X = a + j1;
+            uint64_t* Y = X + t;
+            for (uint64_t j = 0; j < t; ++j) {
+                uint64_t tx = X[j] + Y[j];
+                uint64_t ty = X[j] + twice_q - Y[j];
+                X[j] = (tx >= twice_q) ? tx - twice_q : tx;
+                Y[j] = mul_lazy(ty, W, Wp, q);
+            }
+            j1 += t << 1;
+        }
+        t <<= 1;
+    }
+    uint64_t inv_n_p = ho_mult_factor64(inv_n, q);
+    uint64_t inv_n_w_p = ho_mult_factor64(inv_n_w, q);
+    uint64_t* X = a;
+    uint64_t* Y = a + (n >> 1);
+    for (uint64_t j = 0; j < (n >> 1); ++j) {
+        uint64_t tx = X[j] + Y[j];
+        if (tx >= twice_q) tx -= twice_q;
+        uint64_t ty = X[j] + twice_q - Y[j];
+        X[j] = mul_lazy(tx, inv_n, inv_n_p, q);
+        Y[j] = mul_lazy(ty, inv_n_w, inv_n_w_p, q);
+    }
 }
 
 void ho_fwd_ntt_batch(uint64_t* a, uint64_t batch, uint64_t n, uint64_t q,

@@ -136,6 +136,12 @@ int ho_keyswitch_alt_batch(uint64_t* result, const uint64_t* t_target,
                            const uint64_t* const* k_switch_keys,
                            const uint64_t* modswitch_factors, int threads);
 
+/* forward / inverse transform with the reference's output_mod_factor = 4 / 2: no final correction,
+ * the lazy words of the Harvey butterflies are the result (tests/test_utils/ntt.cpp:535-546, 648-657) */
+void ho_fwd_ntt_lazy(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* roots, const uint64_t* precon);
+void ho_inv_ntt_lazy(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* inv_roots, const uint64_t* precon_inv,
+                     uint64_t inv_n, uint64_t inv_n_w);
+
 /* ---- helpers shared by tests ---- */
 /* 64-bit FNV-1a over the little-endian bytes of v[0..n). */
 uint64_t ho_fnv1a(const uint64_t* v, size_t n);

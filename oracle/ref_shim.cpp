@@ -57,6 +57,17 @@ void ref_inv_ntt(uint64_t* a, uint64_t n, uint64_t q) {
     ntt.ComputeInverse(a, a, 1, 1);
 }
 
+// the reference's mod factors (ntt.cpp:442-470): output_mod_factor 4 (forward) / 2 (inverse) leaves the
+// lazy words of the butterflies as the result
+void ref_fwd_ntt_factors(uint64_t* a, uint64_t n, uint64_t q, uint64_t in_f, uint64_t out_f) {
+    NTT::NTTImpl ntt(n, q);
+    ntt.ComputeForward(a, a, in_f, out_f);
+}
+void ref_inv_ntt_factors(uint64_t* a, uint64_t n, uint64_t q, uint64_t in_f, uint64_t out_f) {
+    NTT::NTTImpl ntt(n, q);
+    ntt.ComputeInverse(a, a, in_f, out_f);
+}
+
 // Batch over caller-supplied tables (free functions ntt.cpp:474-548, 580-659);
 // OpenMP over items -- the timing loop of the CPU baseline.
 void ref_fwd_ntt_batch(uint64_t* a, uint64_t batch, uint64_t n, uint64_t q,

@@ -27,3 +27,14 @@ def acquired(hb):
     hb.acquire_FPGA_resources()
     yield hb
     hb.release_FPGA_resources()
+
+
+def set_variant(hb, name, value):
+    """set_option for kernel variants that only exist in builds with `make EXPERIMENTAL=1` (they measured
+    slower than the defaults): skips the test when the variant is compiled out."""
+    try:
+        hb.set_option(name, value)
+    except hb.HexlB200Error as e:
+        if "EXPERIMENTAL" in str(e):
+            pytest.skip(f"{name}={value} is compiled out of the default build")
+        raise

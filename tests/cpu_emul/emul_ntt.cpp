@@ -132,7 +132,7 @@ int run(uint64_t q, int garbage) {
     if (garbage == 5) for (uint64_t i = 0; i < n; ++i) a[i] = 2 * q - 1;   // worst growth of the lazy inverse sums
     uint64_t inv_n = ho_inv_mod(n % q, q), inv_n_w = ho_mul_mod(inv_n, ir[n - 1], q);
     InvScale sc = {inv_n, ho_mult_factor64(inv_n, q), inv_n_w, ho_mult_factor64(inv_n_w, q)};
-    ExactArith ex = {q, 2 * q, sc};
+    ExactArith ex = {q, 2 * q, sc, 0};
     FastArith fa = {make_fastmod(q), sc};
     LazyInvArith la = {make_fastmod(q), sc};
     int bad = 0, badi = 0, badf = -1, badfi = -1, badli = -1;

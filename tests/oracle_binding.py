@@ -38,6 +38,8 @@ def oracle():
         o.ho_compute_roots_keyswitch.argtypes = [u64, u64, u64, vp]
         o.ho_fwd_ntt.argtypes = [vp, u64, u64, vp, vp]
         o.ho_inv_ntt.argtypes = [vp, u64, u64, vp, vp, u64, u64]
+        o.ho_fwd_ntt_lazy.argtypes = [vp, u64, u64, vp, vp]
+        o.ho_inv_ntt_lazy.argtypes = [vp, u64, u64, vp, vp, u64, u64]
         o.ho_fwd_ntt_reference.argtypes = [vp, u64, u64, vp]
         o.ho_fwd_ntt_batch.argtypes = [vp, u64, u64, u64, vp, vp, C.c_int]
         o.ho_inv_ntt_batch.argtypes = [vp, u64, u64, u64, vp, vp, u64, u64, C.c_int]
@@ -73,6 +75,9 @@ def ref():
         r.ref_tables.argtypes = [u64, u64, vp, vp, vp, vp]
         r.ref_fwd_ntt.argtypes = [vp, u64, u64]
         r.ref_inv_ntt.argtypes = [vp, u64, u64]
+        if hasattr(r, "ref_fwd_ntt_factors"):
+            r.ref_fwd_ntt_factors.argtypes = [vp, u64, u64, u64, u64]
+            r.ref_inv_ntt_factors.argtypes = [vp, u64, u64, u64, u64]
         r.ref_fwd_ntt_batch.argtypes = [vp, u64, u64, u64, vp, vp, C.c_int]
         r.ref_inv_ntt_batch.argtypes = [vp, u64, u64, u64, vp, vp, C.c_int]
         _r = r
@@ -130,6 +135,20 @@ def fwd_ntt(a, t):
 def inv_ntt(a, t):
     a = np.array(a, dtype=np.uint64, copy=True)
     oracle().ho_inv_ntt(P(a), t.n, t.q, P(t.inv_roots), P(t.precon_inv), t.inv_n, t.inv_n_w)
+    return a
+
+
+def fwd_ntt_lazy(a, t):
+    """output_mod_factor = 4: words in [0, 4q)"""
+    a = np.array(a, dtype=np.uint64, copy=True)
+    oracle().ho_fwd_ntt_lazy(P(a), t.n, t.q, P(t.roots), P(t.precon))
+    return a
+
+
+def inv_ntt_lazy(a, t):
+    """output_mod_factor = 2: words in [0, 2q)"""
+    a = np.array(a, dtype=np.uint64, copy=True)
+    oracle().ho_inv_ntt_lazy(P(a), t.n, t.q, P(t.inv_roots), P(t.precon_inv), t.inv_n, t.inv_n_w)
     return a
 
 

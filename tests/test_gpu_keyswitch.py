@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import oracle_binding as ob
+from conftest import set_variant
 from ks_util import KsProblem
 
 pytestmark = pytest.mark.gpu
@@ -62,6 +63,25 @@ def test_device_api_vs_second_restatement(hb, n, D, K):
     plan.keyswitch(res, gpu(p.t_target), 2)
     assert np.array_equal(res.cpu().numpy().view(np.uint64), p.expected(alt=True))
     plan.close()
+
+
+@pytest.mark.parametrize("opt,val", [("ks_fused", 1), ("ks_sub_items", 2), ("ks_sub_items", 5)])
+@pytest.mark.parametrize("n,D,K,batch", [(16384, 7, 8, 5), (16384, 6, 7, 3), (16384, 2, 8, 4), (16384, 1, 2, 3), (8192, 5, 7, 3)])
+def test_fused_kernel_and_l2_rounds(hb, n, D, K, batch, opt, val):
+    """ks_fused = 1: stages S2 + S3 + S4 in one kernel, the sums in tensor memory (keyswitch_fused.cu; N = 16384
+    only, other sizes take the staged kernels); ks_sub_items: S2 + S3 in rounds of a few items so that the
+    NTT'd digits stay in L2.  Both must reproduce the oracle bit for bit."""
+    p = KsProblem(n, D, K, batch, 51, seed=2024)
+    hb.set_option(opt, val)
+    try:
+        plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+        res = gpu(p.result)
+        plan.keyswitch(res, gpu(p.t_target), batch)
+        got = res.cpu().numpy().view(np.uint64)
+        plan.close()
+    finally:
+        hb.set_option(opt, 0)
+    assert np.array_equal(got, p.expected())
 
 
 def test_out_of_range_target_words_go_to_the_exact_kernel(hb):
@@ -162,7 +182,7 @@ def test_mac_variants_agree_with_oracle(hb, n, D, K, batch, bits, mac_items):
     load (default); 2 = 128-bit accumulators, one reduction per output; 8; 1 = register-resident
     keys): all must give the oracle's words, odd batch sizes included."""
     p = KsProblem(n, D, K, batch, bits)
-    hb.set_option("ks_mac_items", mac_items)
+    set_variant(hb, "ks_mac_items", mac_items)
     try:
         plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
         res = gpu(p.result)

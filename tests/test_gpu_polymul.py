@@ -117,3 +117,37 @@ def test_bad_arguments(hb):
     assert f(*args(x.data_ptr() + 8, n)) == -1      # misaligned
     assert f(*args(x.data_ptr(), 1000)) == -1       # not a power of two
     assert f(*args(None, n)) == -1
+
+
+@pytest.mark.parametrize("bits", [51, 40, 36])
+def test_single_launch_kernel_matches_three_launch_path(hb, bits):
+    """N = 16384, FP64-contract modulus: one launch per chunk (NTT(a) parked in tensor memory, NTT(b), product,
+    INTT -- polymul_fused.cu) vs the three-launch version, vs the oracle pipeline; items with out-of-contract
+    words in a, in b, or in both go to the exact kernels through the deferred list; aliasing result = a."""
+    n = 16384
+    q = ob.primes(1, bits, n)[0]
+    t = ob.Tables(n, q)
+    B = 300                                  # more items than CTAs: the persistent loop wraps
+    a = np.stack([ob.splitmix(n, 1000 + i, q) for i in range(12)])
+    b = np.stack([ob.splitmix(n, 2000 + i, q) for i in range(12)])
+    a = np.ascontiguousarray(np.resize(a, (B, n)))
+    b = np.ascontiguousarray(np.resize(b, (B, n)))
+    a[:, 1] = np.arange(B, dtype=np.uint64)
+    a[5, 77] = np.uint64(2**64 - 1)          # a out of contract
+    b[9, 0] = np.uint64(3 * q + 1)           # b out of contract
+    a[160] = np.uint64(2**63 + 11)           # both, in the second round of the persistent loop
+    b[160, 5] = np.uint64(2**64 - 3)
+    a[299, 16383] = np.uint64(2 * q)         # last item
+    outs = {}
+    for fused in (1, 0):
+        hb.set_option("polymul_fused", fused)
+        try:
+            outs[fused] = run(hb, a, b, t)
+            if fused:
+                alias = run(hb, a, b, t, alias=True)
+        finally:
+            hb.set_option("polymul_fused", 1)
+    assert np.array_equal(outs[1], outs[0])
+    assert np.array_equal(alias, outs[1])
+    for i in (0, 1, 147, 148, 149, 298):
+        assert np.array_equal(outs[1][i], oracle_pipeline(a[i], b[i], t)), i

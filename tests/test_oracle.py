@@ -257,3 +257,25 @@ def test_keyswitch_rlwe_noise(n, D, K):
         assert max(abs(x) for x in d) < bound, max(abs(x) for x in d)
     for d in noises[1:]:
         assert d == noises[0]
+
+
+@pytest.mark.parametrize("n,bits", [(1024, 20), (4096, 51), (16384, 51), (16384, 60)])
+def test_lazy_output_mod_factors_against_live_reference_build(n, bits):
+    """output_mod_factor 4 (forward) / 2 (inverse): the oracle's lazy words equal the reference's own
+    (tests/test_utils/ntt.cpp:442-470 through oracle/_ref), and reduce to the canonical transform."""
+    r = ob.ref()
+    q = ob.primes(1, bits, n)[0]
+    t = ob.Tables(n, q)
+    a = ob.splitmix(n, 4711, q)
+    lf, li = ob.fwd_ntt_lazy(a, t), ob.inv_ntt_lazy(a, t)
+    assert lf.max() < 4 * q and li.max() < 2 * q
+    assert np.array_equal(lf % np.uint64(q), ob.fwd_ntt(a, t)) and np.array_equal(li % np.uint64(q), ob.inv_ntt(a, t))
+    assert (lf >= q).any()                            # genuinely lazy (the inverse rarely leaves a word above q)
+    if r is None or not hasattr(r, "ref_fwd_ntt_factors"):
+        pytest.skip("oracle/_ref not built")
+    x = a.copy()
+    r.ref_fwd_ntt_factors(ob.P(x), n, q, 1, 4)
+    assert np.array_equal(x, lf)
+    x = a.copy()
+    r.ref_inv_ntt_factors(ob.P(x), n, q, 1, 2)
+    assert np.array_equal(x, li)

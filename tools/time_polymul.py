@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "hexl-fpga_b200")); sys.path.insert(0, os.
 import hexl_b200 as hb, oracle_binding as ob
 from quick_time import timeit, gpu
 N, q, B = 16384, 2251799814045697, 2048
+hb.set_option("polymul_fused", int(os.environ.get("PM_FUSED", "1")))
 t = ob.Tables(N, q)
 a = torch.randint(0, q, (B, N), dtype=torch.int64, device="cuda")
 b = torch.randint(0, q, (B, N), dtype=torch.int64, device="cuda")
