@@ -308,7 +308,7 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
         *launches += 1;
         return launch_mode<C, FWD, kFastTrust>(tmap, smap, data, tab, batch, list, st, stride, offset);
     }
-    if ((e = launch_mode<C, FWD, kFastVote>(tmap, smap, data, tab, batch, list, st))) return e;
+    if ((e = launch_mode<C, FWD, kFastVote>(tmap, smap, data, tab, batch, list, st, stride, offset))) return e;
     // polynomials with out-of-contract words (none in normal use): exact pass
     // over the deferred list; exits at once when the list is empty
     *launches += 2;

@@ -31,33 +31,18 @@ struct Fp64ArithPre : Fp64Arith {
     HB_HD uint64_t enter_inv(uint64_t x) const { return x; }
 };
 
-// tail output of NTT(a): park the row in tensor memory (columns [ri][word][lo, hi] of the thread's lane)
+// Tail output of the two forward transforms, ONE type so that the transform body exists once in the kernel
+// (three unrolled transform bodies, ~210 KB of SASS, overflow the SM's instruction cache: ncu showed
+// "no instruction" as the top stall, 3.7 warps per issue, profiles/r2_ncu_pm_summary.txt):
+//   mul == 0 (NTT(a)): park the row in tensor memory (columns [ri][word][lo, hi] of the thread's lane)
+//   mul == 1 (NTT(b)): multiply by the parked row and put the product row back into the transform buffer
 template <class CC>
-struct OfPark {
-    uint32_t taddr;
-    Fp64Mod m;
-    template <class C>
-    HB_D void prefetch(uint32_t) const {}
-    template <class C>
-    HB_D void store(uint32_t row, const uint64_t* v) const {
-        const int ri = C::WARPTAIL ? (int)((row >> 5) & 1u) : (int)(row / C::NT);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint64_t w[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = d2u(fp_cred(u2d(v[h * 8 + k]), m));   // |w| <= q/2: a valid "twiddle"
-            tmem_st16(taddr + (uint32_t)ri * 32u + (uint32_t)h * 16u, w);
-        }
-    }
-};
-
-// tail output of NTT(b): multiply by the parked row and put the product row back into the transform buffer
-template <class CC>
-struct OfMulBack {
+struct OfParkMul {
     uint32_t taddr;
     Fp64Mod m;
     double inv_q;
     uint64_t* W;
+    uint32_t mul;
     template <class C>
     HB_D void prefetch(uint32_t) const {}
     template <class C>
@@ -65,20 +50,27 @@ struct OfMulBack {
         const int ri = C::WARPTAIL ? (int)((row >> 5) & 1u) : (int)(row / C::NT);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            const uint32_t ta = taddr + (uint32_t)ri * 32u + (uint32_t)h * 16u;
             uint64_t w[8];
-            tmem_ld16(taddr + (uint32_t)ri * 32u + (uint32_t)h * 16u, w);
+            if (!mul) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                // y * w (mod q): |y| <= 1.25 q, |w| <= q/2; the quotient factor w/q is formed on the fly
-                // (two roundings instead of one: |c - y w / q| <= 1/2 + 0.41, so |r| < q, still exact)
-                uint64_t p[2];
+                for (int k = 0; k < 8; ++k) w[k] = d2u(fp_cred(u2d(v[h * 8 + k]), m));   // |w| <= q/2: a valid "twiddle"
+                tmem_st16(ta, w);
+            } else {
+                tmem_ld16(ta, w);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double wd = u2d(w[2 * c + e]);
-                    const double r = fp_mulmod(u2d(v[h * 8 + 2 * c + e]), wd, fp_mul(wd, inv_q), m);
-                    p[e] = d2u(fp_cred(r, m));
+                for (int c = 0; c < 4; ++c) {
+                    // y * w (mod q): |y| <= 1.25 q, |w| <= q/2; the quotient factor w/q is formed on the fly
+                    // (two roundings instead of one: |c - y w / q| <= 1/2 + 0.41, so |r| < q, still exact)
+                    uint64_t p[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double wd = u2d(w[2 * c + e]);
+                        const double r = fp_mulmod(u2d(v[h * 8 + 2 * c + e]), wd, fp_mul(wd, inv_q), m);
+                        p[e] = d2u(fp_cred(r, m));
+                    }
+                    st_chunk(W + row * 16 + (((uint32_t)(h * 4 + c) ^ (row & 7u)) << 1), p);
                 }
-                st_chunk(W + row * 16 + (((uint32_t)(h * 4 + c) ^ (row & 7u)) << 1), p);
             }
         }
     }
@@ -137,32 +129,32 @@ k_polymul_fused(const __grid_constant__ CUtensorMap m_a, const __grid_constant__
         };
         Fp64ArithRaw a;
         a.m = t.fd;
-        // ---- NTT(a), parked in tensor memory; b lands behind it ----
-        Prefetch pf;
-        pf.map = &m_b;
-        pf.row = leader ? i * ROWS : kNoPrefetch;
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        tmem_wait_st();   // the previous item's product has consumed the parked words (program order), stores drained
-        if (!ntt_fwd_cta<C, kFastVote>(W, t, a, XfIdent(), OfPark<C>{taddr, t.fd}, pf)) {
-            // a is out of contract; its prefetch of b was issued by thread 0 only in the deferral path
+        // ---- phase 0: NTT(a), parked in tensor memory, b lands behind it;  phase 1: NTT(b) (.) NTT(a) back
+        //      into the buffer.  One call site: the forward transform body exists once. ----
+        bool ok = true;
+#pragma unroll 1
+        for (uint32_t phase = 0; phase < 2 && ok; ++phase) {
+            Prefetch pf;
+            pf.map = &m_b;
+            pf.row = (phase == 0 && leader) ? i * ROWS : kNoPrefetch;
             mbar_wait(bar, parity);
             parity ^= 1;
-            abandon();
-            continue;
+            tmem_wait_st();   // tensor-memory stores of the previous phase / item have drained
+            ok = ntt_fwd_cta<C, kFastVote>(W, t, a, XfIdent(), OfParkMul<C>{taddr, t.fd, inv_q, W, phase}, pf);
+            if (!ok && phase == 0) {
+                // a is out of contract; the deferral path has started b's load (thread 0): let it land
+                mbar_wait(bar, parity);
+                parity ^= 1;
+            }
         }
-        // ---- NTT(b) (.) NTT(a) back into the buffer ----
-        pf.row = kNoPrefetch;
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        tmem_wait_st();
-        if (!ntt_fwd_cta<C, kFastVote>(W, t, a, XfIdent(), OfMulBack<C>{taddr, t.fd, inv_q, W}, pf)) {
+        if (!ok) {
             abandon();
             continue;
         }
         // ---- INTT of the product rows; the next item's a is prefetched once the buffer is in registers ----
         Fp64ArithPre ai;
         ai.m = t.fd;
+        Prefetch pf;
         pf.map = &m_a;
         pf.row = (leader && next < n_items) ? next * ROWS : kNoPrefetch;
         ntt_inv_cta<C, kFastTrust>(W, t, ai, XfIdent(), OfWords{res + (size_t)i * C::N}, pf);

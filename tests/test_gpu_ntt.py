@@ -195,7 +195,7 @@ def test_empty_batch_and_bad_arguments(hb):
     r, p = to_gpu(t.roots), to_gpu(t.precon)
     assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, n, 0, None) == 0   # batch 0: no-op
     assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr() + 8, r.data_ptr(), p.data_ptr(), q, n, 1, None) == -1  # misaligned
-    assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, 32768, 1, None) == -1  # n too large
+    assert hb.lib().hexl_b200_ntt_fwd(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, 65536, 1, None) == -1  # n too large
     assert hb.lib().hexl_b200_ntt_inv(x.data_ptr(), r.data_ptr(), p.data_ptr(), q, q, 0, n, 1, None) == -1  # inv_n >= q
 
 

@@ -39,6 +39,25 @@ elif op == "dyadic":
     res = torch.empty((B, 3 * M * n), dtype=torch.int64, device="cuda")
     for _ in range(3):
         hb.dyadic_multiply(res, op1, op2, n, gpu(moduli), M, B)
+elif op == "polymul":
+    N, q = 16384, 2251799814045697
+    t = ob.Tables(N, q)
+    hb.set_option("polymul_fused", variant)
+    a = torch.randint(0, q, (batch, N), dtype=torch.int64, device="cuda")
+    b = torch.randint(0, q, (batch, N), dtype=torch.int64, device="cuda")
+    res = torch.empty_like(a)
+    tw = [gpu(x) for x in (t.roots, t.precon, t.inv_roots, t.precon_inv)]
+    for _ in range(2):
+        hb.poly_multiply(res, a, b, *tw, q, t.inv_n, t.inv_n_w, N)
+elif op == "keyswitch_fused":
+    n, D, K, B = 16384, 7, 8, batch
+    hb.set_option("ks_fused", 1)
+    p = KsProblem(n, D, K, 1, 51)
+    plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+    res = gpu(p.result).repeat(B, 1).contiguous()
+    tt = gpu(p.t_target).repeat(B, 1).contiguous()
+    for _ in range(2):
+        plan.keyswitch(res, tt, B)
 elif op == "keyswitch":
     n, D, K, B = 16384, 7, 8, batch if len(sys.argv) > 3 else 64
     p = KsProblem(n, D, K, 1, 51)
