@@ -52,6 +52,8 @@ static std::atomic<int> g_inv_lazy{0};     // correction-free inverse butterflie
 static std::atomic<int> g_small_path{1};
 // butterflies on the FP64 pipe for 2^36 <= q <= 2^53/3 in the plain NTT entry points (option "fp64_path")
 static std::atomic<int> g_fp64_path{1};
+// forward FP64 butterflies with a full correction every other stage for q <= 2^51 (1 + 1/32) (option "fp64_alt")
+static std::atomic<int> g_fp64_alt{1};
 
 hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
                        const hb::TwPair* itw, int logn, const hb::Tw32* ftw32, const hb::Tw32* itw32) {
@@ -77,6 +79,7 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.ftwd = nullptr;
     t.itwd = nullptr;
     t.fp64_ok = 0;          // set by the callers that build the FP64 tables
+    t.fp64_alt_ok = (g_fp64_alt.load() && hb::fp64_alt_modulus_ok(q)) ? 1u : 0u;
     t.lazy_out = 0;
     return t;
 }
@@ -243,6 +246,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "warp_tail")) {
         hb::g_warp_tail = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "fp64_alt")) {
+        g_fp64_alt = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "fp64_path")) {
@@ -644,7 +651,9 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         qmax = moduli[i] > qmax ? moduli[i] : qmax;
     }
     p->dev.s2_no_reduce = (p->dev.fp64_ok && qmax <= qmin + (qmin >> 2)) ? 1u : 0u;   // q_j - 1 < vote bound of every q_r
-    p->dev.pad = 0;
+    p->dev.fp64_alt_ok = p->dev.fp64_ok;
+    for (uint64_t i = 0; i < K; ++i)
+        if (!h_tabs[i].fp64_alt_ok) p->dev.fp64_alt_ok = 0;
     p->dev.logn = (uint32_t)logn;
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;

@@ -19,6 +19,8 @@
 // y = D*(D-1) + j for r == D.  Every stage output is canonical in [0,q), so the
 // result is the unique value the reference pipeline produces.  The four
 // transform stages are the persistent TMA-fed kernels of ntt_block.cuh.
+#include <type_traits>
+
 #include "launch.h"
 
 namespace hb {
@@ -49,7 +51,7 @@ struct JobIntt1 {
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{U + (size_t)item * C::N}; }
 };
-template <class C, int MODE, bool FP64 = false>
+template <class C, int MODE, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobIntt1<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, false, MODE, JobIntt1<C>, false, FP64>(&tmap, &smap, job, n_items, list);
@@ -96,7 +98,7 @@ struct JobNtt1 {
         return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
     }
 };
-template <class C, int MODE, bool FP64 = false>
+template <class C, int MODE, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobNtt1<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE, JobNtt1<C>, false, FP64>(&tmap, &smap, job, n_items, list);
@@ -378,7 +380,7 @@ struct JobIntt2 {
         return OfWordsRound{ACC + (size_t)poly(item) * C::N, qk, qk >> 1};
     }
 };
-template <class C, int MODE, bool FP64 = false>
+template <class C, int MODE, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt2(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobIntt2<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, false, MODE, JobIntt2<C>, false, FP64>(&tmap, &smap, job, n_items, list);
@@ -467,7 +469,7 @@ struct JobNtt2 {
                          ks.tabs[i].q, ks.msf[i], ks.msf_p[i]};
     }
 };
-template <class C, int MODE, bool FP64 = false>
+template <class C, int MODE, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt2(const __grid_constant__ CUtensorMap tmap,
         const __grid_constant__ CUtensorMap smap, const JobNtt2<C> job, uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE, JobNtt2<C>, false, FP64>(&tmap, &smap, job, n_items, list);
@@ -555,7 +557,11 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
             if (launches) *launches = nl + 2;
             return cudaSuccess;
         }
-        if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+        if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
+            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 2>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+        } else {
+            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+        }
         nl += 1;
     } else if (ks.fast_ok) {
         // S1 sees caller data: vote + deferred exact pass; the later stages read
@@ -594,7 +600,11 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     if ((e = cudaGetLastError())) return e;
     if (ks.fast_ok && ks.fp64_ok) {
         if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
-        if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+        if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
+            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, 2>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+        } else {
+            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+        }
     } else if (ks.fast_ok) {
         if ((e = run_persistent(k_ks_intt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;
         if ((e = run_persistent(k_ks_ntt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobNtt2<C>{ks, ACC, result}, items * 2 * D, list, st))) return e;

@@ -19,7 +19,7 @@ struct KsDev {
     // reduced mod q_j is below 1.25 q_r for every target modulus, i.e. already inside the forward
     // transform's input contract, and NTT_r(x) = NTT_r(x mod q_r): stage S2 skips its base conversion
     uint32_t s2_no_reduce;
-    uint32_t pad;
+    uint32_t fp64_alt_ok;   // every modulus <= 2^51 (1 + 1/32): forward stages correct every other stage (modarith.cuh)
     const ModTab* tabs;     // [K]
     const Divisor* divs;    // [K]
     const uint64_t* keys;   // [D][2][K][N]  == k_switch_keys[j][(c*K+i)*N + l]

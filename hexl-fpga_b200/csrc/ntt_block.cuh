@@ -31,6 +31,7 @@ struct ModTab {
     const TwPair* ftwd;
     const TwPair* itwd;
     uint32_t fp64_ok;       // 2^36 <= q <= 2^53 / 3 and the tables above are there
+    uint32_t fp64_alt_ok;   // ... and q <= 2^51 (1 + 1/32): forward butterflies that correct every other stage
     uint32_t lazy_out;      // the caller wants the lazy words of the reference's output_mod_factor 4 / 2: exact kernels only
 };
 
@@ -525,11 +526,12 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 //   const ModTab& mod(item)
 //   Xf xf(item), Of of(item, store_map)
 // `list`: the deferred list (written in kFastVote, read in kExactList mode).
-template <class C, bool FWD, int MODE, class Job, bool LAZY = false, bool FP64 = false>
+// FP64: 0 integer butterflies, 1 FP64-pipe butterflies, 2 (forward only) FP64 with a full correction every other stage
+template <class C, bool FWD, int MODE, class Job, bool LAZY = false, int FP64 = 0>
 HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
                          uint32_t* list) {
     static_assert(!LAZY || (!FWD && (MODE == kFastVote || MODE == kFastTrust)), "LAZY is an inverse fast-path option");
-    static_assert(!FP64 || (!LAZY && (MODE == kFastVote || MODE == kFastTrust)), "FP64 is a fast-path option");
+    static_assert(FP64 == 0 || (!LAZY && (MODE == kFastVote || MODE == kFastTrust)), "FP64 is a fast-path option");
     // The 128-byte TMA swizzle needs the buffer 1024-byte aligned; the dynamic
     // shared window of a kernel without static shared memory starts aligned.
     // launched with programmatic stream serialization (ntt_launch.cuh): wait for the kernel in front
@@ -553,7 +555,7 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     }
     // FP64 kernels of the plain batched calls (one modulus per launch, launched with BYTES_TW of
     // shared memory): the twiddles of the head passes move next to the buffer once
-    constexpr bool SMEM_HEAD = FP64 && Job::kOneModulus && SmemPlan<C>::kHeadTwFits;
+    constexpr bool SMEM_HEAD = FP64 != 0 && Job::kOneModulus && SmemPlan<C>::kHeadTwFits;
     if constexpr (SMEM_HEAD) {
         const ModTab& t0 = job.mod(0);
         const ulonglong2* src = reinterpret_cast<const ulonglong2*>(FWD ? t0.ftwd : t0.itwd + C::inv_off(0));
@@ -581,13 +583,22 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         parity ^= 1;
         const ModTab& t = job.mod(item);
         bool done;
-        if constexpr (SMEM_HEAD) {
+        if constexpr (SMEM_HEAD && FWD && FP64 == 2) {
+            Fp64AltArithS a;
+            a.m = t.fd;
+            a.head_s = head_s;
+            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (FWD && FP64 == 2) {
+            Fp64AltArith a;
+            a.m = t.fd;
+            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (SMEM_HEAD) {
             Fp64ArithS a;
             a.m = t.fd;
             a.head_s = head_s;
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
-        } else if constexpr (FP64) {
+        } else if constexpr (FP64 != 0) {
             const Fp64Arith a = {t.fd};
             if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);

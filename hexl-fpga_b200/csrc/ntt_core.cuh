@@ -209,6 +209,7 @@ struct ExactArith {
     uint32_t lazy_out;     // output_mod_factor 4 (forward) / 2 (inverse) of the reference: no final correction
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly(X, Y, t.w, t.wp, q, twoq); }
+    template <int S> HB_HD void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd(X, Y, t); }
     HB_HD uint64_t fwd_final(uint64_t x) const {      // ntt.cpp:535-546
         if (lazy_out) return x;
         x -= (x >= twoq) ? twoq : 0;
@@ -235,6 +236,7 @@ struct FastArith {
     InvScale sc;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly_fast(X, Y, t.w, t.wp, m); }
+    template <int S> HB_HD void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd(X, Y, t); }
     HB_HD uint64_t fwd_final(uint64_t x) const { return reduce_small_multiple(x, m); }
     HB_HD void inv(uint64_t& X, uint64_t& Y, const TwPair& t) const { inv_bfly_fast(X, Y, t.w, t.wp, m); }
     HB_HD void inv_last(uint64_t& X, uint64_t& Y) const {
@@ -268,6 +270,7 @@ struct Fp64Arith {
     HB_HD uint64_t enter_fwd(uint64_t x) const { return d2u(fp_from_int(x)); }               // [0, 1.25q)
     HB_HD uint64_t enter_inv(uint64_t x) const { return d2u(fp_cred(fp_from_int(x), m)); }   // |v| <= q/2
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly_fp64(X, Y, t.w, t.wp, m); }
+    template <int S> HB_HD void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd(X, Y, t); }
     HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical(u2d(x), m); }
     template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
         inv_bfly_fp64(X, Y, t.w, t.wp, m);
@@ -300,6 +303,23 @@ struct Fp64ArithS : Fp64Arith {
         return *p;
 #endif
     }
+};
+
+// Forward-only FP64 arithmetic with a full correction every other stage (modarith.cuh, fwd_bfly_fp64_a / _b):
+// S = the global stage index, even stages correct.  Moduli up to 2^51 (1 + 1/32).
+struct Fp64AltArith : Fp64Arith {
+    template <int S> HB_HD void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
+        if constexpr ((S & 1) == 0) fwd_bfly_fp64_a(X, Y, t.w, t.wp, m);
+        else fwd_bfly_fp64_b(X, Y, t.w, t.wp, m);
+    }
+    HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical_full(u2d(x), m); }
+};
+struct Fp64AltArithS : Fp64ArithS {
+    template <int S> HB_HD void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
+        if constexpr ((S & 1) == 0) fwd_bfly_fp64_a(X, Y, t.w, t.wp, m);
+        else fwd_bfly_fp64_b(X, Y, t.w, t.wp, m);
+    }
+    HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical_full(u2d(x), m); }
 };
 
 // inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
@@ -399,6 +419,7 @@ struct SmallArith {
         X = tx + T;
         Y = tx + m.twoq - T;
     }
+    template <int S> HB_HD void fwd_at(uint32_t& X, uint32_t& Y, const Tw32& t) const { fwd(X, Y, t); }
     HB_HD uint32_t fwd_final(uint32_t x) const { return csub32(csub32(x, m.twoq), m.q); }
     HB_HD void inv(uint32_t& X, uint32_t& Y, const Tw32& t) const {   // values in [0,2q)
         const uint32_t tx = X + Y;
@@ -478,7 +499,8 @@ struct NoFin {
     HB_HD void operator()(int, int) const {}
     HB_HD void operator()(int, int, int) const {}
 };
-template <int R, int TS, class A, class Fin = NoFin>
+// S0: global index of the group's first stage (arithmetic policies whose butterfly depends on the stage)
+template <int R, int TS, int S0, class A, class Fin = NoFin>
 HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a, const Fin& fin = Fin()) {
     static_for<0, R>([&](auto dc) {
         constexpr int d = decltype(dc)::value;
@@ -488,7 +510,7 @@ HB_HD void fwd_group(typename A::elem* v, const typename A::Tw* g, const A& a, c
             const typename A::Tw t = (TS == 1) ? a.ld_head(g + ((1 << d) + blk) * TS) : a.ld(g + ((1 << d) + blk) * TS);
             static_for<0, half>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                a.fwd(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
+                a.template fwd_at<S0 + d>(v[blk * 2 * half + j], v[blk * 2 * half + j + half], t);
                 if constexpr (d == R - 1) fin(blk * 2 * half + j, blk * 2 * half + j + half);
             });
         });
@@ -669,7 +691,7 @@ HB_HD void fwd_head_compute(uint32_t tid, typename A::elem* v, const typename A:
     static_for<0, Gm::G>([&](auto gc) {
         constexpr int gi = decltype(gc)::value;
         const uint32_t hi = Gm::hi(tid + gi * C::NT);
-        fwd_group<Ps::R, 1>(v + gi * (1 << Ps::R), tw + C::fwd_off(P) + (hi << Ps::R), a,
+        fwd_group<Ps::R, 1, Ps::S0>(v + gi * (1 << Ps::R), tw + C::fwd_off(P) + (hi << Ps::R), a,
                             [&](int k0, int k1) { fin(gi, k0, k1); });
     });
 }
@@ -698,7 +720,7 @@ HB_HD void fwd_tail_compute(uint32_t tid, typename A::elem* v, const typename A:
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tail_row<C>(tid, ri);
-        fwd_group<C::LOGROW, 32>(v + ri * C::ROW, tw + C::fwd_off(C::NP) + tail_tw_base<C>(row), a);
+        fwd_group<C::LOGROW, 32, C::HEAD>(v + ri * C::ROW, tw + C::fwd_off(C::NP) + tail_tw_base<C>(row), a);
         static_for<0, C::ROW>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             v[ri * C::ROW + k] = a.fwd_final(v[ri * C::ROW + k]);

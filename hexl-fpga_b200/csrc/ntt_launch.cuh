@@ -38,13 +38,13 @@ struct JobInv : JobPlain<C> {
     }
 };
 
-template <class C, int MODE, bool FP64 = false>
+template <class C, int MODE, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_fwd(const __grid_constant__ CUtensorMap tmap,
                                                    const __grid_constant__ CUtensorMap smap, const JobFwd<C> job,
                                                    uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, true, MODE, JobFwd<C>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
-template <class C, int MODE, bool LAZY = false, bool FP64 = false>
+template <class C, int MODE, bool LAZY = false, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_constant__ CUtensorMap tmap, const JobInv<C> job,
                                                    uint32_t n_items, uint32_t* list) {
     ntt_persistent<C, false, MODE, JobInv<C>, LAZY, FP64>(&tmap, nullptr, job, n_items, list);
@@ -62,7 +62,7 @@ struct JobInvMul : JobPlain<C> {
     }
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{this->data + (size_t)item * C::N}; }
 };
-template <class C, int MODE, bool FP64 = false>
+template <class C, int MODE, int FP64 = 0>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv_mul(const __grid_constant__ CUtensorMap tmap,
                                                                    const JobInvMul<C> job, uint32_t n_items) {
     ntt_persistent<C, false, MODE, JobInvMul<C>, false, FP64>(&tmap, nullptr, job, n_items, nullptr);
@@ -153,6 +153,19 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         job.offset = offset;
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
             using CW = typename WarpTailCfg<C>::type;
+            if (tab.fp64_ok && tab.fp64_alt_ok && g_warp_tail && !std::is_same<CW, C>::value) {
+                // q <= 2^51 (1 + 1/32): full correction every other stage (modarith.cuh), ~15 % fewer scheduler cycles
+                auto kern = k_ntt_fwd<CW, MODE, 2>;
+                const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();
+                if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
+                JobFwd<CW> jobw;
+                jobw.data = base;
+                jobw.tab = tab;
+                jobw.stride = stride;
+                jobw.offset = offset;
+                e = launch_dep(kern, (unsigned)persistent_grid((const void*)kern, CW::NT, smemw, cnt), CW::NT, smemw, st, tmap, smap, jobw, (uint32_t)cnt, list);
+                return e != cudaSuccess ? e : cudaGetLastError();
+            }
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
                 auto kern = k_ntt_fwd<CW, MODE, true>;
                 const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();

@@ -13,8 +13,8 @@
 //      owns) and stores the result in natural order, while the next item's a is prefetched.
 // Inputs are caller data: both forward transforms carry the range vote of the plain kernels, and an item
 // with an out-of-contract word is left to the exact three-kernel path (deferred list, as everywhere).
-// Shapes: N = 16384 and moduli inside the FP64 contract (2^36 <= q <= 2^53/3); everything else takes the
-// three-launch version (capi.cu).
+// Shapes: N = 16384 and moduli 2^36 <= q <= 2^51 (1 + 1/32) (the FP64 butterflies that correct every other
+// stage); everything else takes the three-launch version (capi.cu).
 #include "ntt_launch.cuh"
 #include "tmem.cuh"
 
@@ -22,8 +22,9 @@ namespace hb {
 
 int g_polymul_fused = 1;   // option "polymul_fused"
 
-// forward transform whose tail hands over the raw centred doubles (|v| <= 1.25 q) instead of canonical words
-struct Fp64ArithRaw : Fp64Arith {
+// forward transform (full correction every other stage, modarith.cuh) whose tail hands over the raw
+// doubles (|v| <= 1.92 q < 2^52) instead of canonical words
+struct Fp64ArithRaw : Fp64AltArith {
     HB_HD uint64_t fwd_final(uint64_t x) const { return x; }
 };
 // inverse transform whose input rows already hold centred doubles with |v| <= q/2 (1 + 2^-20)
@@ -54,14 +55,14 @@ struct OfParkMul {
             uint64_t w[8];
             if (!mul) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[k] = d2u(fp_cred(u2d(v[h * 8 + k]), m));   // |w| <= q/2: a valid "twiddle"
+                for (int k = 0; k < 8; ++k) w[k] = d2u(fp_cred_full(u2d(v[h * 8 + k]), m));   // |w| <= q/2: a valid "twiddle"
                 tmem_st16(ta, w);
             } else {
                 tmem_ld16(ta, w);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    // y * w (mod q): |y| <= 1.25 q, |w| <= q/2; the quotient factor w/q is formed on the fly
-                    // (two roundings instead of one: |c - y w / q| <= 1/2 + 0.41, so |r| < q, still exact)
+                    // y * w (mod q): |y| <= 1.92 q < 2^52, |w| <= q/2; the quotient factor w/q is formed on the
+                    // fly (two roundings instead of one: |c - y w / q| <= 1/2 + 0.5, so |r| <= q, still exact)
                     uint64_t p[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -165,7 +166,7 @@ k_polymul_fused(const __grid_constant__ CUtensorMap m_a, const __grid_constant__
 }
 
 bool polymul_fused_available(const ModTab& tab, uint32_t logn) {
-    return g_polymul_fused && logn == 14 && tab.fp64_ok && tab.fwd_fast_ok && tab.inv_fast_ok;
+    return g_polymul_fused && logn == 14 && tab.fp64_ok && tab.fp64_alt_ok && tab.fwd_fast_ok && tab.inv_fast_ok;
 }
 
 // res[i] <- a[i] * b[i]; items with out-of-contract words are appended to `list` (word 0 = count, zero on

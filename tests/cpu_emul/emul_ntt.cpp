@@ -229,6 +229,16 @@ int run_small_all() {
 }
 
 // FP64-pipe arithmetic (modarith.cuh): words converted on entry as the kernels do after the vote
+// Fp64AltArith that records the largest |word| / q leaving every stage
+static double g_alt_max[32];
+struct AltProbe : Fp64AltArith {
+    template <int S> void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
+        Fp64AltArith::fwd_at<S>(X, Y, t);
+        const double v = fmax(fabs(u2d(X)), fabs(u2d(Y))) / m.q;
+        if (v > g_alt_max[S]) g_alt_max[S] = v;
+    }
+};
+
 template <int LOGN, int LOGE, int WT = 0>
 int run_fp64(uint64_t q, int kind) {
     using C = NttCfg<LOGN, LOGE, 4, WT>;
@@ -274,7 +284,27 @@ int run_fp64(uint64_t q, int kind) {
     for (uint64_t i = 0; i < n; ++i) badi += out[i] != ref[i];
     printf("FP64 LOGN=%d LOGE=%d warp-tail=%d q=%llu in=%d fwd/inv mismatch=%d/%d\n", LOGN, LOGE, WT,
            (unsigned long long)q, kind, bad, badi);
-    return bad + badi;
+    // forward butterflies that correct every other stage (moduli up to 2^51 (1 + 1/32)): same canonical words,
+    // and every intermediate word inside the bounds the analysis in modarith.cuh states
+    int bada = 0;
+    if (fp64_alt_modulus_ok(q)) {
+        AltProbe pa;
+        pa.m = fa.m;
+        for (int i = 0; i < 32; ++i) g_alt_max[i] = 0.0;
+        ref = a;
+        for (auto& x : ref) x %= q;
+        ho_fwd_ntt(ref.data(), n, q, roots.data(), precon.data());
+        for (uint64_t i = 0; i < n; ++i) ad[i] = pa.enter_fwd(a[i]);
+        emul_fwd<C, C>(ad, out, ftw.data(), pa);
+        for (uint64_t i = 0; i < n; ++i) bada += out[i] != ref[i];
+        double worst_a = 0, worst_b = 0;
+        for (int sidx = 0; sidx < LOGN; ++sidx) ((sidx & 1) ? worst_b : worst_a) = fmax((sidx & 1) ? worst_b : worst_a, g_alt_max[sidx]);
+        // after a correcting stage <= 1.26 q, after a plain one <= 1.92 q (and below 2^52 in any case)
+        if (worst_a > 1.26 || worst_b > 1.92 || worst_b * (double)q >= 4503599627370496.0) ++bada;
+        printf("FP64-alt LOGN=%d q=%llu in=%d fwd mismatch=%d max|v|/q after even/odd stages %.4f / %.4f\n", LOGN,
+               (unsigned long long)q, kind, bada, worst_a, worst_b);
+    }
+    return bad + badi + bada;
 }
 
 template <int LOGN, int LOGE, int WT = 0>
@@ -286,6 +316,12 @@ int run_fp64_all() {
         if (ho_generate_primes(p, 1, b, (size_t)1 << LOGN) != 1) continue;
         for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE, WT>(p[0], k);
     }
+    // the largest modulus that takes the every-other-stage correction: the last NTT prime below 2^51 (1 + 1/32)
+    for (uint64_t c = ((((uint64_t)1 << 51) + ((uint64_t)1 << 46)) / (2ull << LOGN)) * (2ull << LOGN) + 1;; c -= (2ull << LOGN))
+        if (fp64_alt_modulus_ok(c) && ho_is_prime(c)) {
+            for (int k = 0; k < 6; ++k) rc += run_fp64<LOGN, LOGE, WT>(c, k);
+            break;
+        }
     // the largest admissible modulus: the last NTT prime below 2^53 / 3
     for (uint64_t c = (((uint64_t)1 << 53) / 3 / (2ull << LOGN)) * (2ull << LOGN) + 1;; c -= (2ull << LOGN))
         if (c <= (((uint64_t)1 << 53) / 3) && ho_is_prime(c)) {
@@ -338,6 +374,18 @@ static int fp64_properties() {
             const double bound = (double)q * (0.5 + (double)ya / 18014398509481984.0) + 1.0;
             if (fabs(rr) > bound) ++fbad;
             if (fp_to_canonical(rr, m) != want) ++fbad;
+            // full correction: any |x| < 2 q  ->  an integer congruent to x within q/2 (1 + 2^-40)
+            {
+                const uint64_t xa = r[1] % (2 * q);
+                const double xf = neg ? -(double)(int64_t)xa : (double)(int64_t)xa;
+                const double xc = fp_cred_full(xf, m);
+                const int64_t xi = (int64_t)xc;
+                if ((double)xi != xc || fabs(xc) > (double)q * 0.5 * (1.0 + 1e-12) + 1.0) ++fbad;
+                uint64_t wantx = xa % q;
+                if (neg && wantx) wantx = q - wantx;
+                if ((uint64_t)(((xi % (int64_t)q) + (int64_t)q) % (int64_t)q) != wantx) ++fbad;
+                if (fp_to_canonical_full(xf, m) != wantx) ++fbad;
+            }
             // conditional correction: |x| <= 1.5 q -> at most max(q/2 (1 + 2^-20), |x| - q)
             const double x = neg ? -(double)(int64_t)ya : (double)(int64_t)ya;
             const double xr = fp_cred(x, m);

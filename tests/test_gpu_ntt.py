@@ -425,3 +425,32 @@ def test_n32768_forward_and_inverse(hb, bits):
         assert np.array_equal(goti[i], ob.inv_ntt(polys[i], t)), ("inv", i)
     back = run_inv(hb, list(got), t)
     assert all(np.array_equal(back[i], polys[i]) for i in range(len(polys)))
+
+
+@pytest.mark.parametrize("n", [16384, 8192, 4096])
+def test_forward_every_other_stage_correction_agrees(hb, n):
+    """Moduli up to 2^51 (1 + 1/32) take forward FP64 butterflies that correct every other stage (option
+    fp64_alt, default on; csrc/modarith.cuh fwd_bfly_fp64_a / _b).  Same words as with the option off and as
+    the oracle, on random polynomials and on the words that push the bounds (all at the contract's edge)."""
+    import torch
+
+    lim = (1 << 51) + (1 << 46)
+    q_edge = next(c for c in range(lim - (lim - 1) % (2 * n), 0, -2 * n) if ob.is_prime(c))
+    for q in (ob.primes(1, 51, n)[0], q_edge, ob.primes(1, 40, n)[0]):
+        t = ob.Tables(n, q)
+        top = q + (q >> 2) - 1
+        polys = [ob.splitmix(n, 4000 + i, q) for i in range(3)]
+        polys.append(np.full(n, q - 1, dtype=np.uint64))
+        polys.append(np.full(n, top, dtype=np.uint64))                                   # in contract for the vote, not canonical
+        polys.append(np.where(np.arange(n) % 2 == 0, top, q >> 1).astype(np.uint64))
+        polys.append(np.where((np.arange(n) >> (np.arange(n) % 14)) & 1, top, (q >> 1) + 1).astype(np.uint64))
+        outs = []
+        for alt in (1, 0):
+            hb.set_option("fp64_alt", alt)
+            try:
+                outs.append(run_fwd(hb, polys, t))
+            finally:
+                hb.set_option("fp64_alt", 1)
+        assert np.array_equal(outs[0], outs[1]), q
+        for i in range(len(polys)):
+            assert np.array_equal(outs[0][i], ob.fwd_ntt(polys[i] % np.uint64(q), t)), (q, i)
