@@ -417,13 +417,31 @@ HB_HD double fp_cred_full(double x, const Fp64Mod& m) {
     const double c = fp_add(fp_fma(x, m.inv_q, magic), -magic);
     return fp_fma(c, m.nq, x);
 }
-// |v| < 2^52  ->  canonical residue in [0, q) as an integer (full reduction first)
-HB_HD uint64_t fp_to_canonical_full(double v, const Fp64Mod& m) {
-    v = fp_cred_full(v, m);
+// integer-valued double with |v| < q (and |v| <= 2^51)  ->  canonical residue in [0, q) as an integer:
+// v + (v < 0 ? q : 0).  The bit pattern of v + 1.5 * 2^52 is that of the constant plus v as a two's-complement
+// integer, so the sign of v is one comparison of the high word, and the high word's offset and the conditional
+// + q are folded into one predicated 64-bit add: one DADD + 4 ALU instructions.
+HB_HD uint64_t fp_canon_signed(double v, const Fp64Mod& m) {
+#if defined(__CUDA_ARCH__)
+    const double t = __dadd_rn(v, u2d(kFpMagicBits));
+    uint64_t out;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+        "mov.b64 {lo, hi}, %1;\n\t"
+        "setp.lt.u32 p, hi, 0x43380000;\n\t"
+        "add.u32 hi, hi, 0xBCC80000;\n\t"
+        "@p add.cc.u32 lo, lo, %2;\n\t"
+        "@p addc.u32 hi, hi, %3;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "=l"(out)
+        : "d"(t), "r"((uint32_t)m.qi), "r"((uint32_t)(m.qi >> 32)));
+    return out;
+#else
     const int64_t s = (int64_t)(d2u(fp_add(v, u2d(kFpMagicBits))) - kFpMagicBits);
-    const int64_t t = s + ((s >> 63) & (int64_t)m.qi);
-    return (uint64_t)t;
+    return (uint64_t)(s + ((s >> 63) & (int64_t)m.qi));
+#endif
 }
+// |v| < 2^52  ->  canonical residue in [0, q) as an integer (full reduction first)
+HB_HD uint64_t fp_to_canonical_full(double v, const Fp64Mod& m) { return fp_canon_signed(fp_cred_full(v, m), m); }
 // y * w (mod q) for |y| <= 2^52, in |r| <= q (1/2 + |y| 2^-54)
 HB_HD double fp_mulmod(double y, double w, double wi, const Fp64Mod& m) {
     const double magic = u2d(kFpMagicBits);
@@ -436,11 +454,7 @@ HB_HD double fp_mulmod(double y, double w, double wi, const Fp64Mod& m) {
 // integer word below 2^52 -> double
 HB_HD double fp_from_int(uint64_t x) { return fp_add(u2d(x | kFpTwo52Bits), -u2d(kFpTwo52Bits)); }
 // |v| <= 1.5 q  ->  canonical residue in [0, q) as an integer
-HB_HD uint64_t fp_to_canonical(double v, const Fp64Mod& m) {
-    v = fp_cred(v, m);                                             // |v| < 2^51
-    const int64_t s = (int64_t)(d2u(fp_add(v, u2d(kFpMagicBits))) - kFpMagicBits);
-    return (uint64_t)(s + ((s >> 63) & (int64_t)m.qi));
-}
+HB_HD uint64_t fp_to_canonical(double v, const Fp64Mod& m) { return fp_canon_signed(fp_cred(v, m), m); }
 HB_HD void fwd_bfly_fp64(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, const Fp64Mod& m) {
     const double x = fp_cred(u2d(X), m);
     const double r = fp_mulmod(u2d(Y), u2d(w), u2d(wi), m);
@@ -476,11 +490,22 @@ HB_HD void inv_bfly_fp64(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, cons
     X = d2u(fp_cred(s, m));
     Y = d2u(fp_mulmod(u, u2d(w), u2d(wi), m));
 }
+// First inverse stage: the words come straight from fp_from_int, x, y in [0, 1.25 q) (the contract of the
+// range vote), no centring on entry.  The sum (< 2.5 q) takes the full correction, which accepts any
+// magnitude; the difference |u| < 1.25 q is inside the product's contract as it is.
+HB_HD void inv_bfly_fp64_first(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, const Fp64Mod& m) {
+    const double x = u2d(X), y = u2d(Y);
+    const double s = fp_add(x, y), u = fp_add(x, -y);
+    X = d2u(fp_cred_full(s, m));
+    Y = d2u(fp_mulmod(u, u2d(w), u2d(wi), m));
+}
+// Last inverse stage with the n^-1 scaling.  |s|, |u| <= 1.5 q, so both products come out with
+// |r| <= q (1/2 + 1.5 q 2^-54) <= 0.75 q <= 2^51 (q <= 2^53 / 3): inside fp_canon_signed's range without a correction.
 HB_HD void inv_last_bfly_fp64(uint64_t& X, uint64_t& Y, const Fp64Mod& m) {
     const double x = u2d(X), y = u2d(Y);
     const double s = fp_add(x, y), u = fp_add(x, -y);
-    X = fp_to_canonical(fp_mulmod(s, m.inv_n, m.inv_n_q, m), m);
-    Y = fp_to_canonical(fp_mulmod(u, m.inv_n_w, m.inv_n_w_q, m), m);
+    X = fp_canon_signed(fp_mulmod(s, m.inv_n, m.inv_n_q, m), m);
+    Y = fp_canon_signed(fp_mulmod(u, m.inv_n_w, m.inv_n_w_q, m), m);
 }
 
 // x mod q for any x < 2^64 with mu = floor(2^64/q)   (q < 2^63).

@@ -101,11 +101,13 @@ struct SmemPlan {
     static constexpr uint32_t FLAG_WORD = BAR_WORD + 1;   // range-vote flag (fast-vote kernels)
     static constexpr uint32_t KQ_WORD = BAR_WORD + 2;     // two tables of k*q, k < 64 (iteration parity)
     static constexpr uint32_t CNT_WORD = BAR_WORD + 2 + 128;   // warps done with the buffer (C::WARPTAIL)
+    static constexpr uint32_t TMEM_WORD = CNT_WORD + 1;        // tensor-memory base address (kernels that allocate TMEM)
     static constexpr size_t BYTES = (size_t)(BAR_WORD + 2 + 128 + 1) * 8;
     // head-pass twiddles of the FP64 plain kernels (Fp64ArithS), 16-byte entries behind everything else
     static constexpr uint32_t HEAD_TW_FWD = C::fwd_off(C::NP), HEAD_TW_INV = C::INV_ENTRIES - C::N;
     static constexpr uint32_t HEAD_TW = HEAD_TW_FWD > HEAD_TW_INV ? HEAD_TW_FWD : HEAD_TW_INV;
     static constexpr uint32_t TW_WORD = (BAR_WORD + 2 + 128 + 1 + 1) & ~1u;
+    static_assert(TW_WORD > TMEM_WORD, "shared-memory plan: the twiddle area overlaps the control words");
     static constexpr size_t BYTES_TW = (size_t)TW_WORD * 8 + (size_t)HEAD_TW * 16;
     static constexpr bool kHeadTwFits = BYTES_TW <= 227u * 1024u;
 };
@@ -189,6 +191,73 @@ HB_D void tma_store_rows3(const CUtensorMap* map, const void* smem_src, uint32_t
 }
 // all earlier bulk stores of this thread have finished READING shared memory
 HB_D void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// tensor memory (TMEM: 512 columns x 128 lanes x 32 bit per SM) as a plain per-thread scratchpad, see tmem.cuh
+// ---------------------------------------------------------------------------
+HB_D void tmem_alloc_all(uint32_t* smem_slot) {   // one warp; 512 columns = the whole TMEM of the SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(smem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+HB_D void tmem_dealloc_all(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's lane = 8 accumulator words
+HB_D void tmem_ld16(uint32_t taddr, uint64_t* a) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = ((uint64_t)r[2 * i + 1] << 32) | r[2 * i];
+}
+HB_D void tmem_st16(uint32_t taddr, const uint64_t* a) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"((uint32_t)a[0]), "r"((uint32_t)(a[0] >> 32)), "r"((uint32_t)a[1]), "r"((uint32_t)(a[1] >> 32)),
+          "r"((uint32_t)a[2]), "r"((uint32_t)(a[2] >> 32)), "r"((uint32_t)a[3]), "r"((uint32_t)(a[3] >> 32)),
+          "r"((uint32_t)a[4]), "r"((uint32_t)(a[4] >> 32)), "r"((uint32_t)a[5]), "r"((uint32_t)(a[5] >> 32)),
+          "r"((uint32_t)a[6]), "r"((uint32_t)(a[6] >> 32)), "r"((uint32_t)a[7]), "r"((uint32_t)(a[7] >> 32))
+        : "memory");
+}
+HB_D void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+
+// tensor-memory address of column `col` of the calling thread's lane
+HB_D uint32_t tmem_thread_addr(uint32_t tmem_base, uint32_t col) {
+    return tmem_base + ((((threadIdx.x >> 5) & 3u) * 32u) << 16) + col;
+}
+
+
+// Split load: issue now, use after tmem_ld_wait16 on the same registers.  The wait instruction covers every
+// tcgen05.ld the thread has issued so far; passing the destination registers through it ("+r") is what keeps
+// the compiler from scheduling a consumer between the load and the wait.
+HB_D void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+HB_D void tmem_ld_wait16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// packed twiddle k (0..3) of a 16-register block: {w, wp} = columns 4k .. 4k+3
+HB_D TwPair tmem_pair(const uint32_t* r, int k) {
+    TwPair t;
+    t.w = ((uint64_t)r[4 * k + 1] << 32) | r[4 * k];
+    t.wp = ((uint64_t)r[4 * k + 3] << 32) | r[4 * k + 2];
+    return t;
+}
 
 // One polynomial = N/16 rows of 128 bytes; a TMA box holds at most 256 rows.
 template <class C>
@@ -399,6 +468,156 @@ HB_D bool vote_read() {
     return true;
 }
 
+// ---------------------------------------------------------------------------
+// tail-pass twiddles in tensor memory (arithmetic policies with kTmemTail, ntt_core.cuh)
+// ---------------------------------------------------------------------------
+// Layout in a thread's lane: row ri, packed slot s (1..15, slot 0 is padding) at columns (ri * 16 + s) * 4 ..+3
+// = {w lo, w hi, w' lo, w' hi}.  Compile-time switch for A/B measurements.
+#ifndef HB_TMEM_TAIL
+#define HB_TMEM_TAIL 1
+#endif
+template <class C>
+struct TmemTail {
+    static constexpr uint32_t ROWS = C::E / C::ROW;
+    static constexpr uint32_t COLS = ROWS * C::ROW * 4;                  // per thread
+    static constexpr uint32_t TOTAL = ((C::NT / 32 + 3) / 4) * COLS;     // four warps share a lane quarter
+    static constexpr bool kFits = C::LOGROW == 4 && TOTAL <= 512;
+};
+// this thread's first column
+template <class C>
+HB_D uint32_t tmem_tail_addr(uint32_t tmem_base) {
+    return tmem_thread_addr(tmem_base, (threadIdx.x >> 7) * TmemTail<C>::COLS);
+}
+// once per launch: every thread parks the twiddles of its own tail rows; `tail` = first tail entry of the
+// packed table (forward: ftwd + fwd_off(NP), inverse: itwd)
+template <class C>
+HB_D void tail_tw_to_tmem(uint32_t tid, const TwPair* tail, uint32_t ttail) {
+#pragma unroll
+    for (int ri = 0; ri < (int)TmemTail<C>::ROWS; ++ri) {
+        const TwPair* src = tail + tail_tw_base<C>(tail_row<C>(tid, ri));
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+            uint64_t w[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int slot = blk * 4 + k;
+                TwPair p = {0, 0};
+                if (slot != 0) p = ldpair(src + 32 * slot);
+                w[2 * k] = p.w;
+                w[2 * k + 1] = p.wp;
+            }
+            tmem_st16(ttail + (uint32_t)(ri * 64 + blk * 16), w);
+        }
+    }
+    tmem_wait_st();
+}
+// no instruction: the registers of a second load become "defined here" for the compiler (placed right
+// behind the tmem_ld_wait16 that covers both loads)
+HB_D void tmem_touch16(uint32_t* r) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+
+// fwd_tail_compute (ntt_core.cuh) with the twiddles read from tensor memory, four packed slots per load, each
+// load issued one butterfly stage ahead of its use (two 16-register buffers in turns)
+template <class C, class A, class F>
+HB_D void fwd_tail_compute_tmem(uint64_t* v, const A& a, const F& after_row) {
+    constexpr int ROWS = (int)TmemTail<C>::ROWS, S0 = C::HEAD;
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(a.ttail, ra);         // row 0, slots 0..3
+    tmem_ld16_issue(a.ttail + 16, rb);    //        slots 4..7
+    static_for<0, ROWS>([&](auto rc) {
+        constexpr int ri = decltype(rc)::value;
+        uint64_t* x = v + ri * 16;
+        const uint32_t ta = a.ttail + (uint32_t)ri * 64u;
+        tmem_ld_wait16(ra);
+        tmem_touch16(rb);
+        {   // stage 0: slot 1, pairs (j, j + 8)
+            const TwPair t = tmem_pair(ra, 1);
+            static_for<0, 8>([&](auto jc) { a.template fwd_at<S0>(x[decltype(jc)::value], x[decltype(jc)::value + 8], t); });
+        }
+        static_for<0, 2>([&](auto bc) {   // stage 1: slots 2, 3
+            constexpr int blk = decltype(bc)::value;
+            const TwPair t = tmem_pair(ra, 2 + blk);
+            static_for<0, 4>([&](auto jc) {
+                a.template fwd_at<S0 + 1>(x[blk * 8 + decltype(jc)::value], x[blk * 8 + decltype(jc)::value + 4], t);
+            });
+        });
+        tmem_ld16_issue(ta + 32, ra);     // slots 8..11
+        static_for<0, 4>([&](auto bc) {   // stage 2: slots 4..7
+            constexpr int blk = decltype(bc)::value;
+            const TwPair t = tmem_pair(rb, blk);
+            static_for<0, 2>([&](auto jc) {
+                a.template fwd_at<S0 + 2>(x[blk * 4 + decltype(jc)::value], x[blk * 4 + decltype(jc)::value + 2], t);
+            });
+        });
+        tmem_ld_wait16(ra);
+        tmem_ld16_issue(ta + 48, rb);     // slots 12..15
+        static_for<0, 4>([&](auto bc) {   // stage 3, first half: slots 8..11
+            constexpr int blk = decltype(bc)::value;
+            a.template fwd_at<S0 + 3>(x[blk * 2], x[blk * 2 + 1], tmem_pair(ra, blk));
+        });
+        tmem_ld_wait16(rb);
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64, ra);        // next row, slots 0..3
+        static_for<0, 4>([&](auto bc) {   // stage 3, second half: slots 12..15
+            constexpr int blk = decltype(bc)::value;
+            a.template fwd_at<S0 + 3>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(rb, blk));
+        });
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 16, rb);   // next row, slots 4..7
+        static_for<0, C::ROW>([&](auto kc) { x[decltype(kc)::value] = a.fwd_final(x[decltype(kc)::value]); });
+        after_row(ri);
+    });
+}
+
+// inv_tail_compute with the twiddles from tensor memory (stage d uses slots 2^(3-d) + blk)
+template <class C, class A>
+HB_D void inv_tail_compute_tmem(uint64_t* v, const A& a) {
+    constexpr int ROWS = (int)TmemTail<C>::ROWS;
+    uint32_t ra[16], rb[16];
+    tmem_ld16_issue(a.ttail + 32, ra);    // row 0, slots 8..11
+    tmem_ld16_issue(a.ttail + 48, rb);    //        slots 12..15
+    static_for<0, ROWS>([&](auto rc) {
+        constexpr int ri = decltype(rc)::value;
+        uint64_t* x = v + ri * 16;
+        const uint32_t ta = a.ttail + (uint32_t)ri * 64u;
+        tmem_ld_wait16(ra);
+        tmem_touch16(rb);
+        static_for<0, 4>([&](auto bc) {   // stage 0, first half: slots 8..11
+            constexpr int blk = decltype(bc)::value;
+            a.template inv_at<0>(x[blk * 2], x[blk * 2 + 1], tmem_pair(ra, blk));
+        });
+        tmem_ld16_issue(ta + 16, ra);     // slots 4..7
+        static_for<0, 4>([&](auto bc) {   // stage 0, second half: slots 12..15
+            constexpr int blk = decltype(bc)::value;
+            a.template inv_at<0>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(rb, blk));
+        });
+        tmem_ld_wait16(ra);
+        tmem_ld16_issue(ta, rb);          // slots 0..3
+        static_for<0, 4>([&](auto bc) {   // stage 1: slots 4..7
+            constexpr int blk = decltype(bc)::value;
+            const TwPair t = tmem_pair(ra, blk);
+            static_for<0, 2>([&](auto jc) {
+                a.template inv_at<1>(x[blk * 4 + decltype(jc)::value], x[blk * 4 + decltype(jc)::value + 2], t);
+            });
+        });
+        tmem_ld_wait16(rb);
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 32, ra);   // next row, slots 8..11
+        static_for<0, 2>([&](auto bc) {   // stage 2: slots 2, 3
+            constexpr int blk = decltype(bc)::value;
+            const TwPair t = tmem_pair(rb, 2 + blk);
+            static_for<0, 4>([&](auto jc) {
+                a.template inv_at<2>(x[blk * 8 + decltype(jc)::value], x[blk * 8 + decltype(jc)::value + 4], t);
+            });
+        });
+        {   // stage 3: slot 1
+            const TwPair t = tmem_pair(rb, 1);
+            static_for<0, 8>([&](auto jc) { a.template inv_at<3>(x[decltype(jc)::value], x[decltype(jc)::value + 8], t); });
+        }
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 48, rb);   // next row, slots 12..15
+    });
+}
+
 // returns false when the polynomial was deferred (fast-vote mode only)
 template <class C, int MODE, class A, class Xf, class Of>
 HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, const Of& of, const Prefetch& pf) {
@@ -441,7 +660,10 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         pf.template issue<C>(); // ... so the buffer can take the next polynomial
     }
     // each row leaves as soon as it is final: its staged TMA store drains while the next row is computed
-    fwd_tail_compute<C>(tid, v, ftw, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); });
+    if constexpr (A::kTmemTail)
+        fwd_tail_compute_tmem<C>(v, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); });
+    else
+        fwd_tail_compute<C>(tid, v, ftw, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); });
     return true;
 }
 
@@ -476,7 +698,8 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 #pragma unroll
         for (int e = 0; e < C::E; ++e) v[e] = a.enter_inv(v[e]);
     }
-    inv_tail_compute<C>(tid, v, itw, a);
+    if constexpr (A::kTmemTail) inv_tail_compute_tmem<C>(v, a);
+    else inv_tail_compute<C>(tid, v, itw, a);
     tail_store<C>(tid, W, v);
     if constexpr (C::WARPTAIL) {
         // the first head pass stays inside the words this warp has just written: no block barrier
@@ -563,7 +786,21 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         constexpr uint32_t COUNT = FWD ? SmemPlan<C>::HEAD_TW_FWD : SmemPlan<C>::HEAD_TW_INV;
         for (uint32_t e = tid; e < COUNT; e += C::NT) dst[e] = src[e];
     }
+    // ... and the twiddles of the tail pass into tensor memory (one CTA per SM at this shape: the whole TMEM)
+    constexpr bool TMEM_TAIL = SMEM_HEAD && HB_TMEM_TAIL != 0 && C::LOGN == 14 && TmemTail<C>::kFits;
+    if constexpr (TMEM_TAIL) {
+        if (tid < 32) tmem_alloc_all(reinterpret_cast<uint32_t*>(W + SmemPlan<C>::TMEM_WORD));
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     __syncthreads();
+    uint32_t tmem_base = 0, ttail = 0;
+    if constexpr (TMEM_TAIL) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(W + SmemPlan<C>::TMEM_WORD);
+        ttail = tmem_tail_addr<C>(tmem_base);
+        const ModTab& t0 = job.mod(0);
+        tail_tw_to_tmem<C>(tid, FWD ? t0.ftwd + C::fwd_off(C::NP) : t0.itwd, ttail);
+    }
     uint32_t head_s = 0;
     if constexpr (SMEM_HEAD) {
         // volatile: the address (and with it every load of these twiddles) stays behind the barrier above
@@ -583,7 +820,20 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         parity ^= 1;
         const ModTab& t = job.mod(item);
         bool done;
-        if constexpr (SMEM_HEAD && FWD && FP64 == 2) {
+        if constexpr (TMEM_TAIL && FWD && FP64 == 2) {
+            Fp64AltArithST a;
+            a.m = t.fd;
+            a.head_s = head_s;
+            a.ttail = ttail;
+            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (TMEM_TAIL) {
+            Fp64ArithST a;
+            a.m = t.fd;
+            a.head_s = head_s;
+            a.ttail = ttail;
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (SMEM_HEAD && FWD && FP64 == 2) {
             Fp64AltArithS a;
             a.m = t.fd;
             a.head_s = head_s;
@@ -630,6 +880,11 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     }
     // staged TMA stores read shared memory asynchronously: drain before exit
     if (FWD && SmemPlan<C>::kStagedStore && (tid & 31u) == 0) tma_store_wait_read();
+    if constexpr (TMEM_TAIL) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) tmem_dealloc_all(tmem_base);
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -203,6 +203,7 @@ struct ExactArith {
     using Tw = TwPair;
     static constexpr bool kFp64 = false;
     static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    static constexpr bool kTmemTail = false;   // tail-pass twiddles in tensor memory (Fp64ArithST)
     HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     uint64_t q, twoq;
     InvScale sc;
@@ -231,6 +232,7 @@ struct FastArith {
     using Tw = TwPair;
     static constexpr bool kFp64 = false;
     static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    static constexpr bool kTmemTail = false;   // tail-pass twiddles in tensor memory (Fp64ArithST)
     HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     FastMod m;
     InvScale sc;
@@ -263,17 +265,20 @@ struct Fp64Arith {
     using Tw = TwPair;
     static constexpr bool kFp64 = true;
     static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    static constexpr bool kTmemTail = false;   // tail-pass twiddles in tensor memory (Fp64ArithST)
     HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     static constexpr bool kLazyInv = false;
     Fp64Mod m;
     HB_HD Tw ld(const Tw* p) const { return ldpair(p); }
     HB_HD uint64_t enter_fwd(uint64_t x) const { return d2u(fp_from_int(x)); }               // [0, 1.25q)
-    HB_HD uint64_t enter_inv(uint64_t x) const { return d2u(fp_cred(fp_from_int(x), m)); }   // |v| <= q/2
+    HB_HD uint64_t enter_inv(uint64_t x) const { return d2u(fp_from_int(x)); }               // [0, 1.25q): stage E = 0 copes
     HB_HD void fwd(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd_bfly_fp64(X, Y, t.w, t.wp, m); }
     template <int S> HB_HD void fwd_at(uint64_t& X, uint64_t& Y, const TwPair& t) const { fwd(X, Y, t); }
     HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical(u2d(x), m); }
+    // E = 0 marks the very first stage of a transform (inv_tail_compute): words as they entered
     template <int E> HB_HD void inv_at(uint64_t& X, uint64_t& Y, const TwPair& t) const {
-        inv_bfly_fp64(X, Y, t.w, t.wp, m);
+        if constexpr (E == 0) inv_bfly_fp64_first(X, Y, t.w, t.wp, m);
+        else inv_bfly_fp64(X, Y, t.w, t.wp, m);
     }
     template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last_bfly_fp64(X, Y, m); }
 };
@@ -322,6 +327,20 @@ struct Fp64AltArithS : Fp64ArithS {
     HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical_full(u2d(x), m); }
 };
 
+// The S policies with the twiddles of the TAIL pass in tensor memory (ntt_block.cuh, tail_tw_to_tmem): a
+// persistent CTA of the plain batched calls keeps one modulus, and the 15 twiddles of each of a thread's tail
+// rows are the same for every polynomial it transforms, so each thread parks them once per launch in its own
+// lane of the SM's otherwise idle TMEM (2 rows x 16 slots x 16 bytes = 128 columns) and reads them back with
+// tcgen05.ld (12 cycles) instead of pulling 245 KiB per transform through L2.
+struct Fp64ArithST : Fp64ArithS {
+    static constexpr bool kTmemTail = true;
+    uint32_t ttail;    // tensor-memory address of this thread's slot 0 (row 0)
+};
+struct Fp64AltArithST : Fp64AltArithS {
+    static constexpr bool kTmemTail = true;
+    uint32_t ttail;
+};
+
 // inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
 // E = log2 of the bound (in units of q) of the words entering the stage
 struct LazyInvArith {
@@ -329,6 +348,7 @@ struct LazyInvArith {
     using Tw = TwPair;
     static constexpr bool kFp64 = false;
     static constexpr bool kSmemHead = false;   // head-pass twiddles in shared memory (Fp64ArithS)
+    static constexpr bool kTmemTail = false;   // tail-pass twiddles in tensor memory (Fp64ArithST)
     HB_HD Tw ld_head(const Tw* p) const { return ldpair(p); }
     FastMod m;
     InvScale sc;
@@ -401,6 +421,7 @@ struct SmallArith {
     using elem = uint32_t;
     using Tw = Tw32;
     static constexpr bool kSmemHead = false;
+    static constexpr bool kTmemTail = false;
     HB_HD Tw ld_head(const Tw* p) const { return ld(p); }
     Small32 m;
     HB_HD Tw ld(const Tw* p) const {
@@ -749,7 +770,8 @@ HB_HD void inv_tail_compute(uint32_t tid, typename A::elem* v, const typename A:
     static_for<0, C::E / C::ROW>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         const uint32_t row = tail_row<C>(tid, ri);
-        inv_group<C::LOGROW, false, 32, 1>(v + ri * C::ROW, tw + tail_tw_base<C>(row), a);
+        // E0: the lazy policy's bound exponent (words enter below 2q); 0 for the others = "first stage of the transform"
+        inv_group<C::LOGROW, false, 32, (A::kLazyInv ? 1 : 0)>(v + ri * C::ROW, tw + tail_tw_base<C>(row), a);
     });
     if constexpr (A::kLazyInv) {
         static_assert(InvLazy<C>::valid(), "lazy inverse bound schedule broken for this shape");

@@ -374,6 +374,8 @@ static int fp64_properties() {
             const double bound = (double)q * (0.5 + (double)ya / 18014398509481984.0) + 1.0;
             if (fabs(rr) > bound) ++fbad;
             if (fp_to_canonical(rr, m) != want) ++fbad;
+            // a product of a word below 1.5 q is below 0.75 q <= 2^51: the sign fix alone makes it canonical
+            if (fabs(rr) > 2251799813685248.0 || fp_canon_signed(rr, m) != want) ++fbad;
             // full correction: any |x| < 2 q  ->  an integer congruent to x within q/2 (1 + 2^-40)
             {
                 const uint64_t xa = r[1] % (2 * q);
