@@ -180,6 +180,7 @@ struct hexl_b200_ks_plan {
     uint64_t* d_keys = nullptr;     // D * 2 * K * n
     hb::TwPair* d_keys_sh = nullptr;  // same, with Shoup factors (fast path)
     void* d_keys_fused = nullptr;     // key quads in the fused kernel's layout (keyswitch_fused.cu)
+    hb::TwPair* d_keys_fp = nullptr;  // {centred key, key / q} doubles (FP64-pipe multiply-accumulate)
     uint64_t* d_small = nullptr;    // msf, msf_p
     hb::ModTab* d_tabs = nullptr;
     hb::Divisor* d_divs = nullptr;
@@ -267,6 +268,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "ks_fused")) {
         hb::g_ks_fused = value ? 1 : 0;     // read when a plan is created and on every call
+        return 0;
+    }
+    if (!strcmp(name, "ks_mac_fp64")) {
+        hb::g_ks_mac_fp64 = value ? 1 : 0;   // read on every call
         return 0;
     }
     if (!strcmp(name, "ks_sub_items")) {
@@ -667,6 +672,15 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         p->dev.keys_sh = p->d_keys_sh;
         g_launches += 1;
     }
+    p->dev.keys_fp = nullptr;
+    if (p->dev.fast_ok && p->dev.fp64_alt_ok && logn == 14) {
+        if ((e = cudaMalloc(&p->d_keys_fp, D * 2 * K * n * sizeof(hb::TwPair))))
+            return cleanup(cuda_fail(e, "cudaMalloc FP64 keys"));
+        if ((e = hb::launch_ks_prepare_keys_fp64(p->dev, p->d_keys_fp, 0)) || (e = cudaDeviceSynchronize()))
+            return cleanup(cuda_fail(e, "prepare FP64 keys"));
+        p->dev.keys_fp = p->d_keys_fp;
+        g_launches += 1;
+    }
     p->dev.keys_fused = nullptr;
     {
         hb::KsDev probe = p->dev;
@@ -686,7 +700,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
 
 int hexl_b200_ks_plan_destroy(hexl_b200_ks_plan* p) {
     if (!p) return 0;
-    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_keys_sh); cudaFree(p->d_keys_fused); cudaFree(p->d_small);
+    cudaFree(p->d_packed); cudaFree(p->d_keys); cudaFree(p->d_keys_sh); cudaFree(p->d_keys_fp); cudaFree(p->d_keys_fused); cudaFree(p->d_small);
     cudaFree(p->d_tabs); cudaFree(p->d_divs); cudaFree(p->ws);
     delete p;
     return 0;

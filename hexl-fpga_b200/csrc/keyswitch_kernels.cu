@@ -34,6 +34,9 @@ int g_ks_fused = 0;
 // (V, D*D polynomials per item) inside the 126 MB L2 between the transform that writes them and the
 // multiply-accumulate that reads them, so they never travel to HBM.
 int g_ks_sub_items = 0;
+// Multiply-accumulate on the FP64 pipe (k_ks_mac_fp64) fed by S2 transforms that leave the raw doubles of their
+// last stage in V (option "ks_mac_fp64", default on; needs every modulus <= 2^51 (1 + 1/32) and N = 16384)
+int g_ks_mac_fp64 = 1;
 int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys, 2 = 128-bit accumulators (both slower: latency bound)
 
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
@@ -211,6 +214,84 @@ k_ks_mac_fast(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* _
     }
 }
 
+// FP64-pipe version (every modulus <= 2^51 (1 + 1/32), the moduli of the every-other-stage forward butterflies).
+// The integer version above is bound by the integer multiplier (76 % busy, 18 IMAD per key product); here a key
+// product is the six-instruction FP64 modular product of the butterflies, its twiddle the key itself:
+// keys_fp[j][c][i][l] = {centred key mod q_i, fl(key / q_i)}.  And the stage in front does not have to produce
+// canonical words any more: V holds the raw doubles of S2's last butterfly stage (|v| <= 1.92 q < 2^52, k_ks_ntt1
+// with FP64 = 3: no exit conversion, 12 of a transform's ~170 scheduler cycles per word), read here as they are.
+// The digit under its own modulus comes from the caller's t_target as integers (converted on the fly; a word
+// above 2^52 -- out of contract, the integer kernels accept it -- is reduced first).  Every term is an exact
+// integer with |r| <= q (1/2 + |y| 2^-54) <= 0.75 q; the sums take a full correction every fourth term, so they
+// stay below 0.5 q + 4 * 0.75 q = 3.5 q < 2^53 and every addition is exact.
+template <int kMacItems>
+__global__ void __launch_bounds__(256, 3)
+k_ks_mac_fp64(KsDev ks, const uint64_t* __restrict__ t_target, const uint64_t* __restrict__ V,
+              uint64_t* __restrict__ ACC, uint32_t items) {
+    const uint32_t N = 1u << ks.logn;
+    const uint32_t l = (blockIdx.x * 256 + threadIdx.x) * 2;
+    const uint32_t r = blockIdx.y, b0 = blockIdx.z * kMacItems;
+    const uint32_t idx = (r == ks.D) ? ks.K - 1 : r;
+    const Fp64Mod m = ks.tabs[idx].fd;
+    const uint64_t q = ks.tabs[idx].q, mu = ks.tabs[idx].mu;
+    double a0[kMacItems][2], a1[kMacItems][2];
+#pragma unroll
+    for (int it = 0; it < kMacItems; ++it) a0[it][0] = a0[it][1] = a1[it][0] = a1[it][1] = 0.0;
+    for (uint32_t j = 0; j < ks.D; ++j) {
+        const TwPair* k0 = ks.keys_fp + (((size_t)j * 2 + 0) * ks.K + idx) * N + l;
+        const TwPair* k1 = ks.keys_fp + (((size_t)j * 2 + 1) * ks.K + idx) * N + l;
+        // all loads of the digit in flight before the first product waits on one (cf. k_ks_mac_fast)
+        uint64_t x0[kMacItems], x1[kMacItems];
+#pragma unroll
+        for (int it = 0; it < kMacItems; ++it) {
+            const uint32_t b = min(b0 + it, items - 1);
+            const uint64_t* op = (j == r) ? t_target + ((size_t)b * ks.D + j) * N
+                                          : V + ((size_t)b * ks.D * ks.D + ks_y(ks.D, r, j)) * N;
+            ld2(op + l, x0[it], x1[it]);
+        }
+        TwPair u0, u1, w0, w1;
+        ld_keys2(k0, u0, u1);
+        ld_keys2(k1, w0, w1);
+        if (j == r) {   // caller integers -> doubles (uniform branch: r is the block's)
+#pragma unroll
+            for (int it = 0; it < kMacItems; ++it) {
+                if ((x0[it] | x1[it]) >> 52) {
+                    x0[it] = barrett_reduce64(x0[it], q, mu);
+                    x1[it] = barrett_reduce64(x1[it], q, mu);
+                }
+                x0[it] = d2u(fp_from_int(x0[it]));
+                x1[it] = d2u(fp_from_int(x1[it]));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kMacItems; ++it) {
+            a0[it][0] = fp_add(a0[it][0], fp_mulmod(u2d(x0[it]), u2d(u0.w), u2d(u0.wp), m));
+            a0[it][1] = fp_add(a0[it][1], fp_mulmod(u2d(x1[it]), u2d(u1.w), u2d(u1.wp), m));
+            a1[it][0] = fp_add(a1[it][0], fp_mulmod(u2d(x0[it]), u2d(w0.w), u2d(w0.wp), m));
+            a1[it][1] = fp_add(a1[it][1], fp_mulmod(u2d(x1[it]), u2d(w1.w), u2d(w1.wp), m));
+        }
+        if ((j & 3u) == 3u) {
+#pragma unroll
+            for (int it = 0; it < kMacItems; ++it) {
+                a0[it][0] = fp_cred_full(a0[it][0], m);
+                a0[it][1] = fp_cred_full(a0[it][1], m);
+                a1[it][0] = fp_cred_full(a1[it][0], m);
+                a1[it][1] = fp_cred_full(a1[it][1], m);
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < kMacItems; ++it) {
+        const uint32_t b = b0 + it;
+        if (b < items) {
+            st2(ACC + (((size_t)b * 2 + 0) * ks.R + r) * N + l, fp_to_canonical_full(a0[it][0], m),
+                fp_to_canonical_full(a0[it][1], m));
+            st2(ACC + (((size_t)b * 2 + 1) * ks.R + r) * N + l, fp_to_canonical_full(a1[it][0], m),
+                fp_to_canonical_full(a1[it][1], m));
+        }
+    }
+}
+
 #ifdef HB_EXPERIMENTAL_VARIANTS
 // Wide-accumulator version (all moduli < 2^58, D <= 16): no per-term reduction at
 // all.  Every term is a plain 64x64 product of a reduced operand and a reduced
@@ -358,6 +439,26 @@ __global__ void k_ks_prepare_keys(KsDev ks, TwPair* __restrict__ out) {
         out[e] = t;
         const_cast<uint64_t*>(ks.keys)[e] = k;   // the plan's own device copy: keep it reduced (k_ks_mac_wide)
     }
+}
+
+// one-time per plan: keys_fp from the raw keys (run after k_ks_prepare_keys: ks.keys is reduced by then, which
+// this kernel does not rely on)
+__global__ void k_ks_prepare_keys_fp64(KsDev ks, TwPair* __restrict__ out) {
+    const uint32_t N = 1u << ks.logn;
+    const size_t total = (size_t)ks.D * 2 * ks.K * N;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t i = (uint32_t)((e / N) % ks.K);
+        const uint64_t q = ks.tabs[i].q;
+        const double kc = fp_centred(ks.keys[e] % q, q);
+        TwPair t;
+        t.w = d2u(kc);
+        t.wp = d2u(fp_quot(kc, q));
+        out[e] = t;
+    }
+}
+cudaError_t launch_ks_prepare_keys_fp64(const KsDev& ks, TwPair* out, cudaStream_t st) {
+    k_ks_prepare_keys_fp64<<<148 * 4, 256, 0, st>>>(ks, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st) {
@@ -523,6 +624,10 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     int nl = 0;
     // FP64 stages: tail rows dealt out by warp where the shape allows it (ntt_core.cuh, NttCfg::WARPTAIL)
     using CW = typename KsWarpTailCfg<C>::type;
+    // V as raw doubles + the multiply-accumulate on the FP64 pipe (not in the rounds of ks_sub_items, whose
+    // multiply-accumulate is the integer one)
+    const bool mac_fp64 = !fused && g_ks_mac_fp64 && ks.fast_ok && ks.fp64_ok && ks.fp64_alt_ok && ks.keys_fp &&
+                          !std::is_same<CW, C>::value && !(g_ks_sub_items > 0 && (uint64_t)g_ks_sub_items < items);
     if (fused) {
         // S1, then S2 + S3 + S4 in one kernel (the sums in tensor memory), then S5
         if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
@@ -557,7 +662,9 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
             if (launches) *launches = nl + 2;
             return cudaSuccess;
         }
-        if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
+        if (mac_fp64) {
+            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+        } else if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
             if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 2>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
         } else {
             if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
@@ -592,7 +699,10 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         k_ks_mac_fast<8><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
     } else
 #endif
-    if (ks.fast_ok && ks.keys_sh) {
+    if (mac_fp64) {
+        dim3 gf(C::N / 512, ks.R, (unsigned)((items + 3) / 4));
+        k_ks_mac_fp64<4><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
+    } else if (ks.fast_ok && ks.keys_sh) {
         dim3 gf(C::N / 512, ks.R, (unsigned)((items + 3) / 4));
         k_ks_mac_fast<4><<<gf, 256, 0, st>>>(ks, t_target, V, ACC, (uint32_t)items);
     } else

@@ -27,6 +27,9 @@ struct KsDev {
     const uint64_t* msf;    // [K] modswitch_factors[i] mod q_i
     const uint64_t* msf_p;  // [K] Shoup factors of msf
     const void* keys_fused; // key quads in the layout of the fused kernel (keyswitch_fused.cu), or null
+    // same index space as keys_sh: {centred key mod q_i, its quotient by q_i} as doubles, for the multiply-
+    // accumulate on the FP64 pipe (k_ks_mac_fp64); null unless fp64_alt_ok
+    const TwPair* keys_fp;
 };
 
 bool ntt_shape_supported(uint32_t logn);
@@ -114,6 +117,8 @@ extern int g_warp_tail;
 extern int g_pdl;
 size_t ks_scratch_words_per_item(const KsDev& ks);
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);
+cudaError_t launch_ks_prepare_keys_fp64(const KsDev& ks, TwPair* out, cudaStream_t st);
+extern int g_ks_mac_fp64;
 cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
                             uint64_t* scratch, cudaStream_t st, int* launches);
 

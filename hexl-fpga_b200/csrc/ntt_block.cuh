@@ -749,7 +749,8 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 //   const ModTab& mod(item)
 //   Xf xf(item), Of of(item, store_map)
 // `list`: the deferred list (written in kFastVote, read in kExactList mode).
-// FP64: 0 integer butterflies, 1 FP64-pipe butterflies, 2 (forward only) FP64 with a full correction every other stage
+// FP64: 0 integer butterflies, 1 FP64-pipe butterflies, 2 (forward only) FP64 with a full correction every other stage,
+//       3 (forward only) as 2 with the raw doubles as output (|v| <= 1.92 q, any representative of the residue)
 template <class C, bool FWD, int MODE, class Job, bool LAZY = false, int FP64 = 0>
 HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
                          uint32_t* list) {
@@ -837,6 +838,10 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
             Fp64AltArithS a;
             a.m = t.fd;
             a.head_s = head_s;
+            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (FWD && FP64 == 3) {
+            Fp64ArithRaw a;      // as FP64 == 2, raw doubles out
+            a.m = t.fd;
             done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (FWD && FP64 == 2) {
             Fp64AltArith a;

@@ -327,6 +327,13 @@ struct Fp64AltArithS : Fp64ArithS {
     HB_HD uint64_t fwd_final(uint64_t x) const { return fp_to_canonical_full(u2d(x), m); }
 };
 
+// Forward transform (full correction every other stage) whose tail hands over the raw doubles, |v| <= 1.92 q
+// < 2^52, instead of canonical words: for consumers that multiply on the FP64 pipe anyway (the polynomial
+// multiply of polymul_fused.cu, the keyswitch multiply-accumulate k_ks_mac_fp64)
+struct Fp64ArithRaw : Fp64AltArith {
+    HB_HD uint64_t fwd_final(uint64_t x) const { return x; }
+};
+
 // The S policies with the twiddles of the TAIL pass in tensor memory (ntt_block.cuh, tail_tw_to_tmem): a
 // persistent CTA of the plain batched calls keeps one modulus, and the 15 twiddles of each of a thread's tail
 // rows are the same for every polynomial it transforms, so each thread parks them once per launch in its own

@@ -22,11 +22,7 @@ namespace hb {
 
 int g_polymul_fused = 1;   // option "polymul_fused"
 
-// forward transform (full correction every other stage, modarith.cuh) whose tail hands over the raw
-// doubles (|v| <= 1.92 q < 2^52) instead of canonical words
-struct Fp64ArithRaw : Fp64AltArith {
-    HB_HD uint64_t fwd_final(uint64_t x) const { return x; }
-};
+// (Fp64ArithRaw: ntt_core.cuh)
 // inverse transform whose input rows already hold centred doubles with |v| <= q/2 (1 + 2^-20)
 struct Fp64ArithPre : Fp64Arith {
     HB_HD uint64_t enter_inv(uint64_t x) const { return x; }

@@ -84,6 +84,35 @@ def test_fused_kernel_and_l2_rounds(hb, n, D, K, batch, opt, val):
     assert np.array_equal(got, p.expected())
 
 
+@pytest.mark.parametrize("n,D,K,batch", [(16384, 7, 8, 5), (16384, 6, 7, 3), (16384, 2, 8, 4), (16384, 1, 2, 3)])
+def test_integer_multiply_accumulate_matches_the_fp64_one(hb, n, D, K, batch):
+    """ks_mac_fp64 = 1 (default at N = 16384 with moduli up to 2^51 (1 + 1/32)): stage S2 leaves raw doubles in V
+    and stage S3 multiplies on the FP64 pipe; 0: canonical words and the integer Shoup products.  Same bits,
+    also with target words the FP64 product does not take as they are (>= 2^52: reduced first) -- the digit
+    under its own modulus reaches the multiply-accumulate straight from the caller's buffer."""
+    p = KsProblem(n, D, K, batch, 51, seed=77)
+    t = p.t_target.reshape(batch, D, n).copy()
+    t[0, 0, 3] = np.uint64((1 << 63) + 12345)          # garbage: every kernel family must agree on it
+    t[batch - 1, D - 1, n - 1] = np.uint64((1 << 52) + 1)
+    plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
+    out = []
+    for opt in (1, 0):
+        hb.set_option("ks_mac_fp64", opt)
+        try:
+            res = gpu(p.result)
+            plan.keyswitch(res, gpu(p.t_target), batch)
+            clean = res.cpu().numpy().view(np.uint64).copy()
+            res = gpu(p.result)
+            plan.keyswitch(res, gpu(t.reshape(batch, -1)), batch)
+            out.append((clean, res.cpu().numpy().view(np.uint64).copy()))
+        finally:
+            hb.set_option("ks_mac_fp64", 1)
+    plan.close()
+    assert np.array_equal(out[0][0], p.expected())
+    assert np.array_equal(out[1][0], p.expected())
+    assert np.array_equal(out[0][1], out[1][1])
+
+
 def test_out_of_range_target_words_go_to_the_exact_kernel(hb):
     """t_target words in [1.25 q, 2q) are outside the FP64 arithmetic's contract but inside the
     integer kernels': the first stage's range vote must send those digits to the exact kernel, so
