@@ -270,6 +270,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         hb::g_ks_fused = value ? 1 : 0;     // read when a plan is created and on every call
         return 0;
     }
+    if (!strcmp(name, "ks_s5_fp64")) {
+        hb::g_ks_s5_fp64 = value ? 1 : 0;    // read on every call
+        return 0;
+    }
     if (!strcmp(name, "ks_mac_fp64")) {
         hb::g_ks_mac_fp64 = value ? 1 : 0;   // read on every call
         return 0;
@@ -579,7 +583,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     }
     p->n = n; p->D = D; p->K = K; p->R = R;
 
-    std::vector<uint64_t> h_tables(K * 4 * n), h_small(2 * K);
+    std::vector<uint64_t> h_tables(K * 4 * n), h_small(4 * K);   // msf, its Shoup factors, {centred msf, msf / q} as doubles
     std::vector<hb::ModTab> h_tabs(K);
     std::vector<hb::Divisor> h_divs(K);
     auto cleanup = [&](int rc) {
@@ -595,7 +599,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     for (uint64_t i = 0; i < K; ++i) fp64_all = fp64_all && hb::fp64_modulus_ok(moduli[i]);
     if ((e = cudaMalloc(&d_raw, K * 4 * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc raw tables"));
     if ((e = cudaMalloc(&p->d_keys, D * 2 * K * n * 8))) return cleanup(cuda_fail(e, "cudaMalloc keys"));
-    if ((e = cudaMalloc(&p->d_small, 2 * K * 8))) return cleanup(cuda_fail(e, "cudaMalloc small"));
+    if ((e = cudaMalloc(&p->d_small, 4 * K * 8))) return cleanup(cuda_fail(e, "cudaMalloc small"));
     if ((e = cudaMalloc(&p->d_tabs, K * sizeof(hb::ModTab)))) return cleanup(cuda_fail(e, "cudaMalloc tabs"));
     if ((e = cudaMalloc(&p->d_divs, K * sizeof(hb::Divisor)))) return cleanup(cuda_fail(e, "cudaMalloc divs"));
 
@@ -621,6 +625,9 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         h_divs[i] = hb::make_divisor(q);
         h_small[i] = msf[i] % q;                       // host/src/fpga.cpp:1057-1061
         h_small[K + i] = nt::shoup(h_small[i], q);
+        const double msf_c = hb::fp_centred(h_small[i], q);
+        h_small[2 * K + i] = hb::d2u(msf_c);
+        h_small[3 * K + i] = hb::d2u(hb::fp_quot(msf_c, q));
     }
     e = cudaMemcpy(d_raw, h_tables.data(), K * 4 * n * 8, cudaMemcpyHostToDevice);
     for (uint64_t i = 0; i < K && e == cudaSuccess; ++i) {
@@ -638,7 +645,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     for (uint64_t j = 0; j < D; ++j)
         if ((e = cudaMemcpy(p->d_keys + j * 2 * K * n, keys[j], 2 * K * n * 8, cudaMemcpyHostToDevice)))
             return cleanup(cuda_fail(e, "upload keys"));
-    if ((e = cudaMemcpy(p->d_small, h_small.data(), 2 * K * 8, cudaMemcpyHostToDevice)))
+    if ((e = cudaMemcpy(p->d_small, h_small.data(), 4 * K * 8, cudaMemcpyHostToDevice)))
         return cleanup(cuda_fail(e, "upload msf"));
     if ((e = cudaMemcpy(p->d_tabs, h_tabs.data(), K * sizeof(hb::ModTab), cudaMemcpyHostToDevice)))
         return cleanup(cuda_fail(e, "upload tabs"));
@@ -663,6 +670,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;
     p->dev.msf = p->d_small; p->dev.msf_p = p->d_small + K;
+    p->dev.msf_fp = p->dev.fp64_ok ? reinterpret_cast<const double*>(p->d_small + 2 * K) : nullptr;
     p->dev.keys_sh = nullptr;
     if (p->dev.fast_ok) {
         if ((e = cudaMalloc(&p->d_keys_sh, D * 2 * K * n * sizeof(hb::TwPair))))

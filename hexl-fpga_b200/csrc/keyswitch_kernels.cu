@@ -37,6 +37,10 @@ int g_ks_sub_items = 0;
 // Multiply-accumulate on the FP64 pipe (k_ks_mac_fp64) fed by S2 transforms that leave the raw doubles of their
 // last stage in V (option "ks_mac_fp64", default on; needs every modulus <= 2^51 (1 + 1/32) and N = 16384)
 int g_ks_mac_fp64 = 1;
+// Stage S5 with its load transform and its modswitch / accumulate epilogue on the FP64 pipe, `result` read and
+// written through the warp's staging slice by TMA (option "ks_s5_fp64", default on; same conditions as
+// ks_mac_fp64 plus all moduli within 25 % of each other)
+int g_ks_s5_fp64 = 1;
 int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys, 2 = 128-bit accumulators (both slower: latency bound)
 
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
@@ -47,8 +51,13 @@ HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
 template <class C>
 struct JobIntt1 {
     static constexpr bool kOneModulus = false;
+    // N = 16384, FP64 kernels: the grid walks over the polynomials modulus-major, so that a CTA keeps one modulus
+    // for items / gridDim.x transforms in a row and its twiddles stay in shared / tensor memory (ntt_persistent)
+    static constexpr bool kModulusRuns = C::LOGN == 14;
     KsDev ks;
     uint64_t* U;
+    uint32_t B = 0;          // items of the chunk (0: walk in storage order)
+    HB_D uint32_t order(uint32_t i) const { return B ? (i % B) * ks.D + i / B : i; }
     HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
@@ -64,9 +73,27 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_co
 template <class C>
 struct JobNtt1 {
     static constexpr bool kOneModulus = false;
+    static constexpr bool kModulusRuns = C::LOGN == 14;
     KsDev ks;
     uint64_t* V;
     uint32_t item0 = 0;     // first (item, pair) index of this launch (rounds of a few items)
+    uint32_t B = 0;         // items of the chunk (0: walk in storage order)
+    // modulus-major walk: output modulus r < D owns B * (D - 1) polynomials, the special prime B * D
+    HB_D uint32_t order(uint32_t i) const {
+        if (!B) return i;
+        const uint32_t D = ks.D, lo = B * (D - 1);
+        uint32_t b, y;
+        if (i < D * lo) {
+            const uint32_t r = i / lo, rem = i % lo;
+            b = rem / (D - 1);
+            y = r * (D - 1) + rem % (D - 1);
+        } else {
+            const uint32_t rem = i - D * lo;
+            b = rem / D;
+            y = D * (D - 1) + rem % D;
+        }
+        return b * D * D + y;
+    }
     HB_D void decode(uint32_t item, uint32_t& b, uint32_t& r, uint32_t& j) const {
         const uint32_t D = ks.D, per = D * D;
         item += item0;
@@ -469,7 +496,9 @@ cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st
 // ---- S4 -------------------------------------------------------------------
 template <class C>
 struct JobIntt2 {
-    static constexpr bool kOneModulus = false;
+    static constexpr bool kOneModulus = true;    // the special prime
+    static constexpr bool kModulusRuns = false;
+    HB_D uint32_t order(uint32_t i) const { return i; }
     KsDev ks;
     uint64_t* ACC;
     HB_D uint32_t poly(uint32_t item) const { return item * ks.R + ks.D; }   // [b][c][D]
@@ -551,9 +580,109 @@ struct OfKsFinal {
         }
     }
 };
+// The same epilogue for the kernel whose transform hands over raw doubles (FP64 = 3): same data movement (the
+// warp's rows transposed through its staging slice, acc / result touched with coalesced 8-byte accesses), the
+// arithmetic on the FP64 pipe: a - w (|.| <= 2.92 q) takes the full correction, the product with msf is the
+// six-instruction one, and its canonical value meets the caller's word in the reference's own integer add_mod
+// (so a `result` word outside [0, q) gives the reference's wrap-around value, as before).
+// Two other data paths were built and measured slower than this one (stage S5 of 1024 items at 7/8: 2307 us
+// with the integer epilogue): `result` through the slice by TMA in both directions with acc read by the
+// row's owner as 16-byte pieces (2493 us), and the same with 32-byte row accesses instead of the TMA store
+// (2634 us) -- 32 different lines per warp instruction cost more than the transposition saves.
+// The functor carries the job and the item only: pointers and constants are re-derived where they are used,
+// so nothing of it stays in registers through the butterflies.
+template <class C>
+struct JobNtt2Fp;
+template <class CC>
+struct OfKsFinalFp {
+    const JobNtt2Fp<CC>* job;
+    uint32_t item;
+    template <class C>
+    HB_D void prefetch(uint32_t tid) const {
+        const uint64_t* acc = job->acc_poly(item);
+        const uint64_t* res = job->res_poly(item);
+#pragma unroll
+        for (int ri = 0; ri < C::E / 16; ++ri) {
+            const uint32_t off = tail_row<C>(tid, ri) * 16;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(acc + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + off));
+        }
+    }
+    template <class C>
+    HB_D void store(uint32_t rw, const uint64_t* v) const {
+        static_assert(SmemPlan<C>::kStagedStore, "the epilogue transposes through the staging slices");
+        const uint32_t lane = threadIdx.x & 31u;
+        uint64_t* slice = smem_poly<C>() + C::N + (threadIdx.x >> 5) * 512;
+        const uint32_t base = (rw - lane) * 16;   // first word of the warp's 32 rows
+        const uint64_t* acc = job->acc_poly(item) + base + lane;
+        uint64_t* res = job->res_poly(item) + base + lane;
+        // all 32 global loads of the round are issued before anything waits on them
+        uint64_t a[16], r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            a[i] = __ldg(acc + 32 * i);
+            r[i] = res[32 * i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
+        __syncwarp();
+        const uint32_t i = item % job->ks.D;
+        const ModTab* t = job->ks.tabs + i;
+        Fp64Mod m;                   // the fields the epilogue's arithmetic reads
+        m.q = t->fd.q;
+        m.nq = t->fd.nq;
+        m.inv_q = t->fd.inv_q;
+        m.qi = t->q;
+        const uint64_t q = t->q;
+        const double msf_c = job->ks.msf_fp[i], msf_q = job->ks.msf_fp[job->ks.K + i];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t w = lane + 32u * k;
+            const uint32_t row = w >> 4, ch = (w >> 1) & 7u;
+            const double x = u2d(slice[row * 16 + ((ch ^ (row & 7u)) << 1) + (w & 1u)]);
+            const double d = fp_cred_full(fp_add(fp_from_int(a[k]), -x), m);
+            const uint64_t o = fp_canon_signed(fp_mulmod(d, msf_c, msf_q, m), m);
+            res[32 * k] = add_mod(r[k], o, q);
+        }
+    }
+};
+template <class C>
+struct JobNtt2Fp {
+    static constexpr bool kOneModulus = false;
+    static constexpr bool kModulusRuns = C::LOGN == 14;
+    KsDev ks;
+    const uint64_t* ACC;
+    uint64_t* result;
+    CUtensorMap rmap;        // result: [items * 2 * D polynomials], box 32 rows
+    uint32_t B2 = 0;         // 2 * items of the chunk (0: walk in storage order)
+    HB_D uint32_t order(uint32_t i) const { return B2 ? (i % B2) * ks.D + i / B2 : i; }
+    HB_D uint32_t src_row(uint32_t item) const { return ((item / ks.D) * ks.R + ks.D) * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
+    // item = bc * D + i:  ACC[bc][i], result[bc][i]
+    HB_D const uint64_t* acc_poly(uint32_t item) const { return ACC + ((size_t)(item / ks.D) * ks.R + item % ks.D) * C::N; }
+    HB_D uint64_t* res_poly(uint32_t item) const { return result + (size_t)item * C::N; }
+    HB_D uint32_t res_row(uint32_t item) const { return item * (C::N / 16); }
+    HB_D XfKsConvertFp xf(uint32_t item) const {
+        const ModTab& t = ks.tabs[item % ks.D];
+        const uint64_t h = ks.tabs[ks.K - 1].q >> 1;
+        const uint64_t hr = barrett_reduce64(h, t.q, t.mu);
+        return XfKsConvertFp{fp_centred(hr ? t.q - hr : 0, t.q)};      // fix = -floor(qk / 2) mod q
+    }
+    HB_D OfKsFinalFp<C> of(uint32_t item, const CUtensorMap*) const { return OfKsFinalFp<C>{this, item}; }
+};
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt2f(const __grid_constant__ CUtensorMap tmap,
+        const __grid_constant__ CUtensorMap smap, const __grid_constant__ JobNtt2Fp<C> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, true, kFastTrust, JobNtt2Fp<C>, false, 3>(&tmap, &smap, job, n_items, list);
+}
+
 template <class C>
 struct JobNtt2 {
     static constexpr bool kOneModulus = false;
+    static constexpr bool kModulusRuns = false;
+    HB_D uint32_t order(uint32_t i) const { return i; }
     KsDev ks;
     const uint64_t* ACC;
     uint64_t* result;
@@ -610,6 +739,7 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
                             uint64_t* scratch, cudaStream_t st, int* launches) {
     const size_t smem = ntt_smem_bytes<C>();
     const uint64_t D = ks.D, R = ks.R;
+    const uint32_t B = (uint32_t)items;
     const bool fused = use_fused(ks);
     uint64_t* U = scratch;
     uint64_t* V = U + items * D * C::N;
@@ -624,6 +754,7 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     int nl = 0;
     // FP64 stages: tail rows dealt out by warp where the shape allows it (ntt_core.cuh, NttCfg::WARPTAIL)
     using CW = typename KsWarpTailCfg<C>::type;
+    const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();    // FP64 kernels: room for the head-pass twiddles
     // V as raw doubles + the multiply-accumulate on the FP64 pipe (not in the rounds of ks_sub_items, whose
     // multiply-accumulate is the integer one)
     const bool mac_fp64 = !fused && g_ks_mac_fp64 && ks.fast_ok && ks.fp64_ok && ks.fp64_alt_ok && ks.keys_fp &&
@@ -631,17 +762,17 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     if (fused) {
         // S1, then S2 + S3 + S4 in one kernel (the sums in tensor memory), then S5
         if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
-        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<CW>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
         if ((e = launch_ks_fused(ks, ks.keys_fused, t_target, U, ACC, items, st))) return e;
-        if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smemw, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
         if (launches) *launches = 4;
         return cudaSuccess;
     }
     if (ks.fast_ok && ks.fp64_ok) {
         // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, 1.25q)
         if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
-        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smem, m_t, m_t, JobIntt1<CW>{ks, U}, items * D, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
         nl += 2;
         if (g_ks_sub_items > 0 && ks.keys_sh && (uint64_t)g_ks_sub_items < items) {
@@ -650,24 +781,24 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
                 const uint64_t cnt = items - off < (uint64_t)g_ks_sub_items ? items - off : (uint64_t)g_ks_sub_items;
                 JobNtt1<CW> job{ks, V};
                 job.item0 = (uint32_t)(off * D * D);
-                if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, job, cnt * D * D, list, st))) return e;
+                if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smemw, m_u, m_vs, job, cnt * D * D, list, st))) return e;
                 dim3 gf(C::N / 512, ks.R, (unsigned)((cnt + 3) / 4));
                 k_ks_mac_fast<4><<<gf, 256, 0, st>>>(ks, t_target + off * D * C::N, V + off * D * D * C::N,
                                                      ACC + off * 2 * R * C::N, (uint32_t)cnt);
                 if ((e = cudaGetLastError())) return e;
                 nl += 2;
             }
-            if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
-            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smemw, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smemw, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
             if (launches) *launches = nl + 2;
             return cudaSuccess;
         }
         if (mac_fp64) {
-            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;
         } else if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
-            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 2>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 2>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;
         } else {
-            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smem, m_u, m_vs, JobNtt1<CW>{ks, V}, items * D * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, true>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;
         }
         nl += 1;
     } else if (ks.fast_ok) {
@@ -709,11 +840,21 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
         k_ks_mac<<<g, 256, 0, st>>>(ks, t_target, V, ACC);
     if ((e = cudaGetLastError())) return e;
     if (ks.fast_ok && ks.fp64_ok) {
-        if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
+        if ((e = run_persistent(k_ks_intt2<CW, kFastTrust, true>, C::NT, smemw, m_acc, m_acc, JobIntt2<CW>{ks, ACC}, items * 2, list, st))) return e;
+        if constexpr (!std::is_same<CW, C>::value) {
+            if (g_ks_s5_fp64 && ks.fp64_alt_ok && ks.s2_no_reduce && ks.msf_fp) {
+                JobNtt2Fp<CW> job{ks, ACC, result, {}, 2 * B};
+                if ((e = make_poly_tmap(&job.rmap, result, items * 2 * D, C::LOGN, 32))) return e;
+                if ((e = run_persistent(k_ks_ntt2f<CW>, C::NT, smemw, m_acc, m_acc, job, items * 2 * D, list, st))) return e;
+                nl += 3;
+                if (launches) *launches = nl;
+                return cudaSuccess;
+            }
+        }
         if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
-            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, 2>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, 2>, C::NT, smemw, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
         } else {
-            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smem, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_ntt2<CW, kFastTrust, true>, C::NT, smemw, m_acc, m_acc, JobNtt2<CW>{ks, ACC, result}, items * 2 * D, list, st))) return e;
         }
     } else if (ks.fast_ok) {
         if ((e = run_persistent(k_ks_intt2<C, kFastTrust>, C::NT, smem, m_acc, m_acc, JobIntt2<C>{ks, ACC}, items * 2, list, st))) return e;

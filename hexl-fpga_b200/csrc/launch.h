@@ -30,6 +30,7 @@ struct KsDev {
     // same index space as keys_sh: {centred key mod q_i, its quotient by q_i} as doubles, for the multiply-
     // accumulate on the FP64 pipe (k_ks_mac_fp64); null unless fp64_alt_ok
     const TwPair* keys_fp;
+    const double* msf_fp;   // [2K]: centred msf_i and its quotient by q_i (FP64 epilogue of stage S5), or null
 };
 
 bool ntt_shape_supported(uint32_t logn);
@@ -119,6 +120,7 @@ size_t ks_scratch_words_per_item(const KsDev& ks);
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);
 cudaError_t launch_ks_prepare_keys_fp64(const KsDev& ks, TwPair* out, cudaStream_t st);
 extern int g_ks_mac_fp64;
+extern int g_ks_s5_fp64;
 cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
                             uint64_t* scratch, cudaStream_t st, int* launches);
 

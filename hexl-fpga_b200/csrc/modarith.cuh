@@ -419,26 +419,14 @@ HB_HD double fp_cred_full(double x, const Fp64Mod& m) {
 }
 // integer-valued double with |v| < q (and |v| <= 2^51)  ->  canonical residue in [0, q) as an integer:
 // v + (v < 0 ? q : 0).  The bit pattern of v + 1.5 * 2^52 is that of the constant plus v as a two's-complement
-// integer, so the sign of v is one comparison of the high word, and the high word's offset and the conditional
-// + q are folded into one predicated 64-bit add: one DADD + 4 ALU instructions.
+// integer, so the sign of v is one comparison of the high word, and the constant's offset and the conditional
+// + q are folded into one selected 64-bit addend: one DADD + 5 ALU instructions.
 HB_HD uint64_t fp_canon_signed(double v, const Fp64Mod& m) {
-#if defined(__CUDA_ARCH__)
-    const double t = __dadd_rn(v, u2d(kFpMagicBits));
-    uint64_t out;
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
-        "mov.b64 {lo, hi}, %1;\n\t"
-        "setp.lt.u32 p, hi, 0x43380000;\n\t"
-        "add.u32 hi, hi, 0xBCC80000;\n\t"
-        "@p add.cc.u32 lo, lo, %2;\n\t"
-        "@p addc.u32 hi, hi, %3;\n\t"
-        "mov.b64 %0, {lo, hi};\n\t}"
-        : "=l"(out)
-        : "d"(t), "r"((uint32_t)m.qi), "r"((uint32_t)(m.qi >> 32)));
-    return out;
-#else
-    const int64_t s = (int64_t)(d2u(fp_add(v, u2d(kFpMagicBits))) - kFpMagicBits);
-    return (uint64_t)(s + ((s >> 63) & (int64_t)m.qi));
-#endif
+    // 64-bit values throughout (no packing of 32-bit halves: the results feed 16-byte stores and must be free
+    // to sit in adjacent registers)
+    const uint64_t b = d2u(fp_add(v, u2d(kFpMagicBits)));
+    const bool neg = (uint32_t)(b >> 32) < (uint32_t)(kFpMagicBits >> 32);
+    return b + (neg ? m.qi - kFpMagicBits : (uint64_t)0 - kFpMagicBits);
 }
 // |v| < 2^52  ->  canonical residue in [0, q) as an integer (full reduction first)
 HB_HD uint64_t fp_to_canonical_full(double v, const Fp64Mod& m) { return fp_canon_signed(fp_cred_full(v, m), m); }

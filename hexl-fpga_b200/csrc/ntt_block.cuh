@@ -38,12 +38,14 @@ struct ModTab {
 // ---- load transforms (applied to each word as it enters the transform) ----
 struct XfIdent {
     static constexpr bool kPost = false;
+    static constexpr bool kFp64Out = false;   // the words come out as integers (XfKsConvertFp: as doubles)
     HB_D uint64_t operator()(uint64_t x) const { return x; }
 };
 // base conversion of a coefficient-form word to this modulus
 // (device/keyswitch/intt1_redu.hpp:36-38)
 struct XfReduce {
     static constexpr bool kPost = false;
+    static constexpr bool kFp64Out = false;   // the words come out as integers (XfKsConvertFp: as doubles)
     uint64_t q, mu;
     uint32_t skip;   // the words are already inside the transform's input contract (see KsDev::s2_no_reduce)
     HB_D uint64_t operator()(uint64_t x) const { return skip ? x : barrett_reduce64(x, q, mu); }
@@ -54,6 +56,7 @@ struct XfReduce {
 // case) "v mod qi" is one conditional subtraction instead of a Barrett product.
 struct XfKsConvert {
     static constexpr bool kPost = false;
+    static constexpr bool kFp64Out = false;   // the words come out as integers (XfKsConvertFp: as doubles)
     uint64_t q, mu, fix;
     uint32_t small;   // qk < 2*q
     HB_D uint64_t operator()(uint64_t v) const {
@@ -61,6 +64,17 @@ struct XfKsConvert {
         r += fix;
         return r - ((r >= q) ? q : 0);
     }
+};
+
+// The same conversion for the FP64-pipe forward kernels when qk <= 1.25 q (same-size primes) and
+// q <= 2^51 (1 + 1/32): the transform only needs SOME representative of (v + fix) mod q with magnitude below
+// 2^52, so the word is converted and the centred fix added -- |x| <= qk + q/2 <= 1.75 q -- and the two
+// conditional subtractions, the integer add and the separate entry conversion fall away (kFp64Out).
+struct XfKsConvertFp {
+    static constexpr bool kPost = false;
+    static constexpr bool kFp64Out = true;
+    double fix_c;    // centred representative of fix mod q
+    HB_D uint64_t operator()(uint64_t v) const { return d2u(fp_add(fp_from_int(v), fix_c)); }
 };
 
 // Fused polynomial multiply: the polynomial in shared memory is NTT(a); as the
@@ -72,6 +86,7 @@ struct XfKsConvert {
 // canonical, inside the inverse transform's contract.
 struct XfMulGlobal {
     static constexpr bool kPost = true;
+    static constexpr bool kFp64Out = false;   // the words come out as integers (XfKsConvertFp: as doubles)
     const uint64_t* other;   // NTT(b) of this item, same (bit-reversed) order
     const uint64_t* next;    // NTT(b) of the item this CTA transforms next (L2 prefetch), or nullptr
     Divisor dv;
@@ -102,12 +117,14 @@ struct SmemPlan {
     static constexpr uint32_t KQ_WORD = BAR_WORD + 2;     // two tables of k*q, k < 64 (iteration parity)
     static constexpr uint32_t CNT_WORD = BAR_WORD + 2 + 128;   // warps done with the buffer (C::WARPTAIL)
     static constexpr uint32_t TMEM_WORD = CNT_WORD + 1;        // tensor-memory base address (kernels that allocate TMEM)
-    static constexpr size_t BYTES = (size_t)(BAR_WORD + 2 + 128 + 1) * 8;
+    static constexpr uint32_t WBAR_WORD = CNT_WORD + 2;        // one mbarrier per warp (epilogues that TMA-load into the warp's slice)
+    static constexpr uint32_t END_WORD = WBAR_WORD + C::NT / 32;
+    static constexpr size_t BYTES = (size_t)END_WORD * 8;
     // head-pass twiddles of the FP64 plain kernels (Fp64ArithS), 16-byte entries behind everything else
     static constexpr uint32_t HEAD_TW_FWD = C::fwd_off(C::NP), HEAD_TW_INV = C::INV_ENTRIES - C::N;
     static constexpr uint32_t HEAD_TW = HEAD_TW_FWD > HEAD_TW_INV ? HEAD_TW_FWD : HEAD_TW_INV;
-    static constexpr uint32_t TW_WORD = (BAR_WORD + 2 + 128 + 1 + 1) & ~1u;
-    static_assert(TW_WORD > TMEM_WORD, "shared-memory plan: the twiddle area overlaps the control words");
+    static constexpr uint32_t TW_WORD = (END_WORD + 1) & ~1u;
+    static_assert(TW_WORD >= END_WORD, "shared-memory plan: the twiddle area overlaps the control words");
     static constexpr size_t BYTES_TW = (size_t)TW_WORD * 8 + (size_t)HEAD_TW * 16;
     static constexpr bool kHeadTwFits = BYTES_TW <= 227u * 1024u;
 };
@@ -520,51 +537,53 @@ HB_D void tmem_touch16(uint32_t* r) {
 }
 
 // fwd_tail_compute (ntt_core.cuh) with the twiddles read from tensor memory, four packed slots per load, each
-// load issued one butterfly stage ahead of its use (two 16-register buffers in turns)
+// load issued one butterfly stage ahead of its use.  Every load has its own destination registers (the arrays
+// are fully scalarised; at most two or three are alive at a time): re-using two buffers in turns made the
+// compiler copy twiddles out of the way of the next load, ~100 moves per transform.
 template <class C, class A, class F>
 HB_D void fwd_tail_compute_tmem(uint64_t* v, const A& a, const F& after_row) {
     constexpr int ROWS = (int)TmemTail<C>::ROWS, S0 = C::HEAD;
-    uint32_t ra[16], rb[16];
-    tmem_ld16_issue(a.ttail, ra);         // row 0, slots 0..3
-    tmem_ld16_issue(a.ttail + 16, rb);    //        slots 4..7
+    uint32_t r[ROWS][4][16];              // [row][slots 4g .. 4g+3]
+    tmem_ld16_issue(a.ttail, r[0][0]);
+    tmem_ld16_issue(a.ttail + 16, r[0][1]);
     static_for<0, ROWS>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         uint64_t* x = v + ri * 16;
         const uint32_t ta = a.ttail + (uint32_t)ri * 64u;
-        tmem_ld_wait16(ra);
-        tmem_touch16(rb);
+        tmem_ld_wait16(r[ri][0]);
+        tmem_touch16(r[ri][1]);
         {   // stage 0: slot 1, pairs (j, j + 8)
-            const TwPair t = tmem_pair(ra, 1);
+            const TwPair t = tmem_pair(r[ri][0], 1);
             static_for<0, 8>([&](auto jc) { a.template fwd_at<S0>(x[decltype(jc)::value], x[decltype(jc)::value + 8], t); });
         }
         static_for<0, 2>([&](auto bc) {   // stage 1: slots 2, 3
             constexpr int blk = decltype(bc)::value;
-            const TwPair t = tmem_pair(ra, 2 + blk);
+            const TwPair t = tmem_pair(r[ri][0], 2 + blk);
             static_for<0, 4>([&](auto jc) {
                 a.template fwd_at<S0 + 1>(x[blk * 8 + decltype(jc)::value], x[blk * 8 + decltype(jc)::value + 4], t);
             });
         });
-        tmem_ld16_issue(ta + 32, ra);     // slots 8..11
+        tmem_ld16_issue(ta + 32, r[ri][2]);     // slots 8..11
         static_for<0, 4>([&](auto bc) {   // stage 2: slots 4..7
             constexpr int blk = decltype(bc)::value;
-            const TwPair t = tmem_pair(rb, blk);
+            const TwPair t = tmem_pair(r[ri][1], blk);
             static_for<0, 2>([&](auto jc) {
                 a.template fwd_at<S0 + 2>(x[blk * 4 + decltype(jc)::value], x[blk * 4 + decltype(jc)::value + 2], t);
             });
         });
-        tmem_ld_wait16(ra);
-        tmem_ld16_issue(ta + 48, rb);     // slots 12..15
+        tmem_ld_wait16(r[ri][2]);
+        tmem_ld16_issue(ta + 48, r[ri][3]);     // slots 12..15
         static_for<0, 4>([&](auto bc) {   // stage 3, first half: slots 8..11
             constexpr int blk = decltype(bc)::value;
-            a.template fwd_at<S0 + 3>(x[blk * 2], x[blk * 2 + 1], tmem_pair(ra, blk));
+            a.template fwd_at<S0 + 3>(x[blk * 2], x[blk * 2 + 1], tmem_pair(r[ri][2], blk));
         });
-        tmem_ld_wait16(rb);
-        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64, ra);        // next row, slots 0..3
+        tmem_ld_wait16(r[ri][3]);
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64, r[ri + 1 < ROWS ? ri + 1 : ri][0]);        // next row, slots 0..3
         static_for<0, 4>([&](auto bc) {   // stage 3, second half: slots 12..15
             constexpr int blk = decltype(bc)::value;
-            a.template fwd_at<S0 + 3>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(rb, blk));
+            a.template fwd_at<S0 + 3>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(r[ri][3], blk));
         });
-        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 16, rb);   // next row, slots 4..7
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 16, r[ri + 1 < ROWS ? ri + 1 : ri][1]);   // next row, slots 4..7
         static_for<0, C::ROW>([&](auto kc) { x[decltype(kc)::value] = a.fwd_final(x[decltype(kc)::value]); });
         after_row(ri);
     });
@@ -574,47 +593,47 @@ HB_D void fwd_tail_compute_tmem(uint64_t* v, const A& a, const F& after_row) {
 template <class C, class A>
 HB_D void inv_tail_compute_tmem(uint64_t* v, const A& a) {
     constexpr int ROWS = (int)TmemTail<C>::ROWS;
-    uint32_t ra[16], rb[16];
-    tmem_ld16_issue(a.ttail + 32, ra);    // row 0, slots 8..11
-    tmem_ld16_issue(a.ttail + 48, rb);    //        slots 12..15
+    uint32_t r[ROWS][4][16];              // [row][slots 4g .. 4g+3]
+    tmem_ld16_issue(a.ttail + 32, r[0][2]);
+    tmem_ld16_issue(a.ttail + 48, r[0][3]);
     static_for<0, ROWS>([&](auto rc) {
         constexpr int ri = decltype(rc)::value;
         uint64_t* x = v + ri * 16;
         const uint32_t ta = a.ttail + (uint32_t)ri * 64u;
-        tmem_ld_wait16(ra);
-        tmem_touch16(rb);
+        tmem_ld_wait16(r[ri][2]);
+        tmem_touch16(r[ri][3]);
         static_for<0, 4>([&](auto bc) {   // stage 0, first half: slots 8..11
             constexpr int blk = decltype(bc)::value;
-            a.template inv_at<0>(x[blk * 2], x[blk * 2 + 1], tmem_pair(ra, blk));
+            a.template inv_at<0>(x[blk * 2], x[blk * 2 + 1], tmem_pair(r[ri][2], blk));
         });
-        tmem_ld16_issue(ta + 16, ra);     // slots 4..7
+        tmem_ld16_issue(ta + 16, r[ri][1]);     // slots 4..7
         static_for<0, 4>([&](auto bc) {   // stage 0, second half: slots 12..15
             constexpr int blk = decltype(bc)::value;
-            a.template inv_at<0>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(rb, blk));
+            a.template inv_at<0>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(r[ri][3], blk));
         });
-        tmem_ld_wait16(ra);
-        tmem_ld16_issue(ta, rb);          // slots 0..3
+        tmem_ld_wait16(r[ri][1]);
+        tmem_ld16_issue(ta, r[ri][0]);          // slots 0..3
         static_for<0, 4>([&](auto bc) {   // stage 1: slots 4..7
             constexpr int blk = decltype(bc)::value;
-            const TwPair t = tmem_pair(ra, blk);
+            const TwPair t = tmem_pair(r[ri][1], blk);
             static_for<0, 2>([&](auto jc) {
                 a.template inv_at<1>(x[blk * 4 + decltype(jc)::value], x[blk * 4 + decltype(jc)::value + 2], t);
             });
         });
-        tmem_ld_wait16(rb);
-        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 32, ra);   // next row, slots 8..11
+        tmem_ld_wait16(r[ri][0]);
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 32, r[ri + 1 < ROWS ? ri + 1 : ri][2]);   // next row, slots 8..11
         static_for<0, 2>([&](auto bc) {   // stage 2: slots 2, 3
             constexpr int blk = decltype(bc)::value;
-            const TwPair t = tmem_pair(rb, 2 + blk);
+            const TwPair t = tmem_pair(r[ri][0], 2 + blk);
             static_for<0, 4>([&](auto jc) {
                 a.template inv_at<2>(x[blk * 8 + decltype(jc)::value], x[blk * 8 + decltype(jc)::value + 4], t);
             });
         });
         {   // stage 3: slot 1
-            const TwPair t = tmem_pair(rb, 1);
+            const TwPair t = tmem_pair(r[ri][0], 1);
             static_for<0, 8>([&](auto jc) { a.template inv_at<3>(x[decltype(jc)::value], x[decltype(jc)::value + 8], t); });
         }
-        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 48, rb);   // next row, slots 12..15
+        if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 48, r[ri + 1 < ROWS ? ri + 1 : ri][3]);   // next row, slots 12..15
     });
 }
 
@@ -636,7 +655,7 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     const TwPair* ftw = A::kFp64 ? t.ftwd : t.ftw;
     const TwPair* ftw_head = ftw;            // twiddles of the head passes
     if constexpr (A::kSmemHead) ftw_head = a.fwd_base();
-    if constexpr (A::kFp64) {
+    if constexpr (A::kFp64 && !Xf::kFp64Out) {
 #pragma unroll
         for (int e = 0; e < C::E; ++e) v[e] = a.enter_fwd(v[e]);
     }
@@ -768,26 +787,21 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     if constexpr (MODE == kExactList) n_items = list[0];
     auto item_of = [&](uint32_t i) -> uint32_t {
         if constexpr (MODE == kExactList) return list[1 + i];
-        return i;
+        else return job.order(i);      // the order in which the grid walks over the items (identity, or modulus-major)
     };
     if (tid == 0) {
         if (smem_u32(W) & 1023u) __trap();
         mbar_init(bar, 1);
         W[SmemPlan<C>::FLAG_WORD] = 0;
         W[SmemPlan<C>::CNT_WORD] = 0;
+        for (uint32_t w = 0; w < C::NT / 32; ++w) mbar_init(W + SmemPlan<C>::WBAR_WORD + w, 1);
         fence_barrier_init();
     }
-    // FP64 kernels of the plain batched calls (one modulus per launch, launched with BYTES_TW of
-    // shared memory): the twiddles of the head passes move next to the buffer once
-    constexpr bool SMEM_HEAD = FP64 != 0 && Job::kOneModulus && SmemPlan<C>::kHeadTwFits;
-    if constexpr (SMEM_HEAD) {
-        const ModTab& t0 = job.mod(0);
-        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(FWD ? t0.ftwd : t0.itwd + C::inv_off(0));
-        ulonglong2* dst = reinterpret_cast<ulonglong2*>(W + SmemPlan<C>::TW_WORD);
-        constexpr uint32_t COUNT = FWD ? SmemPlan<C>::HEAD_TW_FWD : SmemPlan<C>::HEAD_TW_INV;
-        for (uint32_t e = tid; e < COUNT; e += C::NT) dst[e] = src[e];
-    }
-    // ... and the twiddles of the tail pass into tensor memory (one CTA per SM at this shape: the whole TMEM)
+    // FP64 kernels whose CTAs keep a modulus for long runs of items (the plain batched calls: one modulus per
+    // launch; the keyswitch stages: items dealt out modulus-major, Job::order), launched with BYTES_TW of shared
+    // memory: the twiddles of the head passes sit next to the buffer, those of the tail pass in tensor memory
+    // (one CTA per SM at this shape: the whole TMEM), both (re)loaded when the modulus changes
+    constexpr bool SMEM_HEAD = FP64 != 0 && (Job::kOneModulus || Job::kModulusRuns) && SmemPlan<C>::kHeadTwFits;
     constexpr bool TMEM_TAIL = SMEM_HEAD && HB_TMEM_TAIL != 0 && C::LOGN == 14 && TmemTail<C>::kFits;
     if constexpr (TMEM_TAIL) {
         if (tid < 32) tmem_alloc_all(reinterpret_cast<uint32_t*>(W + SmemPlan<C>::TMEM_WORD));
@@ -799,8 +813,22 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tmem_base = *reinterpret_cast<volatile uint32_t*>(W + SmemPlan<C>::TMEM_WORD);
         ttail = tmem_tail_addr<C>(tmem_base);
-        const ModTab& t0 = job.mod(0);
-        tail_tw_to_tmem<C>(tid, FWD ? t0.ftwd + C::fwd_off(C::NP) : t0.itwd, ttail);
+    }
+    auto load_twiddles = [&](const ModTab& tm) {
+        if constexpr (SMEM_HEAD) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(FWD ? tm.ftwd : tm.itwd + C::inv_off(0));
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(W + SmemPlan<C>::TW_WORD);
+            constexpr uint32_t COUNT = FWD ? SmemPlan<C>::HEAD_TW_FWD : SmemPlan<C>::HEAD_TW_INV;
+            for (uint32_t e = tid; e < COUNT; e += C::NT) dst[e] = src[e];
+        }
+        if constexpr (TMEM_TAIL) tail_tw_to_tmem<C>(tid, FWD ? tm.ftwd + C::fwd_off(C::NP) : tm.itwd, ttail);
+    };
+    const TwPair* cur_tw = nullptr;      // whose twiddles are resident
+    if constexpr (SMEM_HEAD) {
+        const ModTab& t0 = job.mod(blockIdx.x < n_items ? item_of(blockIdx.x) : 0);
+        load_twiddles(t0);
+        cur_tw = FWD ? t0.ftwd : t0.itwd;
+        __syncthreads();
     }
     uint32_t head_s = 0;
     if constexpr (SMEM_HEAD) {
@@ -817,11 +845,25 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         pf.map = tmap;
         pf.row = ((C::WARPTAIL ? (tid & 31u) == 0 : tid == 0) && next < n_items) ? job.src_row(item_of(next))
                                                                                           : kNoPrefetch;
+        const ModTab& t = job.mod(item);
+        if constexpr (SMEM_HEAD && Job::kModulusRuns) {
+            if ((FWD ? t.ftwd : t.itwd) != cur_tw) {     // uniform: the next run of items, under another modulus
+                __syncthreads();                          // slower warps may still be reading the old head twiddles
+                load_twiddles(t);
+                cur_tw = FWD ? t.ftwd : t.itwd;
+                __syncthreads();
+            }
+        }
         mbar_wait(bar, parity);
         parity ^= 1;
-        const ModTab& t = job.mod(item);
         bool done;
-        if constexpr (TMEM_TAIL && FWD && FP64 == 2) {
+        if constexpr (TMEM_TAIL && FWD && FP64 == 3) {
+            Fp64ArithRawST a;
+            a.m = t.fd;
+            a.head_s = head_s;
+            a.ttail = ttail;
+            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (TMEM_TAIL && FWD && FP64 == 2) {
             Fp64AltArithST a;
             a.m = t.fd;
             a.head_s = head_s;

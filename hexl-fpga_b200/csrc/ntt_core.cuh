@@ -347,6 +347,9 @@ struct Fp64AltArithST : Fp64AltArithS {
     static constexpr bool kTmemTail = true;
     uint32_t ttail;
 };
+struct Fp64ArithRawST : Fp64AltArithST {     // raw doubles out (cf. Fp64ArithRaw)
+    HB_HD uint64_t fwd_final(uint64_t x) const { return x; }
+};
 
 // inverse transform for q < 2^52 without per-stage corrections (modarith.cuh);
 // E = log2 of the bound (in units of q) of the words entering the stage
@@ -630,6 +633,17 @@ struct HeadGeom {
     }
 };
 
+// Swizzled position of word k of a head-pass group with base index b and stride 2^LS.  The swizzle only looks
+// at the row bits just above the 128-byte row (bits 4..6 of a uint64 index, 5..7 of a uint32 one): a stride that
+// is a multiple of eight rows leaves them alone, so the group's words sit at swz(b) + k * 2^LS -- one address
+// register and immediate offsets instead of an XOR and a shift per word (the compiler does not see through
+// the XOR / add mix by itself and kept 32 live address registers through the first forward pass).
+template <class S, int LS>
+HB_HD uint32_t head_pos(uint32_t b, uint32_t k) {
+    if constexpr (LS >= (sizeof(S) == 8 ? 7 : 8)) return swz_t<S>(b) + (k << LS);
+    else return swz_t<S>(b + (k << LS));
+}
+
 // load all E words of a head pass from a (swizzled) shared buffer of S-typed
 // words into T-typed registers through xf
 template <class C, int R, int LS, class S, class T, class Xf>
@@ -640,7 +654,7 @@ HB_HD void head_load(uint32_t tid, const S* sm, T* v, const Xf& xf) {
         const uint32_t b = Gm::base(tid + gi * C::NT);
         static_for<0, (1 << R)>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            v[gi * (1 << R) + k] = xf(sm[swz_t<S>(b + ((uint32_t)k << LS))]);
+            v[gi * (1 << R) + k] = xf(sm[head_pos<S, LS>(b, (uint32_t)k)]);
         });
     });
 }
@@ -652,7 +666,7 @@ HB_HD void head_store(uint32_t tid, T* sm, const T* v) {
         const uint32_t b = Gm::base(tid + gi * C::NT);
         static_for<0, (1 << R)>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            sm[swz_t<T>(b + ((uint32_t)k << LS))] = v[gi * (1 << R) + k];
+            sm[head_pos<T, LS>(b, (uint32_t)k)] = v[gi * (1 << R) + k];
         });
     });
 }
@@ -661,7 +675,7 @@ HB_HD void head_store(uint32_t tid, T* sm, const T* v) {
 template <class C, int R, int LS, class T>
 HB_HD void head_store_word(uint32_t tid, T* sm, int gi, int k, T x) {
     using Gm = HeadGeom<C, R, LS>;
-    sm[swz_t<T>(Gm::base(tid + (uint32_t)gi * C::NT) + ((uint32_t)k << LS))] = x;
+    sm[head_pos<T, LS>(Gm::base(tid + (uint32_t)gi * C::NT), (uint32_t)k)] = x;
 }
 
 // tail rows: thread tid owns rows tid + ri*NT of ROW contiguous words (128 bytes); with

@@ -15,6 +15,8 @@ cudaError_t make_rows32_store_tmap(CUtensorMap* out, const void* base, uint64_t 
 template <class C>
 struct JobPlain {
     static constexpr bool kOneModulus = true;   // every item of a launch is transformed under tab
+    static constexpr bool kModulusRuns = false;
+    HB_D uint32_t order(uint32_t i) const { return i; }
     uint64_t* data;
     ModTab tab;
     // item i is polynomial offset + i * stride of the array (1, 0: a plain batch; 2, h: the half-size

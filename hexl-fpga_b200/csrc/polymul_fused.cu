@@ -75,8 +75,8 @@ struct OfParkMul {
 
 template <class C>
 struct PolymulPlan {
-    static constexpr uint32_t TMEM_WORD = SmemPlan<C>::CNT_WORD + 1;
-    static constexpr size_t BYTES = (size_t)(TMEM_WORD + 1) * 8;
+    static constexpr uint32_t TMEM_WORD = SmemPlan<C>::TMEM_WORD;
+    static constexpr size_t BYTES = SmemPlan<C>::BYTES;
     static_assert(BYTES <= 227u * 1024u, "shared-memory plan does not fit");
 };
 

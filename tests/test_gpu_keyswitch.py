@@ -84,29 +84,36 @@ def test_fused_kernel_and_l2_rounds(hb, n, D, K, batch, opt, val):
     assert np.array_equal(got, p.expected())
 
 
+@pytest.mark.parametrize("option", ["ks_mac_fp64", "ks_s5_fp64"])
 @pytest.mark.parametrize("n,D,K,batch", [(16384, 7, 8, 5), (16384, 6, 7, 3), (16384, 2, 8, 4), (16384, 1, 2, 3)])
-def test_integer_multiply_accumulate_matches_the_fp64_one(hb, n, D, K, batch):
+def test_integer_stages_match_the_fp64_ones(hb, n, D, K, batch, option):
     """ks_mac_fp64 = 1 (default at N = 16384 with moduli up to 2^51 (1 + 1/32)): stage S2 leaves raw doubles in V
     and stage S3 multiplies on the FP64 pipe; 0: canonical words and the integer Shoup products.  Same bits,
     also with target words the FP64 product does not take as they are (>= 2^52: reduced first) -- the digit
-    under its own modulus reaches the multiply-accumulate straight from the caller's buffer."""
+    under its own modulus reaches the multiply-accumulate straight from the caller's buffer.
+    ks_s5_fp64 = 1 (default under the same conditions): stage S5's base conversion and modswitch / accumulate
+    epilogue on the FP64 pipe, `result` through TMA; 0: the integer epilogue.  Same bits, also for `result` words
+    outside [0, q) (the reference's wrap-around add_mod decides those)."""
     p = KsProblem(n, D, K, batch, 51, seed=77)
     t = p.t_target.reshape(batch, D, n).copy()
     t[0, 0, 3] = np.uint64((1 << 63) + 12345)          # garbage: every kernel family must agree on it
     t[batch - 1, D - 1, n - 1] = np.uint64((1 << 52) + 1)
+    r_in = p.result.reshape(batch, 2, D, n).copy()
+    r_in[0, 1, D - 1, 7] = np.uint64((1 << 64) - 5)
+    r_in[batch - 1, 0, 0, n - 2] = np.uint64(int(p.moduli[0]) + 3)
     plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
     out = []
     for opt in (1, 0):
-        hb.set_option("ks_mac_fp64", opt)
+        hb.set_option(option, opt)
         try:
             res = gpu(p.result)
             plan.keyswitch(res, gpu(p.t_target), batch)
             clean = res.cpu().numpy().view(np.uint64).copy()
-            res = gpu(p.result)
+            res = gpu(r_in.reshape(batch, -1))
             plan.keyswitch(res, gpu(t.reshape(batch, -1)), batch)
             out.append((clean, res.cpu().numpy().view(np.uint64).copy()))
         finally:
-            hb.set_option("ks_mac_fp64", 1)
+            hb.set_option(option, 1)
     plan.close()
     assert np.array_equal(out[0][0], p.expected())
     assert np.array_equal(out[1][0], p.expected())

@@ -59,6 +59,9 @@ elif op == "keyswitch_fused":
     for _ in range(2):
         plan.keyswitch(res, tt, B)
 elif op == "keyswitch":
+    for kv in os.environ.get("KS_OPTS", "").split(","):
+        if kv:
+            hb.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     n, D, K, B = 16384, 7, 8, batch if len(sys.argv) > 3 else 64
     p = KsProblem(n, D, K, 1, 51)
     plan = hb.KsPlan(n, D, K, D + 1, 2, p.moduli, p.keys, p.msf)
