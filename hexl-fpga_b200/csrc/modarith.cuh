@@ -472,10 +472,19 @@ HB_HD void fwd_bfly_fp64_b(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, co
 HB_HD bool fp64_alt_modulus_ok(uint64_t q) {
     return fp64_modulus_ok(q) && q <= (((uint64_t)1 << 51) + ((uint64_t)1 << 46));
 }
+// HB_INV_CRED_FULL: correct the sum with x - q rint(x / q) (3 FP64 = 6 scheduler cycles) instead of the conditional
+// +-q (1 FP64 + 5 ALU = 7): the inverse kernels are issue-bound with both pipes half idle
+#ifndef HB_INV_CRED_FULL
+#define HB_INV_CRED_FULL 1
+#endif
 HB_HD void inv_bfly_fp64(uint64_t& X, uint64_t& Y, uint64_t w, uint64_t wi, const Fp64Mod& m) {
     const double x = u2d(X), y = u2d(Y);
     const double s = fp_add(x, y), u = fp_add(x, -y);
+#if HB_INV_CRED_FULL
+    X = d2u(fp_cred_full(s, m));
+#else
     X = d2u(fp_cred(s, m));
+#endif
     Y = d2u(fp_mulmod(u, u2d(w), u2d(wi), m));
 }
 // First inverse stage: the words come straight from fp_from_int, x, y in [0, 1.25 q) (the contract of the
