@@ -120,7 +120,7 @@ static int ntt_big(bool fwd, uint64_t* d_operand, const uint64_t* d_tab, const u
     const int variant = 1;
     if (lazy_out) return fail(HEXL_B200_EINVAL, "n = 32768: output_mod_factor must be 1");
     const size_t raw_bytes = (size_t)4 * nh * 8, half_bytes = (size_t)2 << 20;
-    const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
+    const size_t list_bytes = ((batch + 2) * 4 + 255) & ~(size_t)255;
     uint8_t* scratch = nullptr;
     cudaError_t e = g_scratch.get(st, raw_bytes + 2 * half_bytes + 2 * list_bytes, (void**)&scratch);
     if (e != cudaSuccess) return cuda_fail(e, "ntt (n = 32768): scratch");
@@ -245,6 +245,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         hb::g_pdl = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "debug_skip_list")) {
+        hb::g_debug_skip_list = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "warp_tail")) {
         hb::g_warp_tail = value ? 1 : 0;
         return 0;
@@ -352,7 +356,7 @@ int hexl_b200_ntt_fwd_ex(uint64_t* d_operand, const uint64_t* d_roots, const uin
     // inverse twiddles, [1M,1.5M) / [1.5M,2M) the same for the FP64 path, then
     // two deferred lists of 1 + batch words
     uint8_t* scratch = nullptr;
-    const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
+    const size_t list_bytes = ((batch + 2) * 4 + 255) & ~(size_t)255;
     cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(2u << 20) + 2 * list_bytes, (void**)&scratch);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_fwd: scratch");
     hb::TwPair* packed = reinterpret_cast<hb::TwPair*>(scratch);
@@ -415,7 +419,7 @@ int hexl_b200_ntt_inv_ex(uint64_t* d_operand, const uint64_t* d_inv_roots, const
                        (cudaStream_t)stream);
     const int variant = g_ntt_variant.load();
     uint8_t* scratch = nullptr;
-    const size_t list_bytes = ((batch + 1) * 4 + 255) & ~(size_t)255;
+    const size_t list_bytes = ((batch + 2) * 4 + 255) & ~(size_t)255;
     cudaError_t e = g_scratch.get((cudaStream_t)stream, (size_t)(2u << 20) + 2 * list_bytes, (void**)&scratch);
     if (e != cudaSuccess) return cuda_fail(e, "ntt_inv: scratch");
     // second halves, so a forward and an inverse call may be queued back to back
@@ -467,7 +471,7 @@ int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint6
     // per-stream scratch: packed forward / inverse twiddles, one deferred list, and NTT(b) of a chunk
     const uint64_t chunk_max = 2048;
     const uint64_t chunk = batch < chunk_max ? batch : chunk_max;
-    const size_t list_bytes = ((chunk + 1) * 4 + 255) & ~(size_t)255;
+    const size_t list_bytes = ((chunk + 2) * 4 + 255) & ~(size_t)255;
     // (same layout as the NTT entry points: [1M,2M) holds the FP64-pipe tables)
     const size_t tb_off = (size_t)(2u << 20) + list_bytes;
     uint8_t* scratch = nullptr;
@@ -499,7 +503,7 @@ int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint6
         if (fused) {
             // one launch: NTT(a) parked in tensor memory, NTT(b), product, INTT (polymul_fused.cu); items with
             // out-of-contract words go through the exact kernels behind it (deferred list, normally empty)
-            if (off && (e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
+            if (off && (e = cudaMemsetAsync(list, 0, 8, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
             e = hb::launch_polymul_fused(res, d_a + off * n, d_b + off * n, t, cnt, list, st);
             if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: fused kernel");
             e = hb::launch_polymul_deferred(res, tb, d_a + off * n, d_b + off * n, t, cnt, list, st);
@@ -508,10 +512,10 @@ int hexl_b200_poly_multiply(uint64_t* d_result, const uint64_t* d_a, const uint6
             continue;
         }
         // NTT(a) -> result, NTT(b) -> scratch; out-of-contract words take the exact kernel (deferred list)
-        if (off && (e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
+        if (off && (e = cudaMemsetAsync(list, 0, 8, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
         e = hb::launch_ntt_fwd(res, t, (uint32_t)logn, cnt, variant, list, st, &launches, d_a + off * n);
         if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: forward a");
-        if ((e = cudaMemsetAsync(list, 0, 4, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
+        if ((e = cudaMemsetAsync(list, 0, 8, st)) != cudaSuccess) return cuda_fail(e, "poly_multiply: list");
         e = hb::launch_ntt_fwd(tb, t, (uint32_t)logn, cnt, variant, list, st, &launches, d_b + off * n);
         if (e != cudaSuccess) return cuda_fail(e, "poly_multiply: forward b");
         e = hb::launch_ntt_inv_mul(res, tb, t, (uint32_t)logn, cnt, variant, st);

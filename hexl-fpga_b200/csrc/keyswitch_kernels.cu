@@ -761,7 +761,7 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
                           !std::is_same<CW, C>::value && !(g_ks_sub_items > 0 && (uint64_t)g_ks_sub_items < items);
     if (fused) {
         // S1, then S2 + S3 + S4 in one kernel (the sums in tensor memory), then S5
-        if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
+        if ((e = cudaMemsetAsync(list, 0, 8, st))) return e;
         if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
         if ((e = launch_ks_fused(ks, ks.keys_fused, t_target, U, ACC, items, st))) return e;
@@ -771,7 +771,7 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     }
     if (ks.fast_ok && ks.fp64_ok) {
         // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, 1.25q)
-        if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
+        if ((e = cudaMemsetAsync(list, 0, 8, st))) return e;
         if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
         nl += 2;
@@ -804,7 +804,7 @@ static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t
     } else if (ks.fast_ok) {
         // S1 sees caller data: vote + deferred exact pass; the later stages read
         // words this pipeline produced (reduced by their load transforms)
-        if ((e = cudaMemsetAsync(list, 0, 4, st))) return e;
+        if ((e = cudaMemsetAsync(list, 0, 8, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kFastVote>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
         if ((e = run_persistent(k_ks_ntt1<C, kFastTrust>, C::NT, smem, m_u, m_vs, JobNtt1<C>{ks, V}, items * D * D, list, st))) return e;

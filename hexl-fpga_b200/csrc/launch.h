@@ -116,6 +116,7 @@ extern int g_ks_mac_items;
 extern int g_small_tma_store;
 extern int g_warp_tail;
 extern int g_pdl;
+extern int g_debug_skip_list;   // measurement only (option "debug_skip_list"): out-of-contract items are NOT transformed
 size_t ks_scratch_words_per_item(const KsDev& ks);
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);
 cudaError_t launch_ks_prepare_keys_fp64(const KsDev& ks, TwPair* out, cudaStream_t st);

@@ -424,8 +424,17 @@ HB_HD double fp_cred_full(double x, const Fp64Mod& m) {
 HB_HD uint64_t fp_canon_signed(double v, const Fp64Mod& m) {
     // 64-bit values throughout (no packing of 32-bit halves: the results feed 16-byte stores and must be free
     // to sit in adjacent registers)
-    const uint64_t b = d2u(fp_add(v, u2d(kFpMagicBits)));
-    const bool neg = (uint32_t)(b >> 32) < (uint32_t)(kFpMagicBits >> 32);
+    const double t = fp_add(v, u2d(kFpMagicBits));
+    const uint64_t b = d2u(t);
+#if defined(__CUDA_ARCH__)
+    // the high word through an opaque move: the compiler otherwise widens the test to a 64-bit compare (two ISETP)
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "d"(t));
+    (void)lo;
+#else
+    const uint32_t hi = (uint32_t)(b >> 32);
+#endif
+    const bool neg = hi < (uint32_t)(kFpMagicBits >> 32);
     return b + (neg ? m.qi - kFpMagicBits : (uint64_t)0 - kFpMagicBits);
 }
 // |v| < 2^52  ->  canonical residue in [0, q) as an integer (full reduction first)

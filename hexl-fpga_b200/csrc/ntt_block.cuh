@@ -442,12 +442,13 @@ HB_D void fwd_mid_passes(uint32_t tid, uint64_t* W, const TwPair* tw, const A& a
 //   kExactList  reference op sequence for the items of the deferred list
 enum NttMode { kFastVote = 0, kFastTrust = 1, kExactAll = 2, kExactList = 3 };
 
-// deferred list: word 0 = count, words 1.. = item indices
+// deferred list: word 0 = count, word 1 = reserved (zero), words 2.. = item indices; word 0 is zero when a voting
+// kernel starts
+constexpr uint32_t kListHead = 2;
 HB_D void defer_item(uint32_t* list, uint32_t item) {
     const uint32_t slot = atomicAdd(list, 1u);
-    list[1 + slot] = item;
+    list[kListHead + slot] = item;
 }
-
 // Range vote on the freshly loaded words: nonzero when some word may be >=
 // bound.  For bounds above 2^32 only the high words are compared (one max per
 // word): conservative -- words in [hi32(bound)*2^32, bound) are flagged too and
@@ -637,8 +638,9 @@ HB_D void inv_tail_compute_tmem(uint64_t* v, const A& a) {
     });
 }
 
-// returns false when the polynomial was deferred (fast-vote mode only)
-template <class C, int MODE, class A, class Xf, class Of>
+// returns false when the polynomial was deferred (fast-vote mode only); PF_ON_FAIL = false: the buffer is then
+// left free (nothing prefetched into it) because the caller re-loads the same polynomial for the exact pass
+template <class C, int MODE, bool PF_ON_FAIL = true, class A, class Xf, class Of>
 HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, const Of& of, const Prefetch& pf) {
     using P0 = FwdPass<C, 0>;
     const uint32_t tid = threadIdx.x;
@@ -666,7 +668,7 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     __syncthreads();
     if constexpr (MODE == kFastVote) {
         if (vote_read<C>()) {          // global memory still holds the untouched input
-            pf.template issue<C>();
+            if constexpr (PF_ON_FAIL) pf.template issue<C>();
             return false;
         }
     }
@@ -698,7 +700,7 @@ HB_D void inv_mid_passes(uint32_t tid, uint64_t* W, const TwPair* tw, const A& a
     }
 }
 
-template <class C, int MODE, class A, class Xf, class Of>
+template <class C, int MODE, bool PF_ON_FAIL = true, class A, class Xf, class Of>
 HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, const Of& of, const Prefetch& pf) {
     using PL = InvPass<C, C::NP - 1>;
     const uint32_t tid = threadIdx.x;
@@ -730,7 +732,7 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         __syncthreads();
         if constexpr (MODE == kFastVote) {
             if (vote_read<C>()) {
-                pf.template issue<C>();
+                if constexpr (PF_ON_FAIL) pf.template issue<C>();
                 return false;
             }
         }
@@ -742,7 +744,7 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
         __syncthreads();
         if constexpr (MODE == kFastVote) {
             if (vote_read<C>()) {
-                pf.template issue<C>();
+                if constexpr (PF_ON_FAIL) pf.template issue<C>();
                 return false;
             }
         }
@@ -770,6 +772,26 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 // `list`: the deferred list (written in kFastVote, read in kExactList mode).
 // FP64: 0 integer butterflies, 1 FP64-pipe butterflies, 2 (forward only) FP64 with a full correction every other stage,
 //       3 (forward only) as 2 with the raw doubles as output (|v| <= 1.92 q, any representative of the residue)
+// Plain forward FP64 voting kernels (kFoldExact): a polynomial whose vote fails is transformed with the
+// reference op sequence by the same CTA at once (re-loaded, the first pass has overwritten the buffer), so
+// these kernels need neither the deferred list nor the separate pass over it.  That pass costs 6 - 8 us per
+// call (2 % of a 4096-polynomial call) although the list is empty in normal use, because the next call's
+// kernels queue behind it.  Measured per 4096-polynomial forward call: 346.1 us with the separate pass, 342.5
+// like this, 337.8 voting without any exact path (the extra code costs the main loop ~1.4 %), 332.5 without a
+// vote.  A first version kept the list and ran the pass at the end of the kernel behind a grid barrier: same
+// time, plus a residency assumption.  In the inverse kernels the extra code costs the main loop as much as
+// the launch saves (HB_FOLD_INV = 1: 390 us per call either way, 384 voting without any exact path), so they
+// keep the list.
+#ifndef HB_FOLD_INV
+#define HB_FOLD_INV 0
+#endif
+// jobs whose load transform reads a second operand (JobInvMul::kPostXf) keep the list
+template <class J, class = void>
+struct JobPostXf : std::false_type {};
+template <class J>
+struct JobPostXf<J, std::void_t<decltype(J::kPostXf)>> : std::integral_constant<bool, J::kPostXf> {};
+template <class C, bool FWD, int MODE, int FP64, class Job>
+constexpr bool kFoldExact = (FWD || HB_FOLD_INV) && MODE == kFastVote && FP64 != 0 && Job::kOneModulus && !JobPostXf<Job>::value;
 template <class C, bool FWD, int MODE, class Job, bool LAZY = false, int FP64 = 0>
 HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
                          uint32_t* list) {
@@ -781,12 +803,13 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
     // of us (a no-op otherwise), then let the one behind us be scheduled
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;");
+    constexpr bool FOLD = kFoldExact<C, FWD, MODE, FP64, Job>;
     uint64_t* W = smem_poly<C>();
     uint64_t* bar = W + SmemPlan<C>::BAR_WORD;
     const uint32_t tid = threadIdx.x;
     if constexpr (MODE == kExactList) n_items = list[0];
     auto item_of = [&](uint32_t i) -> uint32_t {
-        if constexpr (MODE == kExactList) return list[1 + i];
+        if constexpr (MODE == kExactList) return list[kListHead + i];
         else return job.order(i);      // the order in which the grid walks over the items (identity, or modulus-major)
     };
     if (tid == 0) {
@@ -862,43 +885,43 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
             a.m = t.fd;
             a.head_s = head_s;
             a.ttail = ttail;
-            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (TMEM_TAIL && FWD && FP64 == 2) {
             Fp64AltArithST a;
             a.m = t.fd;
             a.head_s = head_s;
             a.ttail = ttail;
-            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (TMEM_TAIL) {
             Fp64ArithST a;
             a.m = t.fd;
             a.head_s = head_s;
             a.ttail = ttail;
-            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
-            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (SMEM_HEAD && FWD && FP64 == 2) {
             Fp64AltArithS a;
             a.m = t.fd;
             a.head_s = head_s;
-            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (FWD && FP64 == 3) {
             Fp64ArithRaw a;      // as FP64 == 2, raw doubles out
             a.m = t.fd;
-            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (FWD && FP64 == 2) {
             Fp64AltArith a;
             a.m = t.fd;
-            done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (SMEM_HEAD) {
             Fp64ArithS a;
             a.m = t.fd;
             a.head_s = head_s;
-            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
-            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (FP64 != 0) {
             const Fp64Arith a = {t.fd};
-            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
-            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (LAZY) {
             const LazyInvArith a = {t.fm, t.sc};
             done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
@@ -913,17 +936,31 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
                 a.m = t.fm;
                 a.sc = t.sc;
                 a.kq = kq;
-                done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+                done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
             } else {
                 const FastArith a = {t.fm, t.sc};
                 done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
             }
         } else {
             const ExactArith a = {t.q, t.twoq, t.sc, t.lazy_out};
-            if constexpr (FWD) done = ntt_fwd_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
-            else done = ntt_inv_cta<C, MODE>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            if constexpr (FWD) done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
+            else done = ntt_inv_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         }
-        if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
+        if constexpr (FOLD) {
+            if (!done) {     // out of contract (not in normal use): the reference op sequence, right away
+                if (tid == 0) {
+                    fence_proxy_async();
+                    issue_poly_load<C>(W, tmap, bar, job.src_row(item));
+                }
+                mbar_wait(bar, parity);
+                parity ^= 1;
+                const ExactArith ax = {t.q, t.twoq, t.sc, t.lazy_out};
+                if constexpr (FWD) ntt_fwd_cta<C, kExactAll>(W, t, ax, job.xf(item), job.of(item, smap), pf);
+                else ntt_inv_cta<C, kExactAll>(W, t, ax, job.xf(item), job.of(item, smap), pf);
+            }
+        } else {
+            if (MODE == kFastVote && !done && tid == 0) defer_item(list, item);
+        }
     }
     // staged TMA stores read shared memory asynchronously: drain before exit
     if (FWD && SmemPlan<C>::kStagedStore && (tid & 31u) == 0) tma_store_wait_read();

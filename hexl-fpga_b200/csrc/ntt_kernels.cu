@@ -9,6 +9,7 @@
 namespace hb {
 
 int g_pdl = 1;               // plain NTT kernels launched with programmatic stream serialization (option "pdl", ntt_launch.cuh)
+int g_debug_skip_list = 0;   // measurement only, see launch.h
 int g_warp_tail = 1;         // FP64-pipe forward kernel with warp-dealt tail rows (one block barrier per transform instead of three), option "warp_tail"
 int g_small_tma_store = 0;   // small-modulus forward epilogue through TMA stores (option "small_tma_store"): measured 5% slower than the coalesced register stores (slice reuse waits on the store engine), off by default
 
@@ -21,7 +22,7 @@ __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64
     // the transform kernel behind us may be scheduled now; it waits for this grid before it reads anything
     asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (zero_count && e == 0) *zero_count = 0;   // reset the deferred list of the call that follows
+    if (zero_count && e == 0) zero_count[0] = zero_count[1] = 0;   // reset the deferred list (count, barrier word) of the call that follows
     if (fwd_out && e < (uint32_t)C::FWD_ENTRIES) {
         const int s = fwd_pack_src<C>(e);
         TwPair t = {0, 0};

@@ -16,6 +16,7 @@ template <class C>
 struct JobPlain {
     static constexpr bool kOneModulus = true;   // every item of a launch is transformed under tab
     static constexpr bool kModulusRuns = false;
+    static constexpr bool kPostXf = false;       // JobInvMul: the load transform reads a second operand
     HB_D uint32_t order(uint32_t i) const { return i; }
     uint64_t* data;
     ModTab tab;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ntt_inv(const __grid_con
 // inverse transform of NTT(a) (.) NTT(b): the fused tail of a polynomial multiply
 template <class C>
 struct JobInvMul : JobPlain<C> {
+    static constexpr bool kPostXf = true;
     const uint64_t* other;
     Divisor dv;
     uint32_t n_items;
@@ -142,11 +144,17 @@ static cudaError_t launch_dep(void (*kern)(KArgs...), unsigned grid, unsigned bl
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// *folded (voting mode): set when the launched kernel transforms out-of-contract polynomials itself
+// (ntt_block.cuh, kFoldExact: the forward FP64 kernels), i.e. no pass over a deferred list has to follow
 template <class C, bool FWD, int MODE>
 static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap, uint64_t* base, const ModTab& tab,
-                               uint64_t cnt, uint32_t* list, cudaStream_t st, uint32_t stride = 1, uint32_t offset = 0) {
+                               uint64_t cnt, uint32_t* list, cudaStream_t st, uint32_t stride = 1, uint32_t offset = 0,
+                               bool* folded = nullptr) {
     const size_t smem = ntt_smem_bytes<C>();
     cudaError_t e = cudaSuccess;
+    auto fp64_kernel = [&]() {
+        if ((FWD || HB_FOLD_INV) && MODE == kFastVote && folded) *folded = true;
+    };
     if constexpr (FWD) {
         JobFwd<C> job;
         job.data = base;
@@ -156,6 +164,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
             using CW = typename WarpTailCfg<C>::type;
             if (tab.fp64_ok && tab.fp64_alt_ok && g_warp_tail && !std::is_same<CW, C>::value) {
+                fp64_kernel();
                 // q <= 2^51 (1 + 1/32): full correction every other stage (modarith.cuh), ~15 % fewer scheduler cycles
                 auto kern = k_ntt_fwd<CW, MODE, 2>;
                 const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();
@@ -169,6 +178,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
+                fp64_kernel();
                 auto kern = k_ntt_fwd<CW, MODE, true>;
                 const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
@@ -181,6 +191,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
             if (tab.fp64_ok) {       // 36..51-bit modulus: butterflies on the FP64 pipe
+                fp64_kernel();
                 auto kern = k_ntt_fwd<C, MODE, true>;
                 const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
@@ -200,6 +211,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
         if constexpr (MODE == kFastVote || MODE == kFastTrust) {
             using CW = typename WarpTailCfg<C>::type;
             if (tab.fp64_ok && g_warp_tail && !std::is_same<CW, C>::value) {
+                fp64_kernel();
                 auto kern = k_ntt_inv<CW, MODE, false, true>;
                 const size_t smemw = ntt_smem_bytes_fp64_plain<CW>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw))) return e;
@@ -212,6 +224,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
                 return e != cudaSuccess ? e : cudaGetLastError();
             }
             if (tab.fp64_ok) {
+                fp64_kernel();
                 auto kern = k_ntt_inv<C, MODE, false, true>;
                 const size_t smemd = ntt_smem_bytes_fp64_plain<C>();
                 if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemd))) return e;
@@ -323,7 +336,12 @@ static cudaError_t launch_one(uint64_t* data, const ModTab& tab, uint64_t batch,
         *launches += 1;
         return launch_mode<C, FWD, kFastTrust>(tmap, smap, data, tab, batch, list, st, stride, offset);
     }
-    if ((e = launch_mode<C, FWD, kFastVote>(tmap, smap, data, tab, batch, list, st, stride, offset))) return e;
+    bool folded = false;
+    if ((e = launch_mode<C, FWD, kFastVote>(tmap, smap, data, tab, batch, list, st, stride, offset, &folded))) return e;
+    if (folded || g_debug_skip_list) {   // (debug_skip_list: measurement only, deferred items are dropped)
+        *launches += 1;
+        return cudaSuccess;
+    }
     // polynomials with out-of-contract words (none in normal use): exact pass
     // over the deferred list; exits at once when the list is empty
     *launches += 2;
