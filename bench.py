@@ -338,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
                                        "not measured in this run",
                      "algorithmic_bytes_per_launch": BATCH * NTT_BYTES, "launch_s": fwd_s},
         "clocks": clocks,
-        "kernel_variant": "persistent TMA-fed CTAs, 32 words/thread, FP64-pipe butterflies on centred integer-valued doubles (bit-exact), range vote + deferred exact list",
+        "kernel_variant": "persistent TMA-fed CTAs, 32 words/thread, FP64-pipe butterflies on centred integer-valued doubles (bit-exact), head twiddles in shared / tail twiddles in tensor memory, range vote with the exact path inside the forward kernel",
     }
     del x
     torch.cuda.empty_cache()

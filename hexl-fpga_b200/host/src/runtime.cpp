@@ -576,13 +576,33 @@ int run_ntt_batch(DeviceCtx& c, const std::vector<Request>& rs, bool inverse) {
     CU_TRY(cudaMemcpyAsync(c.d_small + n, r0.tw_p, n * 8, cudaMemcpyHostToDevice, c.s_h2d));
     g_h2d += 2 * n * 8;
     const size_t per_chunk = std::max<size_t>(1, c.slot_words / n);
-    const size_t n_chunks = (rs.size() + per_chunk - 1) / per_chunk;
+    // Chunk sizes ramp up at the start of a run and down at its end (1/8, 1/4, 1/2, 1, ..., 1, 1/2, 1/4, 1/8 of a
+    // slot): the first upload and the last download of a run overlap with nothing, so they are kept short.
+    std::vector<size_t> start{0};
+    {
+        constexpr int kRamp = 3;
+        const size_t total = rs.size();
+        size_t ramp[kRamp], tail_need = 0;
+        for (int k = 0; k < kRamp; ++k) tail_need += ramp[k] = std::max<size_t>(1, per_chunk >> (kRamp - k));
+        if (total <= 6 * per_chunk) tail_need = 0;            // short runs: plain chunks
+        size_t pos = 0;
+        for (int k = 0; k < kRamp && tail_need && pos + ramp[k] + tail_need <= total; ++k) start.push_back(pos += ramp[k]);
+        while (pos + per_chunk + tail_need <= total) start.push_back(pos += per_chunk);
+        if (tail_need) {
+            const size_t rest = total - pos - tail_need;      // < per_chunk
+            if (rest) start.push_back(pos += rest);
+            for (int k = kRamp - 1; k >= 0; --k) start.push_back(pos += ramp[k]);
+        } else if (pos < total) {
+            start.push_back(total);
+        }
+    }
+    const size_t n_chunks = start.size() - 1;
     const bool pinned = is_pinned(r0.out) && is_pinned(rs.back().out);
-    auto count_of = [&](size_t chunk) { return std::min(per_chunk, rs.size() - chunk * per_chunk); };
+    auto count_of = [&](size_t chunk) { return start[chunk + 1] - start[chunk]; };
     return run_chunks(
         c, n_chunks, pinned, pinned,
         [&](size_t chunk, ChunkIO& io) {
-            const size_t off = chunk * per_chunk, cnt = count_of(chunk);
+            const size_t off = start[chunk], cnt = count_of(chunk);
             for (size_t i = 0; i < cnt; ++i) push_seg(io.in, rs[off + i].out, i * n, n);
             io.out = io.in;
         },
@@ -913,7 +933,7 @@ int hexl_b200_host_acquire(void) {
     rt->batch_cap[OP_INTT] = env_u64("BATCH_SIZE_INTT", 0);
     rt->batch_cap[OP_KEYSWITCH] = env_u64("BATCH_SIZE_KEYSWITCH", 0);
     rt->debug = (int)env_u64("FPGA_DEBUG", 0);
-    const size_t slot_bytes = (size_t)env_u64("HEXL_B200_SLOT_MB", 64) << 20;
+    const size_t slot_bytes = (size_t)env_u64("HEXL_B200_SLOT_MB", 32) << 20;
     // copy threads for pageable callers: enough to keep a Gen5 x16 link busy in both directions, but
     // never more than the cores this process may use
     unsigned hw = std::thread::hardware_concurrency();
