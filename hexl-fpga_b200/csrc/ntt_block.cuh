@@ -782,6 +782,14 @@ HB_D bool ntt_inv_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
 // time, plus a residency assumption.  In the inverse kernels the extra code costs the main loop as much as
 // the launch saves (HB_FOLD_INV = 1: 390 us per call either way, 384 voting without any exact path), so they
 // keep the list.
+// ... and alternating with other kernels, as every real caller does (bench.py: forward / inverse in turns), the
+// forward call with the exact path inside takes 358.5 us instead of 344.8 with the separate pass, although
+// the same call repeated back to back takes 343.4 instead of 346.4 (tools/time_pattern.py): the kernel is
+// 40 KB larger and comes back into a cold instruction cache every time.  Both are therefore OFF; the code
+// stays for the measurement (make CFLAGS_EXTRA="-DHB_FOLD_FWD=1").
+#ifndef HB_FOLD_FWD
+#define HB_FOLD_FWD 0
+#endif
 #ifndef HB_FOLD_INV
 #define HB_FOLD_INV 0
 #endif
@@ -791,7 +799,7 @@ struct JobPostXf : std::false_type {};
 template <class J>
 struct JobPostXf<J, std::void_t<decltype(J::kPostXf)>> : std::integral_constant<bool, J::kPostXf> {};
 template <class C, bool FWD, int MODE, int FP64, class Job>
-constexpr bool kFoldExact = (FWD || HB_FOLD_INV) && MODE == kFastVote && FP64 != 0 && Job::kOneModulus && !JobPostXf<Job>::value;
+constexpr bool kFoldExact = (FWD ? HB_FOLD_FWD != 0 : HB_FOLD_INV != 0) && MODE == kFastVote && FP64 != 0 && Job::kOneModulus && !JobPostXf<Job>::value;
 template <class C, bool FWD, int MODE, class Job, bool LAZY = false, int FP64 = 0>
 HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const Job& job, uint32_t n_items,
                          uint32_t* list) {

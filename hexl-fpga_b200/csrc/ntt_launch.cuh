@@ -153,7 +153,7 @@ static cudaError_t launch_mode(const CUtensorMap& tmap, const CUtensorMap& smap,
     const size_t smem = ntt_smem_bytes<C>();
     cudaError_t e = cudaSuccess;
     auto fp64_kernel = [&]() {
-        if ((FWD || HB_FOLD_INV) && MODE == kFastVote && folded) *folded = true;
+        if ((FWD ? HB_FOLD_FWD != 0 : HB_FOLD_INV != 0) && MODE == kFastVote && folded) *folded = true;
     };
     if constexpr (FWD) {
         JobFwd<C> job;
