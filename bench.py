@@ -367,11 +367,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end through the reference's host-pointer API (every rank) ----
     ceiling = rank_max(copy_ceiling(dev))
     e2e = {}
-    for kind in ("pinned", "pageable"):
+    for kind in ("pinned", "pageable", "registered"):
         r = e2e_ntt(args, hb, ob, dev, world, kind)
         r["s"] = rank_max(r["s"])
         e2e[kind] = r
-    pin, pag = e2e["pinned"], e2e["pageable"]
+    pin, pag, reg = e2e["pinned"], e2e["pageable"], e2e["registered"]
     step_bytes = 4 * BATCH * N * 8                      # fwd + inv, in + out
     line["e2e"] = {"value": world * 2 * pin["batch"] * pin["steps"] / pin["s"], "unit": "NTT/s",
                    "h2d_bytes_per_step": pin["h2d"], "d2h_bytes_per_step": pin["d2h"],
@@ -381,6 +381,11 @@ def run_ours(args, rank, world, local_rank):
                                 "note": "the same calls on pageable (numpy) buffers: staged through the runtime's "
                                         "pinned ring by its copy threads",
                                 "ratio_to_pinned": pin["s"] / pag["s"] * pag["steps"] / pin["steps"]},
+                   "pageable_registered": {"value": world * 2 * reg["batch"] * reg["steps"] / reg["s"], "unit": "NTT/s",
+                                           "note": "the same pageable buffer registered once in place with "
+                                                   "hexl_b200_host_pin_buffer (what an integration does for its "
+                                                   "ciphertext pool): no staging copies",
+                                           "ratio_to_pinned": pin["s"] / reg["s"] * reg["steps"] / pin["steps"]},
                    "copy_ceiling": {"seconds_per_step": ceiling, "GBps_per_gpu_each_way": step_bytes / 2 / ceiling / 1e9,
                                     "note": "plain cudaMemcpyAsync of one step's bytes (H2D and D2H on two streams, "
                                             "pinned buffers, all ranks at once): the PCIe / host-memory ceiling of "
@@ -474,6 +479,8 @@ def e2e_ntt(args, hb, ob, dev, world, kind="pinned"):
         host = torch.randint(0, Q52, (BATCH, N), dtype=torch.int64)
         if kind == "pinned":
             host = host.pin_memory()
+        elif kind == "registered":
+            hb.pin_buffer(host.numpy())                 # released with the library below
         ref0 = host[:1].clone()
         ptr = host.data_ptr()
         steps = max(2, min(args.steps, 5))

@@ -23,7 +23,7 @@ namespace hexl_b200 {
 static thread_local std::string g_err = "";
 std::atomic<uint64_t> g_launches{0}, g_h2d{0}, g_d2h{0};
 static std::atomic<int> g_ntt_variant{1};   // 1: 32 words/thread at N=16384 (default), 0: 16
-static std::atomic<int64_t> g_ks_workspace_mb{4096};   // scratch budget of one keyswitch plan (180 GB HBM: be generous, fewer chunk tails)
+static std::atomic<int64_t> g_ks_workspace_mb{10240};  // scratch budget of one keyswitch plan: ~1000 items per chunk at D/K = 7/8 (measured optimum, profiles/r2_time_ks_ws.jsonl: long runs of one modulus per CTA, few launch tails)
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -729,8 +729,9 @@ int hexl_b200_keyswitch(hexl_b200_ks_plan* p, uint64_t* d_result, const uint64_t
     const uint64_t per_item = hb::ks_scratch_words_per_item(p->dev);
     uint64_t chunk = ((uint64_t)g_ks_workspace_mb.load() << 20) / 8 / per_item;
     if (chunk < 1) chunk = 1;
-    if (chunk > batch) chunk = batch;
     if (chunk > 16384) chunk = 16384;
+    // equal chunks: a short last chunk runs the same number of launches over a fraction of the work
+    chunk = (batch + (batch + chunk - 1) / chunk - 1) / ((batch + chunk - 1) / chunk);
     std::lock_guard<std::mutex> lk(p->mu);
     if (p->ws_words < chunk * per_item) {
         // stream-ordered work may still use the old buffer

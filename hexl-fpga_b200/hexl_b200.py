@@ -66,6 +66,8 @@ _SIGNATURES = {
     "hexl_b200_host_keyswitch_many": ([vp, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, vp], C.c_int),
     "hexl_b200_get_stats": ([vp], C.c_int),
     "hexl_b200_host_device_stats": ([C.c_int, vp], C.c_int),
+    "hexl_b200_host_pin_buffer": ([vp, u64], C.c_int),
+    "hexl_b200_host_unpin_buffer": ([vp], C.c_int),
     "hexl_b200_reset_stats": ([], C.c_int),
 }
 
@@ -133,6 +135,16 @@ def device_stats(worker):
     st = DeviceStats()
     _check(lib().hexl_b200_host_device_stats(worker, C.addressof(st)), "device_stats")
     return {"device": st.device, "batches": st.batches, "items": st.items}
+
+
+def pin_buffer(arr):
+    """register a numpy array's memory with CUDA in place (hexl_b200_host_pin_buffer); the host API then
+    DMAs straight out of / into it instead of staging it through its pinned ring"""
+    _check(lib().hexl_b200_host_pin_buffer(arr.ctypes.data, arr.nbytes), "pin_buffer")
+
+
+def unpin_buffer(arr):
+    _check(lib().hexl_b200_host_unpin_buffer(arr.ctypes.data), "unpin_buffer")
 
 
 def reset_stats():

@@ -29,7 +29,7 @@
 #include <cuda_runtime.h>
 #include <sched.h>
 #if defined(__x86_64__)
-#include <emmintrin.h>
+#include <immintrin.h>
 #endif
 
 #include <algorithm>
@@ -137,11 +137,39 @@ struct CopyJob {
 // first read for ownership.  Non-temporal stores (SSE2, baseline x86-64) skip that read -- 3 instead of 4 units
 // of memory traffic per direction -- and leave the cache to the caller.
 #if defined(__x86_64__)
+// 64-byte loads and full-line non-temporal stores where the CPU has AVX-512 (one write-combining buffer per
+// store instead of four partial fills), chosen once at run time; the SSE2 loop below is the baseline.
+__attribute__((target("avx512f"))) void copy_stream_512(char* d, const char* s, size_t bytes) {
+    size_t head = (64 - ((uintptr_t)d & 63)) & 63;
+    if (head > bytes) head = bytes;
+    memcpy(d, s, head);
+    d += head;
+    s += head;
+    bytes -= head;
+    const size_t n = bytes / 256;
+    for (size_t i = 0; i < n; ++i) {
+        const __m512i a = _mm512_loadu_si512(s), b = _mm512_loadu_si512(s + 64);
+        const __m512i c = _mm512_loadu_si512(s + 128), e = _mm512_loadu_si512(s + 192);
+        _mm512_stream_si512((__m512i*)d, a);
+        _mm512_stream_si512((__m512i*)(d + 64), b);
+        _mm512_stream_si512((__m512i*)(d + 128), c);
+        _mm512_stream_si512((__m512i*)(d + 192), e);
+        s += 256;
+        d += 256;
+    }
+    memcpy(d, s, bytes - n * 256);
+    _mm_sfence();
+}
+const bool g_avx512 = __builtin_cpu_supports("avx512f") && !getenv("HEXL_B200_NO_AVX512");
 void copy_stream(void* dst, const void* src, size_t bytes) {
     char* d = (char*)dst;
     const char* s = (const char*)src;
     if (bytes < (size_t)64 << 10) {
         memcpy(d, s, bytes);
+        return;
+    }
+    if (g_avx512) {
+        copy_stream_512(d, s, bytes);
         return;
     }
     size_t head = (16 - ((uintptr_t)d & 15)) & 15;
@@ -906,9 +934,61 @@ int set_worksize(Op op, uint64_t ws) {
 
 bool pow2_in(uint64_t n, uint64_t lo, uint64_t hi) { return n >= lo && n <= hi && !(n & (n - 1)); }
 
+// ---- caller buffers pinned in place (hexl_b200_host_pin_buffer) -----------------------------------------
+// page-aligned base -> {bytes, the pointer the caller gave}
+struct PinnedRange {
+    size_t bytes;
+    const void* user;
+};
+std::mutex g_pin_mu;
+std::map<uintptr_t, PinnedRange> g_pins;
+
+void unpin_all() {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (auto& kv : g_pins) cudaHostUnregister((void*)kv.first);
+    g_pins.clear();
+}
+
 }  // namespace
 
 extern "C" {
+
+int hexl_b200_host_pin_buffer(void* p, uint64_t bytes) {
+    if (!p || !bytes) return fail(HEXL_B200_EINVAL, "pin_buffer: NULL pointer or zero size");
+    const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)4095, hi = ((uintptr_t)p + bytes + 4095) & ~(uintptr_t)4095;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pins.upper_bound(lo);
+    if (it != g_pins.begin()) {
+        auto pr = std::prev(it);
+        if (pr->first + pr->second.bytes >= hi) return 0;          // already covered
+        if (pr->first + pr->second.bytes > lo) it = pr;            // overlaps from below
+    }
+    if (it != g_pins.end() && it->first < hi)
+        return fail(HEXL_B200_EINVAL, "pin_buffer: [%p, +%llu) overlaps a range pinned earlier (unpin that one first)", p,
+                    (unsigned long long)bytes);
+    const cudaError_t e = cudaHostRegister((void*)lo, hi - lo, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return cuda_fail(e, "pin_buffer: cudaHostRegister");
+    }
+    g_pins[lo] = PinnedRange{hi - lo, p};
+    return 0;
+}
+
+int hexl_b200_host_unpin_buffer(void* p) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (auto it = g_pins.begin(); it != g_pins.end(); ++it) {
+        if (it->second.user != p) continue;
+        const cudaError_t e = cudaHostUnregister((void*)it->first);
+        g_pins.erase(it);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return cuda_fail(e, "unpin_buffer: cudaHostUnregister");
+        }
+        return 0;
+    }
+    return fail(HEXL_B200_EINVAL, "unpin_buffer: %p was not pinned through hexl_b200_host_pin_buffer", p);
+}
 
 int hexl_b200_host_acquire(void) {
     std::lock_guard<std::mutex> lk(g_life);
@@ -964,13 +1044,17 @@ int hexl_b200_host_acquire(void) {
 int hexl_b200_host_release(void) {
     std::lock_guard<std::mutex> lk(g_life);
     Runtime* rt = g_rt;
-    if (!rt) return 0;
+    if (!rt) {
+        unpin_all();
+        return 0;
+    }
     {
         std::lock_guard<std::mutex> l2(rt->mu);
         rt->stop = true;
     }
     rt->cv_work.notify_all();
     for (auto& t : rt->workers) t.join();
+    unpin_all();       // nothing of ours can still be copying out of the caller's buffers
     for (auto& c : rt->ctxs) c->destroy();
     g_rt = nullptr;
     delete rt;

@@ -154,7 +154,7 @@ int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, ui
  *                      serialization (launch latency overlaps the kernel in front); 0: plain launches
  *   "warp_tail"        1 (default): the FP64-pipe kernels at n = 16384 deal the tail rows out by warp
  *                      (one block barrier per transform instead of three); 0: by thread index
- *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16)
+ *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16, default 10240; a batch is cut into equal chunks that fit)
  *   "ks_mac_items"     items sharing one key load in the keyswitch MAC (1, 4, 8) */
 int hexl_b200_set_option(const char* name, int64_t value);
 
@@ -213,6 +213,17 @@ int hexl_b200_host_keyswitch_many(uint64_t* result_base, const uint64_t* t_targe
                                   uint64_t key_component_count, const uint64_t* moduli,
                                   const uint64_t** k_switch_keys, const uint64_t* modswitch_factors,
                                   const uint64_t* twiddle_factors);
+
+/* Pin a caller buffer in place (not in the reference).  Every caller of the reference passes pageable memory
+ * (std::vector), which this library stages through its own pinned ring with CPU copy threads -- bound by
+ * host cores and host-memory bandwidth (about 0.6 of the pinned rate on a 16-core box).  An integration that
+ * owns long-lived buffers (a ciphertext pool) registers them once; from then on they are the source / target
+ * of the DMA directly, like memory from cudaHostAlloc.  Wraps cudaHostRegister (page-granular, portable
+ * across the NUM_DEV devices).  The buffer must stay mapped until hexl_b200_host_unpin_buffer(p) -- same
+ * pointer -- or hexl_b200_host_release(), which unpins everything.  A range already covered returns 0; a
+ * partial overlap with an earlier range is EINVAL. */
+int hexl_b200_host_pin_buffer(void* p, uint64_t bytes);
+int hexl_b200_host_unpin_buffer(void* p);
 
 /* Counters since acquire: kernel launches issued by this library and bytes
  * moved host<->device by the host-pointer API (for bench.py's gpu_launches /

@@ -41,6 +41,45 @@ def test_pageable_and_pinned_callers_agree(acquired):
         assert np.array_equal(arr, src)
 
 
+def test_buffer_pinned_in_place(acquired):
+    """hexl_b200_host_pin_buffer: a pageable (numpy) buffer registered once is DMA'd directly -- no bytes pass
+    through the staging ring's copy threads, same results -- until it is unpinned again."""
+    hb = acquired
+    n, q, B = 16384, 2251799814045697, 300
+    t = ob.Tables(n, q)
+    data = np.stack([ob.splitmix(n, 4000 + i, q) for i in range(4)])
+    src = np.ascontiguousarray(np.resize(data, (B, n)))
+    src[:, 1] = np.arange(B, dtype=np.uint64)
+    buf = np.empty(B * n + 7, dtype=np.uint64)[7:].reshape(B, n)     # not page-aligned
+    buf[:] = src
+    hb.pin_buffer(buf)
+    hb.pin_buffer(buf[10:20])                           # already covered: a no-op
+    with pytest.raises(hb.HexlB200Error, match="overlaps"):
+        hb._check(hb.lib().hexl_b200_host_pin_buffer(buf.ctypes.data + buf.nbytes - 4096, 1 << 20), "pin_buffer")
+    try:
+        hb.set_worksize_NTT(B)
+        for i in range(B):
+            hb.NTT(buf[i], t.roots, t.precon, q, n)
+        assert hb.NTTCompleted()
+        for i in (0, 1, 150, B - 1):
+            assert np.array_equal(buf[i], ob.fwd_ntt(src[i], t)), i
+        hb.set_worksize_INTT(B)
+        for i in range(B):
+            hb.INTT(buf[i], t.inv_roots, t.precon_inv, q, t.inv_n, t.inv_n_w, n)
+        assert hb.INTTCompleted()
+        assert np.array_equal(buf, src)
+    finally:
+        hb.unpin_buffer(buf)
+    with pytest.raises(hb.HexlB200Error, match="not pinned"):
+        hb.unpin_buffer(buf)
+    # and staged again afterwards
+    hb.set_worksize_NTT(2)
+    hb.NTT(buf[0], t.roots, t.precon, q, n)
+    hb.NTT(buf[1], t.roots, t.precon, q, n)
+    assert hb.NTTCompleted()
+    assert np.array_equal(buf[1], ob.fwd_ntt(src[1], t))
+
+
 def test_pageable_keyswitch_and_dyadic(acquired):
     hb = acquired
     p = KsProblem(8192, 4, 5, 70, 48, seed=5)           # 70 items x 768 KiB > one 64 MiB slot

@@ -169,7 +169,7 @@ def test_chunked_workspace_matches(hb):
         plan.keyswitch(res, gpu(p.t_target), batch)
         assert np.array_equal(res.cpu().numpy().view(np.uint64), p.expected())
     finally:
-        hb.set_option("ks_workspace_mb", 4096)
+        hb.set_option("ks_workspace_mb", 10240)
 
 
 def test_host_api_accumulates(acquired):
