@@ -23,6 +23,10 @@ print(json.dumps({"copy_threads": os.environ.get("HEXL_B200_COPY_THREADS"), "slo
                   "ms_per_step": dt * 1e3, "ntt_per_s": 2 * B / dt, "cpus": len(os.sched_getaffinity(0))}))
 hb.release_FPGA_resources()
 '''
-for th, mb, pin in [("8", "64", "1"), ("4", "64", "0"), ("8", "64", "0"), ("12", "64", "0"), ("16", "64", "0"), ("8", "16", "0"), ("16", "16", "0"), ("8", "128", "0")]:
+CONFIGS = [("8", "32", "1"), ("4", "32", "0"), ("8", "32", "0"), ("12", "32", "0"), ("14", "32", "0"), ("16", "32", "0"),
+           ("12", "16", "0"), ("12", "8", "0"), ("12", "64", "0")]
+if len(sys.argv) > 1:      # threads:slot_mb:pinned ...
+    CONFIGS = [tuple(a.split(":")) for a in sys.argv[1:]]
+for th, mb, pin in CONFIGS:
     env = dict(os.environ, HEXL_B200_COPY_THREADS=th, HEXL_B200_SLOT_MB=mb, PIN=pin)
     subprocess.run([sys.executable, "-c", CODE % {"root": ROOT}], env=env)
