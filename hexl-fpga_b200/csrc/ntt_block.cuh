@@ -323,6 +323,10 @@ struct Prefetch {
     // starts the copy.  `row` is valid in lane 0 of every warp.
     template <class C>
     HB_D void issue_when_all_warps_done() const {
+        // the copy engine will overwrite words this warp wrote in the passes before: order every lane's
+        // generic-proxy stores in front of the async proxy before the warp reports (the issuing lane's own
+        // fence below covers only what that thread has observed)
+        fence_proxy_async();
         __syncwarp();
         if ((threadIdx.x & 31u) == 0) {
             uint64_t* W = smem_poly<C>();

@@ -914,6 +914,39 @@ int submit(const Request& r) {
     return 0;
 }
 
+// `count` asynchronous requests that differ only in their pointers, queued under one lock per stretch of free
+// queue space (the *_many helpers; a worksize of 1 falls back to one synchronous submit per item)
+template <class Advance>
+int submit_many(Request r, uint64_t count, const Advance& advance) {
+    Runtime* rt = g_rt;
+    if (!rt) return fail(HEXL_B200_ENODEV, "%s: acquire_FPGA_resources() has not been called", kOpName[r.op]);
+    uint64_t i = 0;
+    while (i < count) {
+        bool wake;
+        {
+            std::unique_lock<std::mutex> lk(rt->mu);
+            if (rt->worksize[r.op] <= 1) {
+                lk.unlock();
+                if (int rc = submit(r)) return rc;
+                advance(r);
+                ++i;
+                continue;
+            }
+            rt->cv_space.wait(lk, [&] { return rt->queue.size() < rt->capacity; });
+            const bool was_empty = rt->queue.empty();
+            for (; i < count && rt->queue.size() < rt->capacity; ++i) {
+                rt->queue.push_back(r);
+                rt->submitted[r.op]++;
+                if (rt->expected[r.op]) rt->expected[r.op]--;
+                advance(r);
+            }
+            wake = was_empty || rt->expected[r.op] == 0;
+        }
+        if (wake) rt->cv_work.notify_all();
+    }
+    return 0;
+}
+
 int completed(Op op) {
     Runtime* rt = g_rt;
     if (!rt) return fail(HEXL_B200_ENODEV, "%sCompleted: library not acquired", kOpName[op]);
@@ -949,6 +982,64 @@ void unpin_all() {
     std::lock_guard<std::mutex> lk(g_pin_mu);
     for (auto& kv : g_pins) cudaHostUnregister((void*)kv.first);
     g_pins.clear();
+}
+
+// validation + request record of the four operations (shared by the single calls and the *_many helpers)
+int build_dyadic_multiply(Request& r, uint64_t* results, const uint64_t* operand1, const uint64_t* operand2,
+                                   uint64_t n, const uint64_t* moduli, uint64_t n_moduli) {
+    // reference checks: host/src/dyadic_multiply.cpp:15-26 (non-null, n_moduli > 0)
+    if (!results || !operand1 || !operand2 || !moduli)
+        return fail(HEXL_B200_EINVAL, "DyadicMultiply: NULL pointer");
+    if (n == 0 || (n & 1) || n_moduli == 0)
+        return fail(HEXL_B200_EINVAL, "DyadicMultiply: n must be even and n_moduli > 0");
+    r.op = OP_DYADIC;
+    r.out = results; r.in1 = operand1; r.in2 = operand2;
+    r.n = n; r.moduli = moduli; r.n_moduli = n_moduli;
+        return 0;
+}
+
+int build_keyswitch(Request& r, uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n,
+                             uint64_t decomp_modulus_size, uint64_t key_modulus_size,
+                             uint64_t rns_modulus_size, uint64_t key_component_count,
+                             const uint64_t* moduli, const uint64_t** k_switch_keys,
+                             const uint64_t* modswitch_factors, const uint64_t* twiddle_factors) {
+    // reference checks: host/src/keyswitch.cpp:18-37
+    if (!result || !t_target_iter_ptr || !moduli || !k_switch_keys || !modswitch_factors)
+        return fail(HEXL_B200_EINVAL, "KeySwitch: NULL pointer");
+    if (!pow2_in(n, 1024, 16384)) return fail(HEXL_B200_EINVAL, "KeySwitch: n must be a power of two in [1024,16384]");
+    if (key_component_count != 2) return fail(HEXL_B200_EINVAL, "KeySwitch: key_component_count must be 2");
+    if (decomp_modulus_size == 0 || decomp_modulus_size + 1 > key_modulus_size ||
+        rns_modulus_size != decomp_modulus_size + 1)
+        return fail(HEXL_B200_EINVAL, "KeySwitch: inconsistent decomp/key/rns modulus sizes");
+    r.op = OP_KEYSWITCH;
+    r.out = result; r.in1 = t_target_iter_ptr; r.n = n;
+    r.D = decomp_modulus_size; r.K = key_modulus_size; r.R = rns_modulus_size; r.C = key_component_count;
+    r.moduli = moduli; r.keys = k_switch_keys; r.msf = modswitch_factors; r.twiddles = twiddle_factors;
+        return 0;
+}
+
+int build_ntt(Request& r, uint64_t* operand, const uint64_t* roots, const uint64_t* precon, uint64_t q,
+                       uint64_t n) {
+    // reference check: host/src/ntt.cpp:18-26 (n == 16384); we accept 2^10..2^15
+    if (!operand || !roots || !precon) return fail(HEXL_B200_EINVAL, "NTT: NULL pointer");
+    if (!pow2_in(n, 1024, 32768)) return fail(HEXL_B200_EINVAL, "NTT: n must be a power of two in [1024,32768]");
+    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "NTT: modulus out of range");
+    r.op = OP_NTT;
+    r.out = operand; r.tw = roots; r.tw_p = precon; r.q = q; r.n = n;
+        return 0;
+}
+
+int build_intt(Request& r, uint64_t* operand, const uint64_t* inv_roots, const uint64_t* precon_inv, uint64_t q,
+                        uint64_t inv_n, uint64_t inv_n_w, uint64_t n) {
+    // reference check: host/src/intt.cpp:18-27
+    if (!operand || !inv_roots || !precon_inv) return fail(HEXL_B200_EINVAL, "INTT: NULL pointer");
+    if (!pow2_in(n, 1024, 32768)) return fail(HEXL_B200_EINVAL, "INTT: n must be a power of two in [1024,32768]");
+    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "INTT: modulus out of range");
+    if (inv_n >= q || inv_n_w >= q) return fail(HEXL_B200_EINVAL, "INTT: inv_n / inv_n_w not reduced");
+    r.op = OP_INTT;
+    r.out = operand; r.tw = inv_roots; r.tw_p = precon_inv; r.q = q; r.inv_n = inv_n; r.inv_n_w = inv_n_w;
+    r.n = n;
+        return 0;
 }
 
 }  // namespace
@@ -1088,15 +1179,8 @@ int hexl_b200_host_intt_completed(void) { return completed(OP_INTT); }
 
 int hexl_b200_host_dyadic_multiply(uint64_t* results, const uint64_t* operand1, const uint64_t* operand2,
                                    uint64_t n, const uint64_t* moduli, uint64_t n_moduli) {
-    // reference checks: host/src/dyadic_multiply.cpp:15-26 (non-null, n_moduli > 0)
-    if (!results || !operand1 || !operand2 || !moduli)
-        return fail(HEXL_B200_EINVAL, "DyadicMultiply: NULL pointer");
-    if (n == 0 || (n & 1) || n_moduli == 0)
-        return fail(HEXL_B200_EINVAL, "DyadicMultiply: n must be even and n_moduli > 0");
     Request r;
-    r.op = OP_DYADIC;
-    r.out = results; r.in1 = operand1; r.in2 = operand2;
-    r.n = n; r.moduli = moduli; r.n_moduli = n_moduli;
+    if (int rc = build_dyadic_multiply(r, results, operand1, operand2, n, moduli, n_moduli)) return rc;
     return submit(r);
 }
 
@@ -1105,80 +1189,63 @@ int hexl_b200_host_keyswitch(uint64_t* result, const uint64_t* t_target_iter_ptr
                              uint64_t rns_modulus_size, uint64_t key_component_count,
                              const uint64_t* moduli, const uint64_t** k_switch_keys,
                              const uint64_t* modswitch_factors, const uint64_t* twiddle_factors) {
-    // reference checks: host/src/keyswitch.cpp:18-37
-    if (!result || !t_target_iter_ptr || !moduli || !k_switch_keys || !modswitch_factors)
-        return fail(HEXL_B200_EINVAL, "KeySwitch: NULL pointer");
-    if (!pow2_in(n, 1024, 16384)) return fail(HEXL_B200_EINVAL, "KeySwitch: n must be a power of two in [1024,16384]");
-    if (key_component_count != 2) return fail(HEXL_B200_EINVAL, "KeySwitch: key_component_count must be 2");
-    if (decomp_modulus_size == 0 || decomp_modulus_size + 1 > key_modulus_size ||
-        rns_modulus_size != decomp_modulus_size + 1)
-        return fail(HEXL_B200_EINVAL, "KeySwitch: inconsistent decomp/key/rns modulus sizes");
     Request r;
-    r.op = OP_KEYSWITCH;
-    r.out = result; r.in1 = t_target_iter_ptr; r.n = n;
-    r.D = decomp_modulus_size; r.K = key_modulus_size; r.R = rns_modulus_size; r.C = key_component_count;
-    r.moduli = moduli; r.keys = k_switch_keys; r.msf = modswitch_factors; r.twiddles = twiddle_factors;
+    if (int rc = build_keyswitch(r, result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_size, rns_modulus_size, key_component_count, moduli, k_switch_keys, modswitch_factors, twiddle_factors)) return rc;
     return submit(r);
 }
 
 int hexl_b200_host_ntt(uint64_t* operand, const uint64_t* roots, const uint64_t* precon, uint64_t q,
                        uint64_t n) {
-    // reference check: host/src/ntt.cpp:18-26 (n == 16384); we accept 2^10..2^15
-    if (!operand || !roots || !precon) return fail(HEXL_B200_EINVAL, "NTT: NULL pointer");
-    if (!pow2_in(n, 1024, 32768)) return fail(HEXL_B200_EINVAL, "NTT: n must be a power of two in [1024,32768]");
-    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "NTT: modulus out of range");
     Request r;
-    r.op = OP_NTT;
-    r.out = operand; r.tw = roots; r.tw_p = precon; r.q = q; r.n = n;
+    if (int rc = build_ntt(r, operand, roots, precon, q, n)) return rc;
     return submit(r);
 }
 
 int hexl_b200_host_intt(uint64_t* operand, const uint64_t* inv_roots, const uint64_t* precon_inv, uint64_t q,
                         uint64_t inv_n, uint64_t inv_n_w, uint64_t n) {
-    // reference check: host/src/intt.cpp:18-27
-    if (!operand || !inv_roots || !precon_inv) return fail(HEXL_B200_EINVAL, "INTT: NULL pointer");
-    if (!pow2_in(n, 1024, 32768)) return fail(HEXL_B200_EINVAL, "INTT: n must be a power of two in [1024,32768]");
-    if (q < 2 || q >> 62) return fail(HEXL_B200_EINVAL, "INTT: modulus out of range");
-    if (inv_n >= q || inv_n_w >= q) return fail(HEXL_B200_EINVAL, "INTT: inv_n / inv_n_w not reduced");
     Request r;
-    r.op = OP_INTT;
-    r.out = operand; r.tw = inv_roots; r.tw_p = precon_inv; r.q = q; r.inv_n = inv_n; r.inv_n_w = inv_n_w;
-    r.n = n;
+    if (int rc = build_intt(r, operand, inv_roots, precon_inv, q, inv_n, inv_n_w, n)) return rc;
     return submit(r);
 }
 
 
 int hexl_b200_host_ntt_many(uint64_t* base, uint64_t stride, uint64_t count, const uint64_t* roots,
                             const uint64_t* precon, uint64_t q, uint64_t n) {
-    for (uint64_t i = 0; i < count; ++i)
-        if (int rc = hexl_b200_host_ntt(base + i * stride, roots, precon, q, n)) return rc;
-    return 0;
+    if (!count) return 0;
+    Request r;
+    if (int rc = build_ntt(r, base, roots, precon, q, n)) return rc;
+    return submit_many(r, count, [&](Request& x) { x.out += stride; });
 }
 int hexl_b200_host_intt_many(uint64_t* base, uint64_t stride, uint64_t count, const uint64_t* inv_roots,
                              const uint64_t* precon_inv, uint64_t q, uint64_t inv_n, uint64_t inv_n_w,
                              uint64_t n) {
-    for (uint64_t i = 0; i < count; ++i)
-        if (int rc = hexl_b200_host_intt(base + i * stride, inv_roots, precon_inv, q, inv_n, inv_n_w, n))
-            return rc;
-    return 0;
+    if (!count) return 0;
+    Request r;
+    if (int rc = build_intt(r, base, inv_roots, precon_inv, q, inv_n, inv_n_w, n)) return rc;
+    return submit_many(r, count, [&](Request& x) { x.out += stride; });
 }
 int hexl_b200_host_dyadic_multiply_many(uint64_t* results, const uint64_t* op1, const uint64_t* op2,
                                         uint64_t count, uint64_t n, const uint64_t* moduli,
                                         uint64_t n_moduli) {
-    for (uint64_t i = 0; i < count; ++i)
-        if (int rc = hexl_b200_host_dyadic_multiply(results + i * 3 * n_moduli * n, op1 + i * 2 * n_moduli * n,
-                                                    op2 + i * 2 * n_moduli * n, n, moduli, n_moduli))
-            return rc;
-    return 0;
+    if (!count) return 0;
+    Request r;
+    if (int rc = build_dyadic_multiply(r, results, op1, op2, n, moduli, n_moduli)) return rc;
+    return submit_many(r, count, [&](Request& x) {
+        x.out += 3 * n_moduli * n;
+        x.in1 += 2 * n_moduli * n;
+        x.in2 += 2 * n_moduli * n;
+    });
 }
 int hexl_b200_host_keyswitch_many(uint64_t* result, const uint64_t* t_target, uint64_t count, uint64_t n,
                                   uint64_t D, uint64_t K, uint64_t R, uint64_t C, const uint64_t* moduli,
                                   const uint64_t** keys, const uint64_t* msf, const uint64_t* twiddles) {
-    for (uint64_t i = 0; i < count; ++i)
-        if (int rc = hexl_b200_host_keyswitch(result + i * 2 * D * n, t_target + i * D * n, n, D, K, R, C,
-                                              moduli, keys, msf, twiddles))
-            return rc;
-    return 0;
+    if (!count) return 0;
+    Request r;
+    if (int rc = build_keyswitch(r, result, t_target, n, D, K, R, C, moduli, keys, msf, twiddles)) return rc;
+    return submit_many(r, count, [&](Request& x) {
+        x.out += 2 * D * n;
+        x.in1 += D * n;
+    });
 }
 
 }  // extern "C"

@@ -80,6 +80,51 @@ def test_buffer_pinned_in_place(acquired):
     assert np.array_equal(buf[1], ob.fwd_ntt(src[1], t))
 
 
+def test_bulk_submission_helpers(acquired):
+    """hexl_b200_host_*_many: `count` calls in one FFI crossing, queued under one lock per stretch of free queue
+    space -- more calls than the request queue holds (FPGA_BUFSIZE 4096), asynchronous and (worksize 1) synchronous."""
+    hb = acquired
+    n, B = 1024, 5000
+    q = int(ob.primes(1, 51, n)[0])
+    t = ob.Tables(n, q)
+    src = np.stack([ob.splitmix(n, 5000 + i, q) for i in range(16)])
+    buf = np.ascontiguousarray(np.resize(src, (B, n)))
+    buf[:, 2] = np.arange(B, dtype=np.uint64)
+    orig = buf.copy()
+    hb.set_worksize_NTT(B)
+    hb.NTT_many(buf.ctypes.data, n, B, t.roots, t.precon, q, n)
+    assert hb.NTTCompleted()
+    for i in (0, 1, 4095, 4096, B - 1):
+        assert np.array_equal(buf[i], ob.fwd_ntt(orig[i], t)), i
+    hb.set_worksize_INTT(B)
+    hb.INTT_many(buf.ctypes.data, n, B, t.inv_roots, t.precon_inv, q, t.inv_n, t.inv_n_w, n)
+    assert hb.INTTCompleted()
+    assert np.array_equal(buf, orig)
+    # no set_worksize: every call of the bulk helper is synchronous, like a single call
+    hb.NTT_many(buf.ctypes.data, n, 3, t.roots, t.precon, q, n)
+    for i in range(3):
+        assert np.array_equal(buf[i], ob.fwd_ntt(orig[i], t)), i
+    assert np.array_equal(buf[3], orig[3])
+    # keyswitch and dyadic
+    p = KsProblem(4096, 3, 4, 9, 47, seed=11)
+    keys = hb.KeyArray(p.keys)
+    out = np.ascontiguousarray(p.result.copy())
+    tt = np.ascontiguousarray(p.t_target)
+    hb.set_worksize_KeySwitch(p.batch)
+    hb.KeySwitch_many(out.ctypes.data, tt.ctypes.data, p.batch, p.n, p.D, p.K, p.D + 1, 2, p.moduli, keys, p.msf)
+    assert hb.KeySwitchCompleted()
+    assert np.array_equal(out, p.expected())
+    nd, M, Bd = 4096, 2, 7
+    moduli = np.array(ob.primes(M, 50, nd), dtype=np.uint64)
+    op1 = np.stack([ob.splitmix(2 * M * nd, 30 + b, int(moduli[0])) for b in range(Bd)])
+    op2 = np.stack([ob.splitmix(2 * M * nd, 40 + b, int(moduli[0])) for b in range(Bd)])
+    res = np.zeros((Bd, 3 * M * nd), dtype=np.uint64)
+    hb.set_worksize_DyadicMultiply(Bd)
+    hb.DyadicMultiply_many(res.ctypes.data, op1.ctypes.data, op2.ctypes.data, Bd, nd, moduli, M)
+    assert hb.DyadicMultiplyCompleted()
+    assert np.array_equal(res.reshape(-1), ob.dyadic(op1.reshape(-1), op2.reshape(-1), nd, moduli, Bd))
+
+
 def test_pageable_keyswitch_and_dyadic(acquired):
     hb = acquired
     p = KsProblem(8192, 4, 5, 70, 48, seed=5)           # 70 items x 768 KiB > one 64 MiB slot

@@ -17,6 +17,9 @@ def gpu(a):
     return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
 
 
+for kv in os.environ.get("HB_OPTS", "").split(","):      # option=value[,option=value]: applied before anything runs
+    if kv:
+        hb.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 op = sys.argv[1] if len(sys.argv) > 1 else "ntt"
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 batch = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
