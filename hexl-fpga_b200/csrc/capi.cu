@@ -245,6 +245,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         hb::g_pdl = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "time_kernels")) {
+        hb::g_time_kernels = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "debug_skip_list")) {
         hb::g_debug_skip_list = value ? 1 : 0;
         return 0;
@@ -326,6 +330,13 @@ int hexl_b200_reset_stats(void) {
     g_launches = 0;
     g_h2d = 0;
     g_d2h = 0;
+    return 0;
+}
+
+int hexl_b200_kernel_times(float* ms, uint64_t cap, uint64_t* count) {
+    if (!count) return fail(HEXL_B200_EINVAL, "kernel_times: NULL count");
+    const cudaError_t e = hb::take_kernel_times(ms, cap, count);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel_times");
     return 0;
 }
 

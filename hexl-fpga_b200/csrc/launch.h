@@ -116,6 +116,9 @@ extern int g_ks_mac_items;
 extern int g_small_tma_store;
 extern int g_warp_tail;
 extern int g_pdl;
+extern int g_time_kernels;      // measurement only (option "time_kernels"): every plain-NTT kernel launch stands alone between two CUDA events
+void note_kernel_events(cudaEvent_t a, cudaEvent_t b, unsigned grid);
+cudaError_t take_kernel_times(float* ms, uint64_t cap, uint64_t* count);
 extern int g_debug_skip_list;   // measurement only (option "debug_skip_list"): out-of-contract items are NOT transformed
 size_t ks_scratch_words_per_item(const KsDev& ks);
 cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st);

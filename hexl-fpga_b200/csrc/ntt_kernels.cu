@@ -3,6 +3,7 @@
 // next polynomial (see ntt_block.cuh).  Replaces device/fwd_ntt.cpp:81-646 and
 // device/inv_ntt.cpp:82-607 of the reference.
 #include <mutex>
+#include <vector>
 
 #include "ntt_launch.cuh"
 
@@ -10,6 +11,38 @@ namespace hb {
 
 int g_pdl = 1;               // plain NTT kernels launched with programmatic stream serialization (option "pdl", ntt_launch.cuh)
 int g_debug_skip_list = 0;   // measurement only, see launch.h
+int g_time_kernels = 0;      // measurement only, see launch.h
+namespace {
+std::mutex g_kt_mu;
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    unsigned grid;
+};
+std::vector<TimedLaunch> g_kt;
+}  // namespace
+void note_kernel_events(cudaEvent_t a, cudaEvent_t b, unsigned grid) {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    g_kt.push_back({a, b, grid});
+}
+// durations (ms) of the launches timed since the last call, in launch order; the events are released
+cudaError_t take_kernel_times(float* ms, uint64_t cap, uint64_t* count) {
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    cudaError_t err = cudaSuccess;
+    uint64_t n = 0;
+    for (const TimedLaunch& t : g_kt) {
+        cudaError_t e = cudaEventSynchronize(t.b);
+        float v = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&v, t.a, t.b);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        if (n < cap && ms) ms[n] = v;
+        ++n;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    g_kt.clear();
+    *count = n;
+    return err;
+}
 int g_warp_tail = 1;         // FP64-pipe forward kernel with warp-dealt tail rows (one block barrier per transform instead of three), option "warp_tail"
 int g_small_tma_store = 0;   // small-modulus forward epilogue through TMA stores (option "small_tma_store"): measured 5% slower than the coalesced register stores (slice reuse waits on the store engine), off by default
 

@@ -127,6 +127,19 @@ struct WarpTailCfg<NttCfg<14, 5, 4, 0>> {
 template <class... KArgs, class... Args>
 static cudaError_t launch_dep(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
                               Args&&... args) {
+    if (g_time_kernels) {
+        // bench.py's roofline leg: the kernel's own duration, CUDA events on its stream directly around the launch
+        // (a stream marker between two kernels rules the programmatic overlap out, so the launch is a plain one)
+        cudaEvent_t a, b;
+        cudaError_t e;
+        if ((e = cudaEventCreate(&a)) || (e = cudaEventCreate(&b))) return e;
+        if ((e = cudaEventRecord(a, st))) return e;
+        kern<<<grid, block, smem, st>>>(KArgs(args)...);
+        if ((e = cudaGetLastError())) return e;
+        if ((e = cudaEventRecord(b, st))) return e;
+        note_kernel_events(a, b, grid);
+        return cudaSuccess;
+    }
     if (!g_pdl) {
         kern<<<grid, block, smem, st>>>(KArgs(args)...);
         return cudaGetLastError();

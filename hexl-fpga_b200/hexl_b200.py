@@ -66,6 +66,7 @@ _SIGNATURES = {
     "hexl_b200_host_keyswitch_many": ([vp, vp, u64, u64, u64, u64, u64, u64, vp, vp, vp, vp], C.c_int),
     "hexl_b200_get_stats": ([vp], C.c_int),
     "hexl_b200_host_device_stats": ([C.c_int, vp], C.c_int),
+    "hexl_b200_kernel_times": ([vp, u64, vp], C.c_int),
     "hexl_b200_host_pin_buffer": ([vp, u64], C.c_int),
     "hexl_b200_host_unpin_buffer": ([vp], C.c_int),
     "hexl_b200_reset_stats": ([], C.c_int),
@@ -135,6 +136,14 @@ def device_stats(worker):
     st = DeviceStats()
     _check(lib().hexl_b200_host_device_stats(worker, C.addressof(st)), "device_stats")
     return {"device": st.device, "batches": st.batches, "items": st.items}
+
+
+def kernel_times(cap=4096):
+    """durations (ms) of the kernel launches timed since the last call (option "time_kernels"), in launch order"""
+    ms = np.zeros(cap, dtype=np.float32)
+    cnt = u64()
+    _check(lib().hexl_b200_kernel_times(ms.ctypes.data, cap, C.byref(cnt)), "kernel_times")
+    return ms[:min(cap, cnt.value)].copy()
 
 
 def pin_buffer(arr):

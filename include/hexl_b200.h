@@ -154,9 +154,17 @@ int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, ui
  *                      serialization (launch latency overlaps the kernel in front); 0: plain launches
  *   "warp_tail"        1 (default): the FP64-pipe kernels at n = 16384 deal the tail rows out by warp
  *                      (one block barrier per transform instead of three); 0: by thread index
+ *   "time_kernels"     1: time every plain-NTT kernel launch with CUDA events (hexl_b200_kernel_times)
  *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16, default 10240; a batch is cut into equal chunks that fit)
  *   "ks_mac_items"     items sharing one key load in the keyswitch MAC (1, 4, 8) */
 int hexl_b200_set_option(const char* name, int64_t value);
+
+/* Measurement aid for bench.py's roofline leg.  With option "time_kernels" = 1 every kernel launched by
+ * hexl_b200_ntt_fwd / _inv / _poly_multiply stands alone between two CUDA events recorded on its stream
+ * (plain launches: no programmatic overlap with the kernel in front).  This call waits for the launches timed
+ * since the previous call and returns their durations in milliseconds, in launch order (at most `cap` of them
+ * are written; *count is how many there were). */
+int hexl_b200_kernel_times(float* ms, uint64_t cap, uint64_t* count);
 
 /* ------------------------------------------------------------------------- */
 /* (2) host-pointer API: the reference's public functions, C linkage.        */
