@@ -55,6 +55,9 @@ static std::atomic<int> g_fp64_path{1};
 // forward FP64 butterflies with a full correction every other stage for q <= 2^51 (1 + 1/32) (option "fp64_alt")
 static std::atomic<int> g_fp64_alt{1};
 
+// the polynomial after the current one is pulled towards L2 a transform ahead of its TMA load (option "l2_prefetch")
+static std::atomic<int> g_l2_prefetch{1};
+
 hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::TwPair* ftw,
                        const hb::TwPair* itw, int logn, const hb::Tw32* ftw32, const hb::Tw32* itw32) {
     hb::ModTab t;
@@ -76,6 +79,7 @@ hb::ModTab make_modtab(uint64_t q, uint64_t inv_n, uint64_t inv_n_w, const hb::T
     t.small_ok = (hb::small_modulus_ok(q) && (ftw32 || itw32)) ? (uint32_t)g_small_path.load() : 0u;
     t.inv_lazy_ok = (g_inv_lazy.load() && hb::inv_lazy_modulus_ok(q)) ? 1u : 0u;
     t.fd = hb::make_fp64mod(q, inv_n < q ? inv_n : 0, inv_n_w < q ? inv_n_w : 0);
+    t.l2_prefetch = (uint32_t)g_l2_prefetch.load();
     t.ftwd = nullptr;
     t.itwd = nullptr;
     t.fp64_ok = 0;          // set by the callers that build the FP64 tables
@@ -243,6 +247,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "pdl")) {
         hb::g_pdl = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "l2_prefetch")) {
+        g_l2_prefetch = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "time_kernels")) {

@@ -33,6 +33,7 @@ struct ModTab {
     uint32_t fp64_ok;       // 2^36 <= q <= 2^53 / 3 and the tables above are there
     uint32_t fp64_alt_ok;   // ... and q <= 2^51 (1 + 1/32): forward butterflies that correct every other stage
     uint32_t lazy_out;      // the caller wants the lazy words of the reference's output_mod_factor 4 / 2: exact kernels only
+    uint32_t l2_prefetch;   // pull the polynomial after the current one towards L2 while the current one is transformed (option "l2_prefetch")
 };
 
 // ---- load transforms (applied to each word as it enters the transform) ----
@@ -134,11 +135,21 @@ struct OfRows {
     uint64_t* dst;               // direct path: polynomial base in global memory
     const CUtensorMap* smap;     // staged path: store map (box 16 words x 32 rows, 128B swizzle)
     uint32_t row0;               //   first tensor-map row of the output polynomial
-    template <class C>
+    // PREPARED: prepare() has run since the warp's previous store (the wait for the staging slice then sits in front
+    // of the row's final conversion, and the converted words go straight into the 16-byte stores: with the wait
+    // between them the compiler gathered every store's four registers with moves, 64 per transform)
+    template <class C, bool PREPARED = false>
     HB_D void store(uint32_t row, const uint64_t* v) const;
+    template <class C>
+    HB_D void prepare() const;
     template <class C>
     HB_D void prefetch(uint32_t) const {}
 };
+// output functors that want a call in front of a row's final conversion
+template <class Of, class C, class = void>
+struct HasPrepare : std::false_type {};
+template <class Of, class C>
+struct HasPrepare<Of, C, std::void_t<decltype(std::declval<const Of&>().template prepare<C>())>> : std::true_type {};
 struct OfWords {  // inverse: one word at its natural index (coalesced along lo)
     uint64_t* dst;
     HB_D void word(uint32_t idx, uint64_t x) const { dst[idx] = x; }
@@ -189,6 +200,12 @@ HB_D void tma_load_rows(void* smem_dst, const CUtensorMap* map, uint64_t* bar, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(0), "r"(row)
         : "memory");
+}
+
+// the same box towards L2 only (no shared-memory destination, no barrier)
+HB_D void tma_prefetch_rows(const CUtensorMap* map, uint32_t row) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(0), "r"(row)
+                 : "memory");
 }
 
 // 2-D tensor TMA store of one staged box back to global memory (bulk async group)
@@ -402,6 +419,13 @@ HB_D void XfMulGlobal::post(uint32_t tid, uint64_t* v) const {
 }
 
 template <class C>
+HB_D void OfRows::prepare() const {
+    if constexpr (SmemPlan<C>::kStagedStore) {
+        if ((threadIdx.x & 31u) == 0) tma_store_wait_read();   // previous box of this slice has left
+        __syncwarp();
+    }
+}
+template <class C, bool PREPARED>
 HB_D void OfRows::store(uint32_t row, const uint64_t* v) const {
     if constexpr (SmemPlan<C>::kStagedStore) {
         // rows of a warp are consecutive: stage them in the warp's slice (same
@@ -409,8 +433,7 @@ HB_D void OfRows::store(uint32_t row, const uint64_t* v) const {
         // 4 KiB box to the TMA store engine
         const uint32_t lane = threadIdx.x & 31u;
         uint64_t* slice = smem_poly<C>() + C::N + (threadIdx.x >> 5) * 512;
-        if (lane == 0) tma_store_wait_read();   // previous box of this slice has left
-        __syncwarp();
+        if constexpr (!PREPARED) prepare<C>();
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
@@ -545,8 +568,8 @@ HB_D void tmem_touch16(uint32_t* r) {
 // load issued one butterfly stage ahead of its use.  Every load has its own destination registers (the arrays
 // are fully scalarised; at most two or three are alive at a time): re-using two buffers in turns made the
 // compiler copy twiddles out of the way of the next load, ~100 moves per transform.
-template <class C, class A, class F>
-HB_D void fwd_tail_compute_tmem(uint64_t* v, const A& a, const F& after_row) {
+template <class C, class A, class F, class G>
+HB_D void fwd_tail_compute_tmem(uint64_t* v, const A& a, const F& after_row, const G& before_final) {
     constexpr int ROWS = (int)TmemTail<C>::ROWS, S0 = C::HEAD;
     uint32_t r[ROWS][4][16];              // [row][slots 4g .. 4g+3]
     tmem_ld16_issue(a.ttail, r[0][0]);
@@ -589,6 +612,7 @@ HB_D void fwd_tail_compute_tmem(uint64_t* v, const A& a, const F& after_row) {
             a.template fwd_at<S0 + 3>(x[8 + blk * 2], x[8 + blk * 2 + 1], tmem_pair(r[ri][3], blk));
         });
         if constexpr (ri + 1 < ROWS) tmem_ld16_issue(ta + 64 + 16, r[ri + 1 < ROWS ? ri + 1 : ri][1]);   // next row, slots 4..7
+        before_final(ri);
         static_for<0, C::ROW>([&](auto kc) { x[decltype(kc)::value] = a.fwd_final(x[decltype(kc)::value]); });
         after_row(ri);
     });
@@ -686,7 +710,15 @@ HB_D bool ntt_fwd_cta(uint64_t* W, const ModTab& t, const A& a, const Xf& xf, co
     }
     // each row leaves as soon as it is final: its staged TMA store drains while the next row is computed
     if constexpr (A::kTmemTail)
-        fwd_tail_compute_tmem<C>(v, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); });
+    {
+        if constexpr (HasPrepare<Of, C>::value)
+            fwd_tail_compute_tmem<C>(
+                v, a, [&](int ri) { of.template store<C, true>(tail_row<C>(tid, ri), v + ri * 16); },
+                [&](int) { of.template prepare<C>(); });
+        else
+            fwd_tail_compute_tmem<C>(
+                v, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); }, [](int) {});
+    }
     else
         fwd_tail_compute<C>(tid, v, ftw, a, [&](int ri) { of.template store<C>(tail_row<C>(tid, ri), v + ri * 16); });
     return true;
@@ -888,6 +920,13 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
                 cur_tw = FWD ? t.ftwd : t.itwd;
                 __syncthreads();
             }
+        }
+        // The copy of the next polynomial into the buffer can only start when this one has left it (the tail of this
+        // transform); its lines are asked for now, a whole transform earlier, so that the copy finds them in L2.
+        if (tid == 0 && next < n_items && t.l2_prefetch) {
+            const uint32_t row0 = job.src_row(item_of(next));
+#pragma unroll
+            for (uint32_t b = 0; b < TmaGeom<C>::BOXES; ++b) tma_prefetch_rows(tmap, row0 + b * TmaGeom<C>::BOX_ROWS);
         }
         mbar_wait(bar, parity);
         parity ^= 1;
