@@ -691,6 +691,9 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         if (!h_tabs[i].fp64_alt_ok) p->dev.fp64_alt_ok = 0;
     p->dev.logn = (uint32_t)logn;
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
+    p->dev.fD = hb::make_fastdiv((uint32_t)D);
+    p->dev.fDm1 = hb::make_fastdiv((uint32_t)D - 1);
+    p->dev.fDD = hb::make_fastdiv((uint32_t)(D * D));
     p->dev.tabs = p->d_tabs; p->dev.divs = p->d_divs; p->dev.keys = p->d_keys;
     p->dev.msf = p->d_small; p->dev.msf_p = p->d_small + K;
     p->dev.msf_fp = p->dev.fp64_ok ? reinterpret_cast<const double*>(p->d_small + 2 * K) : nullptr;

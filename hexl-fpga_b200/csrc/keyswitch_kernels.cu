@@ -57,9 +57,13 @@ struct JobIntt1 {
     KsDev ks;
     uint64_t* U;
     uint32_t B = 0;          // items of the chunk (0: walk in storage order)
-    HB_D uint32_t order(uint32_t i) const { return B ? (i % B) * ks.D + i / B : i; }
+    HB_D uint32_t order(uint32_t i) const {
+        if (!B) return i;
+        const uint32_t m = fdiv(i, B, ks.fB);
+        return (i - m * B) * ks.D + m;
+    }
     HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
-    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item - fdiv(item, ks.fD) * ks.D]; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
     HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{U + (size_t)item * C::N}; }
 };
@@ -84,24 +88,24 @@ struct JobNtt1 {
         const uint32_t D = ks.D, lo = B * (D - 1);
         uint32_t b, y;
         if (i < D * lo) {
-            const uint32_t r = i / lo, rem = i % lo;
-            b = rem / (D - 1);
-            y = r * (D - 1) + rem % (D - 1);
+            const uint32_t r = fdiv(i, lo, ks.fBlo), rem = i - r * lo;
+            b = fdiv(rem, ks.fDm1);
+            y = r * (D - 1) + (rem - b * (D - 1));
         } else {
             const uint32_t rem = i - D * lo;
-            b = rem / D;
-            y = D * (D - 1) + rem % D;
+            b = fdiv(rem, ks.fD);
+            y = D * (D - 1) + (rem - b * D);
         }
         return b * D * D + y;
     }
     HB_D void decode(uint32_t item, uint32_t& b, uint32_t& r, uint32_t& j) const {
         const uint32_t D = ks.D, per = D * D;
         item += item0;
-        b = item / per;
-        const uint32_t y = item % per;
+        b = fdiv(item, ks.fDD);
+        const uint32_t y = item - b * per;
         if (y < D * (D - 1)) {
-            r = y / (D - 1);
-            const uint32_t jj = y % (D - 1);
+            r = fdiv(y, ks.fDm1);
+            const uint32_t jj = y - r * (D - 1);
             j = jj + (jj >= r ? 1 : 0);
         } else {
             r = D;
@@ -657,15 +661,19 @@ struct JobNtt2Fp {
     uint64_t* result;
     CUtensorMap rmap;        // result: [items * 2 * D polynomials], box 32 rows
     uint32_t B2 = 0;         // 2 * items of the chunk (0: walk in storage order)
-    HB_D uint32_t order(uint32_t i) const { return B2 ? (i % B2) * ks.D + i / B2 : i; }
-    HB_D uint32_t src_row(uint32_t item) const { return ((item / ks.D) * ks.R + ks.D) * (C::N / 16); }
-    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
+    HB_D uint32_t order(uint32_t i) const {
+        if (!B2) return i;
+        const uint32_t m = fdiv(i, B2, ks.fB2);
+        return (i - m * B2) * ks.D + m;
+    }
+    HB_D uint32_t src_row(uint32_t item) const { return ((fdiv(item, ks.fD)) * ks.R + ks.D) * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[(item - fdiv(item, ks.fD) * ks.D)]; }
     // item = bc * D + i:  ACC[bc][i], result[bc][i]
-    HB_D const uint64_t* acc_poly(uint32_t item) const { return ACC + ((size_t)(item / ks.D) * ks.R + item % ks.D) * C::N; }
+    HB_D const uint64_t* acc_poly(uint32_t item) const { return ACC + ((size_t)(fdiv(item, ks.fD)) * ks.R + (item - fdiv(item, ks.fD) * ks.D)) * C::N; }
     HB_D uint64_t* res_poly(uint32_t item) const { return result + (size_t)item * C::N; }
     HB_D uint32_t res_row(uint32_t item) const { return item * (C::N / 16); }
     HB_D XfKsConvertFp xf(uint32_t item) const {
-        const ModTab& t = ks.tabs[item % ks.D];
+        const ModTab& t = ks.tabs[(item - fdiv(item, ks.fD) * ks.D)];
         const uint64_t h = ks.tabs[ks.K - 1].q >> 1;
         const uint64_t hr = barrett_reduce64(h, t.q, t.mu);
         return XfKsConvertFp{fp_centred(hr ? t.q - hr : 0, t.q)};      // fix = -floor(qk / 2) mod q
@@ -686,15 +694,15 @@ struct JobNtt2 {
     KsDev ks;
     const uint64_t* ACC;
     uint64_t* result;
-    HB_D uint32_t src_row(uint32_t item) const { return ((item / ks.D) * ks.R + ks.D) * (C::N / 16); }
-    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item % ks.D]; }
+    HB_D uint32_t src_row(uint32_t item) const { return ((fdiv(item, ks.fD)) * ks.R + ks.D) * (C::N / 16); }
+    HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[(item - fdiv(item, ks.fD) * ks.D)]; }
     HB_D XfKsConvert xf(uint32_t item) const {
-        const ModTab& t = ks.tabs[item % ks.D];
+        const ModTab& t = ks.tabs[(item - fdiv(item, ks.fD) * ks.D)];
         const uint64_t qk = ks.tabs[ks.K - 1].q, h = qk >> 1;
         return XfKsConvert{t.q, t.mu, t.q - barrett_reduce64(h, t.q, t.mu), (qk < 2 * t.q) ? 1u : 0u};
     }
     HB_D OfKsFinal of(uint32_t item, const CUtensorMap*) const {
-        const uint32_t i = item % ks.D, bc = item / ks.D;
+        const uint32_t i = (item - fdiv(item, ks.fD) * ks.D), bc = fdiv(item, ks.fD);
         return OfKsFinal{ACC + ((size_t)bc * ks.R + i) * C::N, result + ((size_t)bc * ks.D + i) * C::N,
                          ks.tabs[i].q, ks.msf[i], ks.msf_p[i]};
     }
@@ -735,11 +743,15 @@ static cudaError_t run_persistent(K kern, int threads, size_t smem, const CUtens
 }
 
 template <class C>
-static cudaError_t ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
+static cudaError_t ks_chunk(const KsDev& ks_in, uint64_t* result, const uint64_t* t_target, uint64_t items,
                             uint64_t* scratch, cudaStream_t st, int* launches) {
     const size_t smem = ntt_smem_bytes<C>();
-    const uint64_t D = ks.D, R = ks.R;
+    const uint64_t D = ks_in.D, R = ks_in.R;
     const uint32_t B = (uint32_t)items;
+    KsDev ks = ks_in;            // + the prepared divisors of this chunk's index arithmetic
+    ks.fB = make_fastdiv(B);
+    ks.fBlo = make_fastdiv(B * (uint32_t)(D - 1));
+    ks.fB2 = make_fastdiv(2 * B);
     const bool fused = use_fused(ks);
     uint64_t* U = scratch;
     uint64_t* V = U + items * D * C::N;

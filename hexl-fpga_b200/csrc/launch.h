@@ -9,6 +9,32 @@
 
 namespace hb {
 
+// Division of a 32-bit index by an invariant divisor: x / d = hi64(x * m) with m = floor(2^64 / d) + 1, exact for
+// every 32-bit x (the error term x * (m - 2^64/d) / 2^64 stays below 1/d as long as x * d < 2^64).  The keyswitch
+// jobs decode (item, modulus, digit) from a running index several times per transform in every thread; the
+// compiler's division by a run-time value is ~25 instructions each (I2F / MUFU.RCP / F2I and two fix-up
+// branches), which added up to 5 % of stage S2's instruction stream.
+struct FastDiv {
+    uint32_t d = 0;
+    uint64_t m = 0;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    f.m = d >= 2 ? ~(uint64_t)0 / d + 1 : 0;
+    return f;
+}
+HB_HD uint32_t fdiv(uint32_t x, const FastDiv& f) {
+    if (f.d <= 1) return x;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__umul64hi((uint64_t)x, f.m);
+#else
+    return (uint32_t)(((unsigned __int128)x * f.m) >> 64);
+#endif
+}
+// x / d with the prepared divisor when it is the one asked for (jobs built for another chunk size fall back)
+HB_HD uint32_t fdiv(uint32_t x, uint32_t d, const FastDiv& f) { return f.d == d ? fdiv(x, f) : x / d; }
+
 // Shape of one keyswitch (reference host/inc/hexl-fpga.h:54-64 arguments) plus
 // the device-resident constants a plan owns.
 struct KsDev {
@@ -31,6 +57,9 @@ struct KsDev {
     // accumulate on the FP64 pipe (k_ks_mac_fp64); null unless fp64_alt_ok
     const TwPair* keys_fp;
     const double* msf_fp;   // [2K]: centred msf_i and its quotient by q_i (FP64 epilogue of stage S5), or null
+    // prepared divisors of the index arithmetic: D, D - 1, D * D (plan), and of the chunk in flight: its item
+    // count B, B * (D - 1) and 2 * B (set by ks_chunk)
+    FastDiv fD, fDm1, fDD, fB, fBlo, fB2;
 };
 
 bool ntt_shape_supported(uint32_t logn);
