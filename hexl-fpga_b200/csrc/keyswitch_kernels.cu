@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_co
 }
 
 // ---- S2 -------------------------------------------------------------------
-template <class C>
+// NR: every digit is already inside the forward contract under every target modulus (KsDev::s2_no_reduce, decided
+// per plan): the load transform is the identity at COMPILE time.  As a run-time flag the kernel carried both
+// versions of the 32-word load and every warp jumped over the unused one once per transform -- 2.7 % of the
+// stage's samples were instruction-cache misses behind that jump.
+template <class C, bool NR = false>
 struct JobNtt1 {
     static constexpr bool kOneModulus = false;
     static constexpr bool kModulusRuns = C::LOGN == 14;
@@ -123,19 +127,23 @@ struct JobNtt1 {
         return (b * ks.D + j) * (C::N / 16);
     }
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[idx_of(item)]; }
-    HB_D XfReduce xf(uint32_t item) const {
-        const ModTab& t = ks.tabs[idx_of(item)];
-        return XfReduce{t.q, t.mu, ks.s2_no_reduce};
+    HB_D auto xf(uint32_t item) const {
+        if constexpr (NR) {
+            return XfIdent();
+        } else {
+            const ModTab& t = ks.tabs[idx_of(item)];
+            return XfReduce{t.q, t.mu, ks.s2_no_reduce};
+        }
     }
     HB_D OfRows of(uint32_t item, const CUtensorMap* smap) const {
         item += item0;
         return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
     }
 };
-template <class C, int MODE, int FP64 = 0>
+template <class C, int MODE, int FP64 = 0, bool NR = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
-        const __grid_constant__ CUtensorMap smap, const JobNtt1<C> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, true, MODE, JobNtt1<C>, false, FP64>(&tmap, &smap, job, n_items, list);
+        const __grid_constant__ CUtensorMap smap, const JobNtt1<C, NR> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, true, MODE, JobNtt1<C, NR>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S3 -------------------------------------------------------------------
@@ -618,21 +626,26 @@ struct OfKsFinalFp {
         const uint32_t lane = threadIdx.x & 31u;
         uint64_t* slice = smem_poly<C>() + C::N + (threadIdx.x >> 5) * 512;
         const uint32_t base = (rw - lane) * 16;   // first word of the warp's 32 rows
-        const uint64_t* acc = job->acc_poly(item) + base + lane;
-        uint64_t* res = job->res_poly(item) + base + lane;
-        // all 32 global loads of the round are issued before anything waits on them
+        // 16-byte accesses: lane l owns the word pairs (2 l, 2 l + 1) + 64 i of the warp's 512 words -- half as many
+        // load / store instructions in flight as with one word per lane (the epilogue's loads stall on the
+        // load / store queue and on L2 latency), and a pair is one chunk of the swizzled staging slice
+        const uint64_t* acc = job->acc_poly(item) + base + 2 * lane;
+        uint64_t* res = job->res_poly(item) + base + 2 * lane;
+        // all 16 global loads of the round are issued before anything waits on them
         uint64_t a[16], r[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            a[i] = __ldg(acc + 32 * i);
-            r[i] = res[32 * i];
+        for (int i = 0; i < 8; ++i) {
+            const ulonglong2 ta = __ldg(reinterpret_cast<const ulonglong2*>(acc + 64 * i));
+            a[2 * i] = ta.x;
+            a[2 * i + 1] = ta.y;
+            ld2(res + 64 * i, r[2 * i], r[2 * i + 1]);
         }
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
         __syncwarp();
-        const uint32_t i = item % job->ks.D;
+        const uint32_t i = item - fdiv(item, job->ks.fD) * job->ks.D;
         const ModTab* t = job->ks.tabs + i;
         Fp64Mod m;                   // the fields the epilogue's arithmetic reads
         m.q = t->fd.q;
@@ -642,13 +655,16 @@ struct OfKsFinalFp {
         const uint64_t q = t->q;
         const double msf_c = job->ks.msf_fp[i], msf_q = job->ks.msf_fp[job->ks.K + i];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t w = lane + 32u * k;
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t w = 2u * lane + 64u * k;
             const uint32_t row = w >> 4, ch = (w >> 1) & 7u;
-            const double x = u2d(slice[row * 16 + ((ch ^ (row & 7u)) << 1) + (w & 1u)]);
-            const double d = fp_cred_full(fp_add(fp_from_int(a[k]), -x), m);
-            const uint64_t o = fp_canon_signed(fp_mulmod(d, msf_c, msf_q, m), m);
-            res[32 * k] = add_mod(r[k], o, q);
+            uint64_t x0, x1;
+            ld2(slice + row * 16 + ((ch ^ (row & 7u)) << 1), x0, x1);
+            const double d0 = fp_cred_full(fp_add(fp_from_int(a[2 * k]), -u2d(x0)), m);
+            const double d1 = fp_cred_full(fp_add(fp_from_int(a[2 * k + 1]), -u2d(x1)), m);
+            const uint64_t o0 = fp_canon_signed(fp_mulmod(d0, msf_c, msf_q, m), m);
+            const uint64_t o1 = fp_canon_signed(fp_mulmod(d1, msf_c, msf_q, m), m);
+            st2(res + 64 * k, add_mod(r[2 * k], o0, q), add_mod(r[2 * k + 1], o1, q));
         }
     }
 };
@@ -806,7 +822,11 @@ static cudaError_t ks_chunk(const KsDev& ks_in, uint64_t* result, const uint64_t
             return cudaSuccess;
         }
         if (mac_fp64) {
-            if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;
+            if (ks.s2_no_reduce) {
+                if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3, true>, C::NT, smemw, m_u, m_vs, JobNtt1<CW, true>{ks, V, 0, B}, items * D * D, list, st))) return e;
+            } else {
+                if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;
+            }
         } else if (ks.fp64_alt_ok && !std::is_same<CW, C>::value) {
             if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 2>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;
         } else {
