@@ -55,6 +55,8 @@ static std::atomic<int> g_fp64_path{1};
 // forward FP64 butterflies with a full correction every other stage for q <= 2^51 (1 + 1/32) (option "fp64_alt")
 static std::atomic<int> g_fp64_alt{1};
 
+// keyswitch stages that walk modulus-major: contiguous stretch of the order per CTA (option "ks_blocked", read at plan creation)
+static std::atomic<int> g_ks_blocked{1};
 // the polynomial after the current one is pulled towards L2 a transform ahead of its TMA load (option "l2_prefetch")
 static std::atomic<int> g_l2_prefetch{1};
 
@@ -247,6 +249,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "pdl")) {
         hb::g_pdl = value ? 1 : 0;
+        return 0;
+    }
+    if (!strcmp(name, "ks_blocked")) {
+        g_ks_blocked = value ? 1 : 0;
         return 0;
     }
     if (!strcmp(name, "l2_prefetch")) {
@@ -691,6 +697,7 @@ int hexl_b200_ks_plan_create(hexl_b200_ks_plan** out, uint64_t n, uint64_t D, ui
         if (!h_tabs[i].fp64_alt_ok) p->dev.fp64_alt_ok = 0;
     p->dev.logn = (uint32_t)logn;
     p->dev.D = (uint32_t)D; p->dev.K = (uint32_t)K; p->dev.R = (uint32_t)R;
+    p->dev.walk_blocked = (uint32_t)g_ks_blocked.load();
     p->dev.fD = hb::make_fastdiv((uint32_t)D);
     p->dev.fDm1 = hb::make_fastdiv((uint32_t)D - 1);
     p->dev.fDD = hb::make_fastdiv((uint32_t)(D * D));

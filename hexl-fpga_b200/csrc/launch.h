@@ -60,6 +60,7 @@ struct KsDev {
     // prepared divisors of the index arithmetic: D, D - 1, D * D (plan), and of the chunk in flight: its item
     // count B, B * (D - 1) and 2 * B (set by ks_chunk)
     FastDiv fD, fDm1, fDD, fB, fBlo, fB2;
+    uint32_t walk_blocked;  // modulus-major stages: every CTA takes one contiguous stretch of the order (option "ks_blocked")
 };
 
 bool ntt_shape_supported(uint32_t logn);

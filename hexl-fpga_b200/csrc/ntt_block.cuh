@@ -890,9 +890,23 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         }
         if constexpr (TMEM_TAIL) tail_tw_to_tmem<C>(tid, FWD ? tm.ftwd + C::fwd_off(C::NP) : tm.itwd, ttail);
     };
+    // How the grid walks over the items.  Strided (CTA c takes c, c + grid, ...) by default.  Jobs that walk
+    // modulus-major (Job::kModulusRuns: the keyswitch stages) give every CTA ONE contiguous stretch of the order
+    // instead: it then crosses a modulus boundary once or twice per launch, not once per modulus, and the 262 KiB
+    // of twiddles it keeps in shared / tensor memory are reloaded that rarely (same makespan: ceil(items / grid)).
+    bool blocked = false;
+    if constexpr (Job::kModulusRuns && MODE != kExactList) blocked = job.ks.walk_blocked != 0;
+    uint32_t i_first = blockIdx.x, i_end = n_items, i_step = gridDim.x;
+    if (blocked) {
+        const uint32_t per = (n_items + gridDim.x - 1) / gridDim.x;
+        i_first = blockIdx.x * per;
+        i_end = i_first + per < n_items ? i_first + per : n_items;
+        if (i_first > n_items) i_first = n_items;
+        i_step = 1;
+    }
     const TwPair* cur_tw = nullptr;      // whose twiddles are resident
     if constexpr (SMEM_HEAD) {
-        const ModTab& t0 = job.mod(blockIdx.x < n_items ? item_of(blockIdx.x) : 0);
+        const ModTab& t0 = job.mod(i_first < n_items ? item_of(i_first) : 0);
         load_twiddles(t0);
         cur_tw = FWD ? t0.ftwd : t0.itwd;
         __syncthreads();
@@ -902,16 +916,16 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         // volatile: the address (and with it every load of these twiddles) stays behind the barrier above
         asm volatile("mov.u32 %0, %1;" : "=r"(head_s) : "r"(smem_u32(W + SmemPlan<C>::TW_WORD)));
     }
-    uint32_t i = blockIdx.x;
-    if (tid == 0 && i < n_items) issue_poly_load<C>(W, tmap, bar, job.src_row(item_of(i)));
+    uint32_t i = i_first;
+    if (tid == 0 && i < i_end) issue_poly_load<C>(W, tmap, bar, job.src_row(item_of(i)));
     uint32_t parity = 0;
-    for (; i < n_items; i += gridDim.x) {
+    for (; i < i_end; i += i_step) {
         const uint32_t item = item_of(i);
-        const uint32_t next = i + gridDim.x;
+        const uint32_t next = i + i_step;
         Prefetch pf;
         pf.map = tmap;
-        pf.row = ((C::WARPTAIL ? (tid & 31u) == 0 : tid == 0) && next < n_items) ? job.src_row(item_of(next))
-                                                                                          : kNoPrefetch;
+        pf.row = ((C::WARPTAIL ? (tid & 31u) == 0 : tid == 0) && next < i_end) ? job.src_row(item_of(next))
+                                                                                        : kNoPrefetch;
         const ModTab& t = job.mod(item);
         if constexpr (SMEM_HEAD && Job::kModulusRuns) {
             if ((FWD ? t.ftwd : t.itwd) != cur_tw) {     // uniform: the next run of items, under another modulus
@@ -923,7 +937,7 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         }
         // The copy of the next polynomial into the buffer can only start when this one has left it (the tail of this
         // transform); its lines are asked for now, a whole transform earlier, so that the copy finds them in L2.
-        if (tid == 0 && next < n_items && t.l2_prefetch) {
+        if (tid == 0 && next < i_end && t.l2_prefetch) {
             const uint32_t row0 = job.src_row(item_of(next));
 #pragma unroll
             for (uint32_t b = 0; b < TmaGeom<C>::BOXES; ++b) tma_prefetch_rows(tmap, row0 + b * TmaGeom<C>::BOX_ROWS);

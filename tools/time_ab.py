@@ -26,7 +26,7 @@ def time_ntt(reps=20):
     f = [a.elapsed_time(b) for a, b, c in evs]; i = [b.elapsed_time(c) for a, b, c in evs]
     return float(np.mean(f)) * 1e3, float(np.mean(i)) * 1e3
 kp = KsProblem(N, 7, 8, 1, 51)
-KB = 1024
+KB = int(os.environ.get('KB', '1024'))
 tt = gpu(kp.t_target).repeat(KB, 1).contiguous()
 r2 = gpu(kp.result).repeat(KB, 1).contiguous()
 def time_ks():
