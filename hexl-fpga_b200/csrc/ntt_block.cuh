@@ -904,6 +904,8 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         if (i_first > n_items) i_first = n_items;
         i_step = 1;
     }
+    // the first polynomial is on its way while the twiddles are brought in
+    if (tid == 0 && i_first < i_end) issue_poly_load<C>(W, tmap, bar, job.src_row(item_of(i_first)));
     const TwPair* cur_tw = nullptr;      // whose twiddles are resident
     if constexpr (SMEM_HEAD) {
         const ModTab& t0 = job.mod(i_first < n_items ? item_of(i_first) : 0);
@@ -917,7 +919,6 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
         asm volatile("mov.u32 %0, %1;" : "=r"(head_s) : "r"(smem_u32(W + SmemPlan<C>::TW_WORD)));
     }
     uint32_t i = i_first;
-    if (tid == 0 && i < i_end) issue_poly_load<C>(W, tmap, bar, job.src_row(item_of(i)));
     uint32_t parity = 0;
     for (; i < i_end; i += i_step) {
         const uint32_t item = item_of(i);
