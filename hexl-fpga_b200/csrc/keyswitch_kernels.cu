@@ -631,20 +631,23 @@ struct OfKsFinalFp {
         // load / store queue and on L2 latency), and a pair is one chunk of the swizzled staging slice
         const uint64_t* acc = job->acc_poly(item) + base + 2 * lane;
         uint64_t* res = job->res_poly(item) + base + 2 * lane;
-        // all 16 global loads of the round are issued before anything waits on them
+        // The sums are asked for first; the caller's words only once the row has left its registers for the slice
+        // (they then take those registers: no spills), and they are not needed before every product of the round is
+        // done -- their latency hides behind the arithmetic instead of in front of it.
         uint64_t a[16], r[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const ulonglong2 ta = __ldg(reinterpret_cast<const ulonglong2*>(acc + 64 * i));
             a[2 * i] = ta.x;
             a[2 * i + 1] = ta.y;
-            ld2(res + 64 * i, r[2 * i], r[2 * i + 1]);
         }
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             st2(slice + lane * 16 + (((uint32_t)c ^ (lane & 7u)) << 1), v[2 * c], v[2 * c + 1]);
         __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ld2(res + 64 * i, r[2 * i], r[2 * i + 1]);
         const uint32_t i = item - fdiv(item, job->ks.fD) * job->ks.D;
         const ModTab* t = job->ks.tabs + i;
         Fp64Mod m;                   // the fields the epilogue's arithmetic reads
@@ -662,10 +665,12 @@ struct OfKsFinalFp {
             ld2(slice + row * 16 + ((ch ^ (row & 7u)) << 1), x0, x1);
             const double d0 = fp_cred_full(fp_add(fp_from_int(a[2 * k]), -u2d(x0)), m);
             const double d1 = fp_cred_full(fp_add(fp_from_int(a[2 * k + 1]), -u2d(x1)), m);
-            const uint64_t o0 = fp_canon_signed(fp_mulmod(d0, msf_c, msf_q, m), m);
-            const uint64_t o1 = fp_canon_signed(fp_mulmod(d1, msf_c, msf_q, m), m);
-            st2(res + 64 * k, add_mod(r[2 * k], o0, q), add_mod(r[2 * k + 1], o1, q));
+            a[2 * k] = fp_canon_signed(fp_mulmod(d0, msf_c, msf_q, m), m);
+            a[2 * k + 1] = fp_canon_signed(fp_mulmod(d1, msf_c, msf_q, m), m);
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            st2(res + 64 * k, add_mod(r[2 * k], a[2 * k], q), add_mod(r[2 * k + 1], a[2 * k + 1], q));
     }
 };
 template <class C>
