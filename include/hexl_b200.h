@@ -154,6 +154,10 @@ int hexl_b200_compute_twiddles(uint64_t n, uint64_t modulus, uint64_t* out4n, ui
  *                      serialization (launch latency overlaps the kernel in front); 0: plain launches
  *   "warp_tail"        1 (default): the FP64-pipe kernels at n = 16384 deal the tail rows out by warp
  *                      (one block barrier per transform instead of three); 0: by thread index
+ *   "l2_prefetch"      1 (default): a transform CTA pulls the polynomial after the current one towards L2 a whole
+ *                      transform ahead of its TMA load (read per call / at keyswitch plan creation)
+ *   "ks_blocked"       1 (default): keyswitch stages that walk their items modulus-major give every CTA one
+ *                      contiguous stretch of the order (read at plan creation); 0: strided
  *   "time_kernels"     1: time every plain-NTT kernel launch with CUDA events (hexl_b200_kernel_times)
  *   "ks_workspace_mb"  keyswitch scratch bound in MiB (>= 16, default 10240; a batch is cut into equal chunks that fit)
  *   "ks_mac_items"     items sharing one key load in the keyswitch MAC (1, 4, 8) */
