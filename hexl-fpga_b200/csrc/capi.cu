@@ -251,6 +251,10 @@ int hexl_b200_set_option(const char* name, int64_t value) {
         hb::g_pdl = value ? 1 : 0;
         return 0;
     }
+    if (!strcmp(name, "ks_u_fp64")) {
+        hb::g_ks_u_fp64 = value ? 1 : 0;
+        return 0;
+    }
     if (!strcmp(name, "ks_blocked")) {
         g_ks_blocked = value ? 1 : 0;
         return 0;

@@ -41,6 +41,9 @@ int g_ks_mac_fp64 = 1;
 // written through the warp's staging slice by TMA (option "ks_s5_fp64", default on; same conditions as
 // ks_mac_fp64 plus all moduli within 25 % of each other)
 int g_ks_s5_fp64 = 1;
+// S1 hands U over as non-negative doubles when S2 takes them as they are (the default FP64 path with same-size
+// moduli): option "ks_u_fp64", default on
+int g_ks_u_fp64 = 1;
 int g_ks_mac_items = 4;   // MAC stage: 4 (default) or 8 items per key load; 1 = register-resident keys, 2 = 128-bit accumulators (both slower: latency bound)
 
 HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
@@ -48,7 +51,9 @@ HB_HD uint32_t ks_y(uint32_t D, uint32_t r, uint32_t j) {
 }
 
 // ---- S1 -------------------------------------------------------------------
-template <class C>
+// DCONV: the kernel produces canonical integers but U is to hold doubles (the exact pass behind an S1 that hands
+// over doubles)
+template <class C, bool DCONV = false>
 struct JobIntt1 {
     static constexpr bool kOneModulus = false;
     // N = 16384, FP64 kernels: the grid walks over the polynomials modulus-major, so that a CTA keeps one modulus
@@ -65,12 +70,15 @@ struct JobIntt1 {
     HB_D uint32_t src_row(uint32_t item) const { return item * (C::N / 16); }
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[item - fdiv(item, ks.fD) * ks.D]; }
     HB_D XfIdent xf(uint32_t) const { return XfIdent(); }
-    HB_D OfWords of(uint32_t item, const CUtensorMap*) const { return OfWords{U + (size_t)item * C::N}; }
+    HB_D auto of(uint32_t item, const CUtensorMap*) const {
+        if constexpr (DCONV) return OfWordsD{U + (size_t)item * C::N};
+        else return OfWords{U + (size_t)item * C::N};
+    }
 };
-template <class C, int MODE, int FP64 = 0>
+template <class C, int MODE, int FP64 = 0, bool DCONV = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_constant__ CUtensorMap tmap,
-        const __grid_constant__ CUtensorMap smap, const JobIntt1<C> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, false, MODE, JobIntt1<C>, false, FP64>(&tmap, &smap, job, n_items, list);
+        const __grid_constant__ CUtensorMap smap, const JobIntt1<C, DCONV> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, false, MODE, JobIntt1<C, DCONV>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S2 -------------------------------------------------------------------
@@ -78,7 +86,8 @@ __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_intt1(const __grid_co
 // per plan): the load transform is the identity at COMPILE time.  As a run-time flag the kernel carried both
 // versions of the 32-word load and every warp jumped over the unused one once per transform -- 2.7 % of the
 // stage's samples were instruction-cache misses behind that jump.
-template <class C, bool NR = false>
+// UFP (with NR): U holds doubles (S1 with FP64 = 4), no entry conversion either.
+template <class C, bool NR = false, bool UFP = false>
 struct JobNtt1 {
     static constexpr bool kOneModulus = false;
     static constexpr bool kModulusRuns = C::LOGN == 14;
@@ -128,7 +137,9 @@ struct JobNtt1 {
     }
     HB_D const ModTab& mod(uint32_t item) const { return ks.tabs[idx_of(item)]; }
     HB_D auto xf(uint32_t item) const {
-        if constexpr (NR) {
+        if constexpr (NR && UFP) {
+            return XfIdentFp();
+        } else if constexpr (NR) {
             return XfIdent();
         } else {
             const ModTab& t = ks.tabs[idx_of(item)];
@@ -140,10 +151,10 @@ struct JobNtt1 {
         return OfRows{V + (size_t)item * C::N, smap, item * (C::N / 16)};
     }
 };
-template <class C, int MODE, int FP64 = 0, bool NR = false>
+template <class C, int MODE, int FP64 = 0, bool NR = false, bool UFP = false>
 __global__ void __launch_bounds__(C::NT, C::MIN_CTAS) k_ks_ntt1(const __grid_constant__ CUtensorMap tmap,
-        const __grid_constant__ CUtensorMap smap, const JobNtt1<C, NR> job, uint32_t n_items, uint32_t* list) {
-    ntt_persistent<C, true, MODE, JobNtt1<C, NR>, false, FP64>(&tmap, &smap, job, n_items, list);
+        const __grid_constant__ CUtensorMap smap, const JobNtt1<C, NR, UFP> job, uint32_t n_items, uint32_t* list) {
+    ntt_persistent<C, true, MODE, JobNtt1<C, NR, UFP>, false, FP64>(&tmap, &smap, job, n_items, list);
 }
 
 // ---- S3 -------------------------------------------------------------------
@@ -805,8 +816,15 @@ static cudaError_t ks_chunk(const KsDev& ks_in, uint64_t* result, const uint64_t
     if (ks.fast_ok && ks.fp64_ok) {
         // same stages with the butterflies on the FP64 pipe: every load transform hands over words in [0, 1.25q)
         if ((e = cudaMemsetAsync(list, 0, 8, st))) return e;
-        if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
-        if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        // U as doubles when its only reader is the S2 kernel that takes them as they are (option "ks_u_fp64")
+        const bool u_fp = mac_fp64 && ks.s2_no_reduce && g_ks_u_fp64;
+        if (u_fp) {
+            if ((e = run_persistent(k_ks_intt1<CW, kFastVote, 4>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_intt1<C, kExactList, 0, true>, C::NT, smem, m_t, m_t, JobIntt1<C, true>{ks, U}, items * D, list, st))) return e;
+        } else {
+            if ((e = run_persistent(k_ks_intt1<CW, kFastVote, true>, C::NT, smemw, m_t, m_t, JobIntt1<CW>{ks, U, B}, items * D, list, st))) return e;
+            if ((e = run_persistent(k_ks_intt1<C, kExactList>, C::NT, smem, m_t, m_t, JobIntt1<C>{ks, U}, items * D, list, st))) return e;
+        }
         nl += 2;
         if (g_ks_sub_items > 0 && ks.keys_sh && (uint64_t)g_ks_sub_items < items) {
             // S2 + S3 in rounds of a few items: V is written and read back while it is still in L2
@@ -827,7 +845,9 @@ static cudaError_t ks_chunk(const KsDev& ks_in, uint64_t* result, const uint64_t
             return cudaSuccess;
         }
         if (mac_fp64) {
-            if (ks.s2_no_reduce) {
+            if (u_fp) {
+                if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3, true, true>, C::NT, smemw, m_u, m_vs, JobNtt1<CW, true, true>{ks, V, 0, B}, items * D * D, list, st))) return e;
+            } else if (ks.s2_no_reduce) {
                 if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3, true>, C::NT, smemw, m_u, m_vs, JobNtt1<CW, true>{ks, V, 0, B}, items * D * D, list, st))) return e;
             } else {
                 if ((e = run_persistent(k_ks_ntt1<CW, kFastTrust, 3>, C::NT, smemw, m_u, m_vs, JobNtt1<CW>{ks, V, 0, B}, items * D * D, list, st))) return e;

@@ -155,6 +155,7 @@ cudaError_t launch_ks_prepare_keys(const KsDev& ks, TwPair* out, cudaStream_t st
 cudaError_t launch_ks_prepare_keys_fp64(const KsDev& ks, TwPair* out, cudaStream_t st);
 extern int g_ks_mac_fp64;
 extern int g_ks_s5_fp64;
+extern int g_ks_u_fp64;
 cudaError_t launch_ks_chunk(const KsDev& ks, uint64_t* result, const uint64_t* t_target, uint64_t items,
                             uint64_t* scratch, cudaStream_t st, int* launches);
 

@@ -534,6 +534,26 @@ HB_HD void inv_last_bfly_fp64(uint64_t& X, uint64_t& Y, const Fp64Mod& m) {
     Y = fp_canon_signed(fp_mulmod(u, m.inv_n_w, m.inv_n_w_q, m), m);
 }
 
+// The same stage for a consumer on the FP64 pipe (keyswitch S1 -> S2): the results stay doubles, as the non-negative
+// representative v + (v < 0 ? q : 0) in [0, q) that the reference's base conversion starts from -- no integer
+// canonicalisation here, no integer-to-double conversion in each of the transforms that read the word.
+HB_HD double fp_nonneg(double v, const Fp64Mod& m) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "d"(v));
+    (void)lo;
+#else
+    const uint32_t hi = (uint32_t)(d2u(v) >> 32);
+#endif
+    return fp_add(v, hi > 0x80000000u ? m.q : 0.0);     // -0.0 counts as zero and comes out as +0.0
+}
+HB_HD void inv_last_bfly_fp64_d(uint64_t& X, uint64_t& Y, const Fp64Mod& m) {
+    const double x = u2d(X), y = u2d(Y);
+    const double s = fp_add(x, y), u = fp_add(x, -y);
+    X = d2u(fp_nonneg(fp_mulmod(s, m.inv_n, m.inv_n_q, m), m));
+    Y = d2u(fp_nonneg(fp_mulmod(u, m.inv_n_w, m.inv_n_w_q, m), m));
+}
+
 // x mod q for any x < 2^64 with mu = floor(2^64/q)   (q < 2^63).
 // device/keyswitch/intt1_redu.hpp:36-38 computes the same canonical value.
 HB_HD uint64_t barrett_reduce64(uint64_t x, uint64_t q, uint64_t mu) {

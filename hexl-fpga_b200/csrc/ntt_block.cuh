@@ -42,6 +42,13 @@ struct XfIdent {
     static constexpr bool kFp64Out = false;   // the words come out as integers (XfKsConvertFp: as doubles)
     HB_D uint64_t operator()(uint64_t x) const { return x; }
 };
+// the words in the buffer are doubles already, inside the forward contract (keyswitch S2 behind an S1 that hands
+// over doubles): no entry conversion
+struct XfIdentFp {
+    static constexpr bool kPost = false;
+    static constexpr bool kFp64Out = true;
+    HB_D uint64_t operator()(uint64_t x) const { return x; }
+};
 // base conversion of a coefficient-form word to this modulus
 // (device/keyswitch/intt1_redu.hpp:36-38)
 struct XfReduce {
@@ -153,6 +160,10 @@ struct HasPrepare<Of, C, std::void_t<decltype(std::declval<const Of&>().template
 struct OfWords {  // inverse: one word at its natural index (coalesced along lo)
     uint64_t* dst;
     HB_D void word(uint32_t idx, uint64_t x) const { dst[idx] = x; }
+};
+struct OfWordsD {  // the same for a kernel that produces canonical integers where the consumer expects doubles
+    uint64_t* dst;
+    HB_D void word(uint32_t idx, uint64_t x) const { dst[idx] = d2u(fp_from_int(x)); }
 };
 // inverse output with the keyswitch rounding v = (x + floor(qk/2)) mod qk
 // (device/keyswitch/intt2_redu.hpp:24-25,43) applied once per special-prime word
@@ -958,6 +969,12 @@ HB_D void ntt_persistent(const CUtensorMap* tmap, const CUtensorMap* smap, const
             a.head_s = head_s;
             a.ttail = ttail;
             done = ntt_fwd_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
+        } else if constexpr (TMEM_TAIL && !FWD && FP64 == 4) {
+            Fp64ArithSTD a;      // doubles out
+            a.m = t.fd;
+            a.head_s = head_s;
+            a.ttail = ttail;
+            done = ntt_inv_cta<C, MODE, !FOLD>(W, t, a, job.xf(item), job.of(item, smap), pf);
         } else if constexpr (TMEM_TAIL) {
             Fp64ArithST a;
             a.m = t.fd;

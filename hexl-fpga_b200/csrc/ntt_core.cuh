@@ -347,6 +347,10 @@ struct Fp64AltArithST : Fp64AltArithS {
     static constexpr bool kTmemTail = true;
     uint32_t ttail;
 };
+// inverse transform whose last stage hands over non-negative doubles in [0, q) (modarith.cuh, inv_last_bfly_fp64_d)
+struct Fp64ArithSTD : Fp64ArithST {
+    template <int E> HB_HD void inv_last_at(uint64_t& X, uint64_t& Y) const { inv_last_bfly_fp64_d(X, Y, m); }
+};
 struct Fp64ArithRawST : Fp64AltArithST {     // raw doubles out (cf. Fp64ArithRaw)
     HB_HD uint64_t fwd_final(uint64_t x) const { return x; }
 };
