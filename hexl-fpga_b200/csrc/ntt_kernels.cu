@@ -52,6 +52,10 @@ __global__ void k_pack_twiddles(const uint64_t* __restrict__ roots, const uint64
                                 TwPair* __restrict__ fwd_out, const uint64_t* __restrict__ inv_roots,
                                 const uint64_t* __restrict__ precon_inv, TwPair* __restrict__ inv_out,
                                 uint32_t* __restrict__ zero_count, const PackExtra x) {
+    // launched with programmatic stream serialization itself (pack_one): this grid may be scheduled while the
+    // kernel in front of it (the previous call's deferred-list pass) still runs, and waits here until that one has
+    // finished -- it overwrites tables the kernels in front read
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // the transform kernel behind us may be scheduled now; it waits for this grid before it reads anything
     asm volatile("griddepcontrol.launch_dependents;");
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,9 +221,8 @@ static cudaError_t pack_one(const uint64_t* roots, const uint64_t* precon, TwPai
         const int t32 = C32::FWD_ENTRIES > C32::INV_ENTRIES ? C32::FWD_ENTRIES : C32::INV_ENTRIES;
         total = t32 > total ? t32 : total;
     }
-    k_pack_twiddles<C><<<(total + 255) / 256, 256, 0, st>>>(roots, precon, fwd_out, inv_roots, precon_inv, inv_out,
-                                                            zero_count, x);
-    return cudaGetLastError();
+    return launch_dep(k_pack_twiddles<C>, (unsigned)((total + 255) / 256), 256u, (size_t)0, st, roots, precon, fwd_out,
+                      inv_roots, precon_inv, inv_out, zero_count, x);
 }
 
 cudaError_t launch_pack_twiddles(uint32_t logn, int variant, const uint64_t* roots, const uint64_t* precon,
