@@ -84,7 +84,7 @@ def test_fused_kernel_and_l2_rounds(hb, n, D, K, batch, opt, val):
     assert np.array_equal(got, p.expected())
 
 
-@pytest.mark.parametrize("option", ["ks_mac_fp64", "ks_s5_fp64"])
+@pytest.mark.parametrize("option", ["ks_mac_fp64", "ks_s5_fp64", "ks_u_fp64"])
 @pytest.mark.parametrize("n,D,K,batch", [(16384, 7, 8, 5), (16384, 6, 7, 3), (16384, 2, 8, 4), (16384, 1, 2, 3)])
 def test_integer_stages_match_the_fp64_ones(hb, n, D, K, batch, option):
     """ks_mac_fp64 = 1 (default at N = 16384 with moduli up to 2^51 (1 + 1/32)): stage S2 leaves raw doubles in V
@@ -93,7 +93,9 @@ def test_integer_stages_match_the_fp64_ones(hb, n, D, K, batch, option):
     under its own modulus reaches the multiply-accumulate straight from the caller's buffer.
     ks_s5_fp64 = 1 (default under the same conditions): stage S5's base conversion and modswitch / accumulate
     epilogue on the FP64 pipe, `result` through TMA; 0: the integer epilogue.  Same bits, also for `result` words
-    outside [0, q) (the reference's wrap-around add_mod decides those)."""
+    outside [0, q) (the reference's wrap-around add_mod decides those).
+    ks_u_fp64 = 1 (default with ks_mac_fp64 and same-size moduli): stage S1 hands U over as non-negative doubles
+    (the exact pass behind it converts) and S2 takes them without an entry conversion; 0: canonical integers."""
     p = KsProblem(n, D, K, batch, 51, seed=77)
     t = p.t_target.reshape(batch, D, n).copy()
     t[0, 0, 3] = np.uint64((1 << 63) + 12345)          # garbage: every kernel family must agree on it
